@@ -1,0 +1,83 @@
+/* mgf.h -- C ABI of libmgf_sm100a.so: B200 (sm_100a) kernels for the GANformer synthesis + latent-projection
+ * hot path.  Plain pointers and sizes only; the caller owns every buffer (device memory unless stated),
+ * sets the current device, and passes the CUDA stream to launch on.  No function allocates or frees
+ * device memory, synchronises the host, or keeps a pointer after it returns, so every call can be
+ * captured in a CUDA graph.
+ *
+ * Return value: 0 = ok, negative = bad argument (MGF_E_*), positive = cudaError_t.  The text of the last
+ * error on the calling thread is returned by mgf_last_error().  There is no CPU fallback anywhere.
+ *
+ * Each entry point cites the reference interface (file:line under the MorphGANformer tree) it replaces.
+ */
+#ifndef MGF_H_
+#define MGF_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGF_E_BADARG  (-1)
+#define MGF_E_DTYPE   (-2)
+#define MGF_E_SHAPE   (-3)
+#define MGF_E_ALIGN   (-4)
+#define MGF_E_UNSUP   (-5)
+#define MGF_E_DRIVER  (-6)
+
+/* dtype codes */
+#define MGF_F32  0
+#define MGF_BF16 1
+#define MGF_F16  2
+#define MGF_F64  3
+
+const char* mgf_last_error(void);
+int mgf_version(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches claim) */
+int64_t mgf_launch_count(void);
+
+/* ---- bias_act ---------------------------------------------------------------------------------------
+ * Replaces bias_act_plugin.bias_act (torch_utils/ops/bias_act.cpp:24-82, kernel bias_act.cu:15-139).
+ * y = clamp(act(x + b[(i / stepB) % sizeB]) * gain) for grad=0; first/second derivative forms for
+ * grad=1/2 exactly as the reference kernel defines them (x = incoming gradient, xref/yref = saved
+ * input/output, dy = saved gradient for grad=2).  Null pointer = absent tensor.  act = 1..9
+ * (linear, relu, lrelu, tanh, sigmoid, elu, selu, softplus, swish), bias_act.py:15-25.  clamp<0 = off. */
+int mgf_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                 int dtype, int grad, int act, float alpha, float gain, float clamp,
+                 int64_t sizeX, int64_t sizeB, int64_t stepB, void* stream);
+
+/* ---- upfirdn2d --------------------------------------------------------------------------------------
+ * Replaces upfirdn2d_plugin.upfirdn2d (torch_utils/ops/upfirdn2d.cpp:8-86, kernels upfirdn2d.cu:21-192):
+ * zero-insert upsample (up), pad/crop (pad0 = padx0,pady0; the far-side padding is implied by outSize),
+ * 2-D FIR with f (fp32, [fH,fW] with element strides fStride; flipped unless flip!=0), decimate (down),
+ * times gain.  Sizes/strides are in elements, order {W,H,C,N} like upfirdn2d.h:6-32. */
+int mgf_upfirdn2d(const void* x, const float* f, void* y, int dtype,
+                  const int64_t inSize[4], const int64_t inStride[4],
+                  const int32_t fSize[2], const int64_t fStride[2],
+                  const int64_t outSize[4], const int64_t outStride[4],
+                  const int32_t up[2], const int32_t down[2], const int32_t pad0[2],
+                  int flip, float gain, void* stream);
+
+/* ---- exact-fp32 direct convolution (the conv2d_gradfix surface) -----------------------------------
+ * Replaces the ATen/cuDNN calls behind conv2d_gradfix.conv2d / conv_transpose2d
+ * (torch_utils/ops/conv2d_gradfix.py:27-35) and their gradients (:96-157).  NCHW contiguous fp32,
+ * weight [OC, IC/groups, KH, KW] contiguous; fp32 FFMA accumulation (no TF32), used for the 1e-4 parity path.
+ *   fwd   : y[N,OC,HO,WO]   = conv(x[N,IC,H,W], w)
+ *   dgrad : dx[N,IC,H,W]    = conv_transpose(dy[N,OC,HO,WO], w)      (also conv_transpose2d forward)
+ *   wgrad : dw[OC,IC/g,KH,KW] = sum_n,oy,ox dy * x                   (dw must be zeroed by the caller; split-K atomics) */
+typedef struct {
+  int32_t N, IC, H, W, OC, HO, WO, KH, KW;
+  int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups;
+} mgf_conv_shape;
+int mgf_conv2d_fwd_f32(const float* x, const float* w, const float* bias, float* y, const mgf_conv_shape* s, void* stream);
+int mgf_conv2d_dgrad_f32(const float* dy, const float* w, float* dx, const mgf_conv_shape* s, void* stream);
+int mgf_conv2d_wgrad_f32(const float* dy, const float* x, float* dw, const mgf_conv_shape* s, void* stream);
+
+/* ---- small elementwise helpers used by the Python host mirror -------------------------------------
+ * fma: out = a*b + c with b broadcast per (n,c) and c broadcast per (h,w) or full (fma.py:7-17 as used by
+ * networks.py:322).  bmode: 0 = b full, 1 = b is [N,C,1,1]; cmode: 0 = none, 1 = c full, 2 = c is [H,W] plane. */
+int mgf_fma(const void* a, const void* b, const void* c, void* out, int dtype,
+            int64_t N, int64_t C, int64_t HW, int bmode, int cmode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGF_H_ */

@@ -1,0 +1,90 @@
+"""ctypes binding of the C ABI in include/mgf.h.  Loads the in-tree libmgf_sm100a.so and fails loudly if it is
+missing -- there is no Python/CPU fallback for any op."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmgf_sm100a.so")
+
+c_void_p, c_int, c_float, c_int64, c_int32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64, ctypes.c_int32
+
+F32, BF16, F16, F64 = 0, 1, 2, 3
+
+
+class ConvShape(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("N", "IC", "H", "W", "OC", "HO", "WO", "KH", "KW", "stride_h", "stride_w",
+                                       "pad_h", "pad_w", "dil_h", "dil_w", "groups")]
+
+
+# name -> (restype, argtypes); the single list the "exports every symbol" test checks against include/mgf.h
+SIGNATURES = {
+    "mgf_last_error": (ctypes.c_char_p, []),
+    "mgf_version": (c_int, []),
+    "mgf_launch_count": (c_int64, []),
+    "mgf_bias_act": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_float, c_float, c_int64, c_int64, c_int64, c_void_p]),
+    "mgf_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "mgf_conv2d_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_void_p]),
+    "mgf_conv2d_dgrad_f32": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_void_p]),
+    "mgf_conv2d_wgrad_f32": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_void_p]),
+    "mgf_fma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "morphganformer_b200: CUDA library %s is missing. Build it with `python -m morphganformer_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class MgfError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().mgf_last_error()
+        raise MgfError("%s failed (status %d): %s" % (what or "mgf call", rc, msg.decode() if msg else ""))
+
+
+def dtype_code(dt):
+    import torch
+    try:
+        return {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.float64: F64}[dt]
+    except KeyError:
+        raise MgfError("unsupported dtype %s" % dt)
+
+
+def stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def require_cuda(t, who):
+    if t.device.type != "cuda":
+        raise MgfError("%s: tensor is on %s; this build has CUDA kernels only (no CPU fallback). "
+                       "Tests compare against oracle/ on the CPU." % (who, t.device))
+
+
+def i64x(*v):
+    return (c_int64 * len(v))(*v)
+
+
+def i32x(*v):
+    return (c_int32 * len(v))(*v)

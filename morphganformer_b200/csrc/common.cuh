@@ -1,0 +1,70 @@
+// common.cuh -- shared helpers for libmgf_sm100a.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/mgf.h"
+
+namespace mgf {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define MGF_FAIL(code, ...) do { ::mgf::set_error(__VA_ARGS__); return (code); } while (0)
+#define MGF_CHECK_LAUNCH(name) do { cudaError_t e_ = cudaGetLastError(); \
+    if (e_ != cudaSuccess) { ::mgf::set_error("%s: launch failed: %s", name, cudaGetErrorString(e_)); return (int)e_; } \
+    ::mgf::count_launch(); } while (0)
+
+static inline int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
+template <class T> struct Cvt;
+template <> struct Cvt<float> {
+  __device__ __forceinline__ static float to(float v) { return v; }
+  __device__ __forceinline__ static float from(float v) { return v; }
+};
+template <> struct Cvt<double> {
+  __device__ __forceinline__ static double to(double v) { return v; }
+  __device__ __forceinline__ static double from(double v) { return v; }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  __device__ __forceinline__ static float to(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ __forceinline__ static __nv_bfloat16 from(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct Cvt<__half> {
+  __device__ __forceinline__ static float to(__half v) { return __half2float(v); }
+  __device__ __forceinline__ static __half from(float v) { return __float2half_rn(v); }
+};
+template <class T> struct Acc { typedef float type; };
+template <> struct Acc<double> { typedef double type; };
+
+// 16-byte vector of T
+template <class T> struct alignas(16) Vec16 { T v[16 / sizeof(T)]; static constexpr int N = 16 / sizeof(T); };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(t);
+}
+
+}  // namespace mgf
