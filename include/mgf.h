@@ -77,6 +77,37 @@ int mgf_conv2d_wgrad_f32(const float* dy, const float* x, float* dw, const mgf_c
 int mgf_fma(const void* a, const void* b, const void* c, void* out, int dtype,
             int64_t N, int64_t C, int64_t HW, int bmode, int cmode, void* stream);
 
+/* ---- tcgen05 implicit-GEMM convolution (bf16 in, fp32 accumulate in TMEM) --------------------------
+ * Replaces, for the bf16 engine, the library calls behind modulated_conv2d (training/networks.py:252-328 ->
+ * conv2d_resample.py:117-139 -> conv2d_gradfix.py:27-35 -> cuDNN grouped conv / conv_transpose) and the torchvision
+ * VGG16 convolutions of LPIPS (lpips/pretrained_networks.py:97-135), forward and input-gradient.
+ *
+ * out[b, y*osy+ofy[ph], x*osx+ofx[ph], co] = epilogue( sum_{tap t, channel k}  A_{amap(t)}[b, y+dy(t), x+dx(t), k]
+ *                                                     * W[g][wz(t)][ph*Cout + co][k] )
+ * for (b, y, x) over the NB x GH x GW tile grid; reads outside an activation tensor are zero (TMA fill).
+ * Activations are NHWC bf16 views (channel stride 1; W/H/N strides in elements, so strided phase views work);
+ * W is a dense bf16 [G][T][NT = phases*Cout][K] tensor, G = NB for per-sample (modulated) weights or 1.
+ * Epilogue, in order (each optional): reduce_out[b, n] += sum_pixels acc*X   (fp32 atomics; X like out),
+ * acc *= scale_n[b, n], += noise[oy, ox] * *noise_strength, += bias[co], act (0 none, 1 leaky-ReLU(alpha), 2 ReLU) * gain,
+ * += add (like out), *= (X > 0 ? 1 : ag_alpha) * ag_gain  (actgrad), store bf16.  bn = 0 picks the N tile. */
+typedef struct { const void* ptr; int64_t C, W, H, N, sW, sH, sN; } mgf_tc_act;
+typedef struct { int8_t amap, dy, dx, _pad; int32_t wz; } mgf_tc_tap;
+typedef struct {
+  mgf_tc_act a[4]; int32_t n_a;
+  const void* w; int64_t w_G, w_T, w_NT, w_K;
+  mgf_tc_tap taps[40]; int32_t ntaps;
+  int32_t GW, GH, NB;
+  int32_t phases, Cout;
+  void* out; int64_t OH, OW, OC; int32_t osy, osx; int32_t ofy[4], ofx[4];
+  const float* scale_n; float* reduce_out; const void* X;
+  const float* noise; const float* noise_strength; const float* bias;
+  int32_t act; float alpha, gain;
+  const void* add;
+  int32_t actgrad; float ag_alpha, ag_gain;
+  int32_t bn; int32_t reduce_per_sample;
+} mgf_conv_tc_desc;
+int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

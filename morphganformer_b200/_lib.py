@@ -32,6 +32,15 @@ SIGNATURES = {
 
 _lib = None
 
+# modules that add their own entries (with ctypes struct types) to SIGNATURES when imported
+_REGISTRARS = ["morphganformer_b200.tc"]
+
+
+def register_all():
+    import importlib
+    for m in _REGISTRARS:
+        importlib.import_module(m)
+
 
 def lib():
     global _lib
@@ -41,6 +50,7 @@ def lib():
                 "morphganformer_b200: CUDA library %s is missing. Build it with `python -m morphganformer_b200.build` "
                 "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
+        register_all()
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

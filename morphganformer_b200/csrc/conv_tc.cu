@@ -1,0 +1,457 @@
+// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate).
+//
+// One kernel covers every dense contraction of the hot path:
+//   * 3x3 stride-1 modulated conv (per-sample weight tiles with the style and demodulation folded in),
+//   * the up-sampling conv (reference: conv_transpose2d stride 2 -> (2H+1)^2 -> 4x4 FIR, conv2d_resample.py:117-134)
+//     as four output phases of 3x3 taps on the low-res grid (the FIR is folded into the per-phase weights, so the
+//     (2H+1)^2 intermediate never exists),
+//   * the resnet skip (1x1 conv + FIR up2) in the same form, the VGG16 convs of LPIPS, and every input gradient
+//     (dgrad = the same contraction with transposed weights; for the up conv 36 taps over four strided phase views).
+//
+// GEMM view: D[128 pixels, BN out-channels] += A[128 pixels, BK in-channels] * B[BN, BK]^T, looped over
+// (channel chunk, tap).  A tiles are TMA boxes {BK, TW, TH, TB} of an NHWC activation tensor shifted by the tap
+// offset -- out-of-bounds rows/cols are zero-filled by TMA, which is exactly the conv zero padding.  B tiles are
+// TMA boxes {BK, BN, 1} of the [G][T][NT][K] weight tensor.  Both land in shared memory in the 128B (or 64B for
+// 32-channel layers) swizzled K-major layout that tcgen05.mma reads through shared-memory descriptors.
+//
+// CTA = 6 warps, persistent over output tiles:
+//   warp 4 (one lane): TMA producer, STAGES-deep mbarrier ring
+//   warp 5 (one lane): tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 0-3        : epilogue -- tcgen05.ld the accumulator, then the fused per-layer tail:
+//                      * per-(sample, channel) scale           (dgrad: the style s[b,i])
+//                      * d(styles) partial sums                (sum over pixels of acc * X, warp-shuffle transpose-reduce + atomics)
+//                      * + noise * strength, + bias, leaky-ReLU/ReLU * gain     (networks.py:1036-1040, bias_act)
+//                      * + residual tensor                     (resnet add, networks.py:1160)
+//                      * activation-gradient mask by the saved output X   (backward of the previous layer's bias_act)
+//                      and 16-byte bf16 stores.  The epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include <cuda.h>
+#include <string.h>
+
+namespace mgf {
+namespace tc {
+
+constexpr int MAX_TAPS = 40;
+constexpr int MAX_AMAPS = 4;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct Tap { int8_t amap, dy, dx, pad; int32_t wz; };
+
+struct alignas(64) Params {
+  CUtensorMap amap[MAX_AMAPS];
+  CUtensorMap bmap;
+  Tap taps[MAX_TAPS];
+  int ntaps, kchunks;
+  int NB, GH, GW, TB, TH, TW, tilesB, tilesH, tilesW, rows;
+  int NT, Cout, n_tiles, per_sample, w_T;
+  void* out; long long OH, OW, OC; int osy, osx; int ofy[4], ofx[4];
+  const float* scale_n; float* reduce_out; const __nv_bfloat16* X;
+  const float* noise; const float* noise_strength; const float* bias;
+  int act; float alpha, gain;
+  const __nv_bfloat16* add;
+  int actgrad; float ag_alpha, ag_gain;
+  uint32_t tx_bytes;
+  int total_tiles;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory operand descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30)
+// (=1, unused for swizzled K-major), SBO>>4 [32,46) = 8 rows * row bytes, version=1 [46,48), layout [61,64) (2 = 128B, 4 = 64B swizzle).
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  constexpr uint64_t row_bytes = BK * 2;
+  constexpr uint64_t sbo = 8 * row_bytes;
+  constexpr uint64_t layout = (BK == 64) ? 2 : 4;
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int BN, int BK>
+struct Cfg {
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;
+  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  // instruction descriptor (InstrDescriptor): D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A/B, N>>3 at 17, M>>4 at 24
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
+
+struct TileCoord { int n0, x0, y0, b0; };
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int BN) {
+  TileCoord t;
+  const int nb = tile % p.n_tiles; int m = tile / p.n_tiles;
+  t.n0 = nb * BN;
+  t.x0 = (m % p.tilesW) * p.TW; m /= p.tilesW;
+  t.y0 = (m % p.tilesH) * p.TH; m /= p.tilesH;
+  t.b0 = m * p.TB;
+  return t;
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ Params p) {
+  using C = Cfg<BN, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = p.kchunks * p.ntaps;
+
+  if (warp == 4) {
+    if (lane == 0) {   // ------------------------------------------------ TMA producer
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
+        for (int kc = 0; kc < p.kchunks; kc++) {
+          for (int tp = 0; tp < p.ntaps; tp++) {
+            const Tap tap = p.taps[tp];
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], p.tx_bytes);
+            uint8_t* sa = smem + stage * C::STAGE;
+            tma_load_4d(&p.amap[tap.amap], &full[stage], sa, kc * BK, t.x0 + tap.dx, t.y0 + tap.dy, t.b0);
+            tma_load_3d(&p.bmap, &full[stage], sa + C::A_BYTES, kc * BK, t.n0, wbase + tap.wz);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {   // ------------------------------------------------ MMA issuer
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int it = 0; it < iters; it++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+          const uint64_t adesc = make_desc<BK>(sa), bdesc = make_desc<BK>(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++)
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), C::IDESC, (it > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty[stage]);           // frees the smem slot once these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[as]);                // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {             // ---------------------------------------------------- epilogue warps 0..3
+    int as = 0; uint32_t aphase = 0;
+    const int r = warp * 32 + lane;          // accumulator row == TMEM lane == pixel index inside the A box
+    const int tx = r % p.TW, ty = (r / p.TW) % p.TH, tb = r / (p.TW * p.TH);
+    const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
+      const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
+      const int phase_idx = t.n0 / p.Cout, co0 = t.n0 % p.Cout;
+      const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
+      const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
+      const long long obase = pix * p.OC + co0;
+      const float nz = (p.noise && valid) ? p.noise[oy * p.OW + ox] * nstr : 0.f;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c * 32), raw);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
+        float xv[32];
+        const bool needX = (p.X != nullptr) && (p.reduce_out != nullptr || p.actgrad);
+        if (needX) {
+          if (valid) {
+            const uint4* xp = reinterpret_cast<const uint4*>(p.X + obase + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const uint4 u = __ldg(xp + q);
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); xv[q * 8 + e * 2] = f.x; xv[q * 8 + e * 2 + 1] = f.y; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) xv[j] = 0.f;
+          }
+        }
+        if (p.reduce_out) {
+          // column sums over the 128 rows of acc * X: warp transpose-reduce (31 shuffles), then one atomic per column per warp
+          float s[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) s[j] = v[j] * xv[j];
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool hi = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; i++) {
+              const float send = hi ? s[i] : s[i + o];
+              const float keep = hi ? s[i + o] : s[i];
+              s[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          // lane L now holds the sum of column L over this warp's 32 rows (all rows of a tile share one sample: TB == 1)
+          atomicAdd(p.reduce_out + (long long)t.b0 * p.NT + t.n0 + c * 32 + lane, s[0]);
+        }
+        if (p.scale_n) {
+          const float* sp = p.scale_n + (long long)(valid ? b : 0) * p.NT + t.n0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] *= __ldg(sp + j);
+        }
+        if (p.noise) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] += nz;
+        }
+        if (p.bias) {
+          const float* bp = p.bias + co0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] += __ldg(bp + j);
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = (v[j] > 0.f ? v[j] : v[j] * p.alpha) * p.gain;
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f) * p.gain;
+        } else if (p.gain != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] *= p.gain;
+        }
+        if (p.add && valid) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.add + obase + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const uint4 u = __ldg(ap + q);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); v[q * 8 + e * 2] += f.x; v[q * 8 + e * 2 + 1] += f.y; }
+          }
+        }
+        if (p.actgrad) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] *= (xv[j] > 0.f ? 1.f : p.ag_alpha) * p.ag_gain;
+        }
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            uint4 u;
+            u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+            u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+            op[q] = u;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box, int bk) {
+  EncodeFn fn = get_encode();
+  if (!fn) MGF_FAIL(MGF_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) MGF_FAIL(MGF_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=%llu,%llu,%llu box=%u,%u,%u",
+                                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+  return 0;
+}
+
+template <int BN, int BK>
+static int launch(const Params& p, int grid, cudaStream_t st) {
+  using C = Cfg<BN, BK>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc: cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  conv_tc_kernel<BN, BK><<<grid, 192, C::SMEM, st>>>(p);
+  MGF_CHECK_LAUNCH("conv_tc");
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace mgf
+
+extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
+  using namespace mgf;
+  using namespace mgf::tc;
+  if (!d) MGF_FAIL(MGF_E_BADARG, "conv_tc: null descriptor");
+  if (d->n_a < 1 || d->n_a > MAX_AMAPS) MGF_FAIL(MGF_E_BADARG, "conv_tc: n_a=%d outside 1..%d", d->n_a, MAX_AMAPS);
+  if (d->ntaps < 1 || d->ntaps > MAX_TAPS) MGF_FAIL(MGF_E_BADARG, "conv_tc: ntaps=%d outside 1..%d", d->ntaps, MAX_TAPS);
+  if (!d->w || !d->out) MGF_FAIL(MGF_E_BADARG, "conv_tc: null weight/output");
+  const long long Cc = d->a[0].C;
+  if (Cc % 32 != 0 || Cc < 32) MGF_FAIL(MGF_E_SHAPE, "conv_tc: input channels (%lld) must be a multiple of 32", Cc);
+  if (d->w_K != Cc) MGF_FAIL(MGF_E_SHAPE, "conv_tc: weight K (%lld) != activation channels (%lld)", (long long)d->w_K, Cc);
+  const int BK = (Cc % 64 == 0) ? 64 : 32;
+  if (d->phases < 1 || d->phases > 4 || d->Cout < 32 || d->Cout % 32) MGF_FAIL(MGF_E_SHAPE, "conv_tc: Cout (%d) must be a multiple of 32, phases 1..4", d->Cout);
+  const long long NT = (long long)d->phases * d->Cout;
+  if (d->w_NT != NT) MGF_FAIL(MGF_E_SHAPE, "conv_tc: weight NT (%lld) != phases*Cout (%lld)", (long long)d->w_NT, NT);
+  if (d->OC < d->Cout || d->OC % 8) MGF_FAIL(MGF_E_SHAPE, "conv_tc: bad output channel stride");
+  int BN = d->bn;
+  if (BN == 0) BN = (d->Cout % 256 == 0) ? 256 : (d->Cout % 128 == 0) ? 128 : (d->Cout % 64 == 0) ? 64 : 32;
+  if (!(BN == 32 || BN == 64 || BN == 128 || BN == 256) || d->Cout % BN) MGF_FAIL(MGF_E_SHAPE, "conv_tc: BN=%d does not divide Cout=%d", BN, d->Cout);
+  if (d->GW < 1 || d->GH < 1 || d->NB < 1) MGF_FAIL(MGF_E_SHAPE, "conv_tc: empty grid");
+  const int per_sample = d->w_G > 1 ? 1 : 0;
+  if (per_sample && d->w_G != d->NB) MGF_FAIL(MGF_E_SHAPE, "conv_tc: per-sample weights need G == NB");
+  if (d->reduce_out && !per_sample && d->NB > 1 && d->reduce_per_sample) MGF_FAIL(MGF_E_UNSUP, "conv_tc: per-sample reduction needs per-sample tiles");
+
+  Params p;
+  memset(&p, 0, sizeof(p));
+  // tile shape: TW x TH x TB pixels = at most 128 rows
+  int TW = 1; while (TW * 2 <= d->GW && TW < 16) TW *= 2;
+  int TH = 1; while (TH * 2 <= d->GH && TW * TH * 2 <= 128) TH *= 2;
+  int TB = 1;
+  if (!per_sample && !d->reduce_per_sample) { while (TW * TH * TB * 2 <= 128 && TB * 2 <= d->NB) TB *= 2; }
+  p.TW = TW; p.TH = TH; p.TB = TB; p.rows = TW * TH * TB;
+  p.NB = d->NB; p.GH = d->GH; p.GW = d->GW;
+  p.tilesW = (d->GW + TW - 1) / TW; p.tilesH = (d->GH + TH - 1) / TH; p.tilesB = (d->NB + TB - 1) / TB;
+  p.NT = (int)NT; p.Cout = d->Cout; p.n_tiles = (int)(NT / BN); p.per_sample = per_sample; p.w_T = (int)d->w_T;
+  const long long total = (long long)p.tilesW * p.tilesH * p.tilesB * p.n_tiles;
+  if (total > 0x7fffffffLL) MGF_FAIL(MGF_E_SHAPE, "conv_tc: too many tiles");
+  p.total_tiles = (int)total;
+  p.ntaps = d->ntaps; p.kchunks = (int)(Cc / BK);
+  for (int i = 0; i < d->ntaps; i++) {
+    if (d->taps[i].amap < 0 || d->taps[i].amap >= d->n_a || d->taps[i].wz < 0 || d->taps[i].wz >= d->w_T)
+      MGF_FAIL(MGF_E_BADARG, "conv_tc: tap %d out of range", i);
+    p.taps[i].amap = d->taps[i].amap; p.taps[i].dy = d->taps[i].dy; p.taps[i].dx = d->taps[i].dx; p.taps[i].wz = d->taps[i].wz;
+  }
+  for (int i = 0; i < d->n_a; i++) {
+    const mgf_tc_act& a = d->a[i];
+    if (!a.ptr || a.C != Cc) MGF_FAIL(MGF_E_SHAPE, "conv_tc: activation %d: null or channel mismatch", i);
+    if (((uintptr_t)a.ptr & 15) || (a.sW * 2) % 16 || (a.sH * 2) % 16 || (a.sN * 2) % 16) MGF_FAIL(MGF_E_ALIGN, "conv_tc: activation %d must be 16-byte aligned/strided", i);
+    cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {(cuuint64_t)a.sW * 2, (cuuint64_t)a.sH * 2, (cuuint64_t)a.sN * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+    if (int e = encode(&p.amap[i], a.ptr, 4, dims, strides, box, BK)) return e;
+  }
+  {
+    if ((uintptr_t)d->w & 15) MGF_FAIL(MGF_E_ALIGN, "conv_tc: weights must be 16-byte aligned");
+    cuuint64_t dims[3] = {(cuuint64_t)d->w_K, (cuuint64_t)d->w_NT, (cuuint64_t)(d->w_G * d->w_T)};
+    cuuint64_t strides[2] = {(cuuint64_t)d->w_K * 2, (cuuint64_t)d->w_K * d->w_NT * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    if (int e = encode(&p.bmap, d->w, 3, dims, strides, box, BK)) return e;
+  }
+  p.out = d->out; p.OH = d->OH; p.OW = d->OW; p.OC = d->OC; p.osy = d->osy; p.osx = d->osx;
+  for (int i = 0; i < 4; i++) { p.ofy[i] = d->ofy[i]; p.ofx[i] = d->ofx[i]; }
+  p.scale_n = d->scale_n; p.reduce_out = d->reduce_out; p.X = (const __nv_bfloat16*)d->X;
+  p.noise = d->noise; p.noise_strength = d->noise_strength; p.bias = d->bias;
+  p.act = d->act; p.alpha = d->alpha; p.gain = d->gain; p.add = (const __nv_bfloat16*)d->add;
+  p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain;
+  if ((p.reduce_out || p.actgrad) && !p.X) MGF_FAIL(MGF_E_BADARG, "conv_tc: reduce/actgrad need X");
+  p.tx_bytes = (uint32_t)((p.rows * BK + BN * BK) * 2);
+  int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
+  cudaStream_t st = (cudaStream_t)stream;
+#define MGF_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch<bn, bk>(p, grid, st);
+  MGF_TC_CASE(256, 64) MGF_TC_CASE(128, 64) MGF_TC_CASE(64, 64) MGF_TC_CASE(32, 64)
+  MGF_TC_CASE(256, 32) MGF_TC_CASE(128, 32) MGF_TC_CASE(64, 32) MGF_TC_CASE(32, 32)
+#undef MGF_TC_CASE
+  MGF_FAIL(MGF_E_UNSUP, "conv_tc: no kernel for BN=%d BK=%d", BN, BK);
+}

@@ -1,0 +1,92 @@
+"""ctypes-level wrapper of mgf_conv_tc (include/mgf.h): the tcgen05 implicit-GEMM convolution used by the bf16 engine.
+Tensors are NHWC bf16 (`[N, H, W, C]` torch tensors, channel stride 1)."""
+import ctypes
+import torch
+from . import _lib
+
+c_void_p, c_int32, c_int64, c_float, c_int8 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_int8
+
+
+class TcAct(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("C", c_int64), ("W", c_int64), ("H", c_int64), ("N", c_int64),
+                ("sW", c_int64), ("sH", c_int64), ("sN", c_int64)]
+
+
+class TcTap(ctypes.Structure):
+    _fields_ = [("amap", c_int8), ("dy", c_int8), ("dx", c_int8), ("_pad", c_int8), ("wz", c_int32)]
+
+
+class ConvTcDesc(ctypes.Structure):
+    _fields_ = [("a", TcAct * 4), ("n_a", c_int32),
+                ("w", c_void_p), ("w_G", c_int64), ("w_T", c_int64), ("w_NT", c_int64), ("w_K", c_int64),
+                ("taps", TcTap * 40), ("ntaps", c_int32),
+                ("GW", c_int32), ("GH", c_int32), ("NB", c_int32),
+                ("phases", c_int32), ("Cout", c_int32),
+                ("out", c_void_p), ("OH", c_int64), ("OW", c_int64), ("OC", c_int64), ("osy", c_int32), ("osx", c_int32),
+                ("ofy", c_int32 * 4), ("ofx", c_int32 * 4),
+                ("scale_n", c_void_p), ("reduce_out", c_void_p), ("X", c_void_p),
+                ("noise", c_void_p), ("noise_strength", c_void_p), ("bias", c_void_p),
+                ("act", c_int32), ("alpha", c_float), ("gain", c_float),
+                ("add", c_void_p),
+                ("actgrad", c_int32), ("ag_alpha", c_float), ("ag_gain", c_float),
+                ("bn", c_int32), ("reduce_per_sample", c_int32)]
+
+
+_lib.SIGNATURES["mgf_conv_tc"] = (ctypes.c_int, [ctypes.POINTER(ConvTcDesc), c_void_p])
+
+
+def nhwc_view(t):
+    """(ptr, C, W, H, N, sW, sH, sN) of a [N, H, W, C] bf16 tensor (any strides with channel stride 1)."""
+    assert t.dtype == torch.bfloat16 and t.ndim == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
+    n, h, w, c = t.shape
+    return (t.data_ptr(), c, w, h, n, t.stride(2), t.stride(1), t.stride(0))
+
+
+def phase_view(t, py, px):
+    """strided view t[:, py::2, px::2, :] of an NHWC tensor as an activation descriptor."""
+    return nhwc_view(t[:, py::2, px::2, :])
+
+
+def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 0), ofx=(0, 0, 0, 0), scale_n=None,
+            reduce_out=None, X=None, noise=None, noise_strength=None, bias=None, act=0, alpha=0.2, gain=1.0, add=None,
+            actgrad=False, ag_alpha=0.2, ag_gain=1.0, bn=0, reduce_per_sample=False):
+    """acts: list of NHWC bf16 tensors or descriptor tuples; w: [G, T, NT, K] bf16 contiguous; taps: [(amap, dy, dx, wz)];
+    grid: (NB, GH, GW); out: [NB, OH, OW, OC] bf16 contiguous."""
+    d = ConvTcDesc()
+    d.n_a = len(acts)
+    for i, a in enumerate(acts):
+        v = a if isinstance(a, tuple) else nhwc_view(a)
+        d.a[i] = TcAct(*v)
+    assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.ndim == 4
+    d.w, d.w_G, d.w_T, d.w_NT, d.w_K = w.data_ptr(), w.shape[0], w.shape[1], w.shape[2], w.shape[3]
+    d.ntaps = len(taps)
+    for i, (am, dy, dx, wz) in enumerate(taps):
+        d.taps[i] = TcTap(am, dy, dx, 0, wz)
+    d.NB, d.GH, d.GW = grid
+    d.phases, d.Cout = phases, cout
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.ndim == 4
+    d.out, d.OH, d.OW, d.OC = out.data_ptr(), out.shape[1], out.shape[2], out.shape[3]
+    d.osy, d.osx = osy, osx
+    for i in range(4):
+        d.ofy[i], d.ofx[i] = ofy[i], ofx[i]
+    for name, t, dt in (("scale_n", scale_n, torch.float32), ("reduce_out", reduce_out, torch.float32), ("X", X, torch.bfloat16),
+                        ("noise", noise, torch.float32), ("noise_strength", noise_strength, torch.float32),
+                        ("bias", bias, torch.float32), ("add", add, torch.bfloat16)):
+        if t is not None:
+            assert t.dtype == dt and t.is_contiguous(), name
+            setattr(d, name, t.data_ptr())
+    d.act, d.alpha, d.gain = act, alpha, gain
+    d.actgrad, d.ag_alpha, d.ag_gain = int(bool(actgrad)), ag_alpha, ag_gain
+    d.bn, d.reduce_per_sample = bn, int(bool(reduce_per_sample))
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().mgf_conv_tc(ctypes.byref(d), _lib.stream_ptr(out.device)), "mgf_conv_tc")
+    return out
+
+
+TAPS_3X3 = [(0, ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+
+
+def pack_w3x3(w):
+    """[Cout, Cin, 3, 3] (correlation weights, as F.conv2d) -> [1, 9, Cout, Cin] bf16."""
+    co, ci, kh, kw = w.shape
+    return w.permute(2, 3, 0, 1).reshape(1, kh * kw, co, ci).to(torch.bfloat16).contiguous()

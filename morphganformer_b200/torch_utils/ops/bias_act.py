@@ -64,7 +64,7 @@ def _make(dim, act, alpha, gain, clamp):
     spec = activation_funcs[act]
     idx = spec.cuda_idx
     keep_x = ("x" in spec.ref) or spec.has_2nd_grad
-    keep_y = "y" in spec.ref
+    keep_y = ("y" in spec.ref) or (clamp >= 0 and "x" not in spec.ref)   # clamp masks the gradient by the saved output
     trivial = act == "linear" and gain == 1 and clamp < 0
 
     class BiasAct(torch.autograd.Function):

@@ -25,6 +25,7 @@ def test_library_builds_and_exports_header_symbols():
 
 
 def test_python_signatures_cover_header():
+    _lib.register_all()
     assert sorted(_lib.SIGNATURES) == _declared()
 
 
