@@ -108,6 +108,54 @@ typedef struct {
 } mgf_conv_tc_desc;
 int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream);
 
+/* ---- bf16 synthesis-engine helpers (engine_kernels.cu); activations NHWC bf16, coefficients fp32 ------------------
+ * style_fwd : s[b,i] = ((wg[b,:] . A[i,:]) * again + abias[i]) * sgain  (FullyConnectedLayer affine, networks.py:138-150, :1022,
+ *             :1056-1059) and, when Wsq is given, d[b,o] = rsqrt(sum_i s^2 Wsq[o,i] + 1e-8) (demodulation, :291).
+ * style_bwd : dwg[b,:] += d(loss)/d(wg) from ds (direct style gradient) and R[b,o] = sum_pixels dy*y (demodulation path).
+ * modulate_weights : out[b][t][n][k] = bf16(base[t][n][k] * rs[b][n % nmod] * cs[b][k])  -- the per-sample "fused_modconv"
+ *             weights (:288-293) laid out as tcgen05 B operands.
+ * small_gemm: out[b,m,n] (+)= sum_k A[b,m,k] Bm[n,k] + bias[n] (attention value/modulation fold, tiny).
+ * torgb_*   : ToRGBLayer (:1054-1065) forward to the public fp32 NCHW image and its backward.
+ * act_bwd   : leaky-ReLU backward of a fused conv epilogue + R[b,o] accumulation.
+ * upfir2_*  : NHWC [1,3,3,1] FIR up-sampling x2 with residual add (resnet skip, :245-250, :1157-1160) and its adjoint;
+ *             fk4 is a HOST array of the four 1-D taps. */
+int mgf_style_fwd(const float* wg, int64_t wg_stride, const float* A, const float* abias, float again, float sgain,
+                  const float* Wsq, float* s_out, float* d_out, int B, int Cin, int O, int wdim, void* stream);
+int mgf_style_bwd(const float* ds, const float* R, const float* s, const float* d, const float* Wsq, const float* A,
+                  float again, float sgain, float* dwg, int64_t dwg_stride, int B, int Cin, int O, int wdim, void* stream);
+int mgf_modulate_weights(const float* base, const float* rs, int nmod, const float* cs, void* out,
+                         int B, int64_t T, int64_t NT, int64_t K, void* stream);
+int mgf_small_gemm(const float* A, int64_t sAb, int64_t sAm, const float* Bm, const float* bias, float* out,
+                   int64_t sOb, int64_t sOm, int B, int M, int N, int K, int accumulate, void* stream);
+int mgf_torgb_fwd(const void* y, const float* wrgb, const float* s, const float* bias, float* img, int B, int64_t HW, int C, void* stream);
+int mgf_torgb_bwd(const float* dimg, const void* y, const float* wrgb, const float* s, void* dy, float* ds, float* R,
+                  int B, int64_t HW, int C, void* stream);
+int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, const float* noise, const float* nstr, const float* bias,
+                float alpha, float gain, int mode, int B, int64_t HW, int C, void* stream);
+int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
+int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
+
+/* ---- fused duplex attention layer (attention.cu): TransformerLayer.forward (networks.py:748-822, default GANformer config)
+ * + noise + bias_act tail (:1036-1040) in one pass over X [B,HW,C] bf16; Kf [16,C], Sc [HW,16], maskbias [B,16], VM [B,16,C],
+ * bm [C] are the host-folded constants described in attention.cu.  bwd writes dX, accumulates dVM [B,16,C] and R [B,C]. */
+int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
+                 const float* noise, const float* nstr, const float* bias, float gain, float alpha,
+                 void* out, float* probs, int B, int64_t HW, int C, void* stream);
+int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
+                 const float* noise, const float* nstr, const float* bias, float gain, float alpha,
+                 void* dX, float* dVM, float* R, int B, int64_t HW, int C, void* stream);
+
+/* ---- projection-loss and optimizer kernels (lpips.cu): lpips/networks_basic.py:64-101, lpips/__init__.py:44-46,
+ * MSELoss (1024_example_percept_MSE.py:143), Adam + latent noise (:117, :134-135, :153). */
+int mgf_lpips_prep(const float* img, const float* target, void* col, float* mse, int B, int R, void* stream);
+int mgf_lpips_prep_bwd(const void* dcol, const float* img, const float* target, float mcoef, float* dimg, int B, int R, void* stream);
+int mgf_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int mgf_maxpool2_bwd(const void* x, const void* dy, const void* extra, void* dx, int B, int H, int W, int C, void* stream);
+int mgf_lpips_head(int mode, const void* f, const void* n1, const float* lin, const float* coef, void* out, float* val,
+                   int relu_mask, int B, int64_t HW, int C, void* stream);
+int mgf_adam_noise_step(float* latent, const float* grad, float* m, float* v, const float* noise_all, int noise_rows, float* latent_n,
+                        const float* sched, int* step_ptr, float beta1, float beta2, float eps, float weight_decay, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,23 @@ SIGNATURES = {
     "mgf_conv2d_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_void_p]),
     "mgf_conv2d_dgrad_f32": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_void_p]),
     "mgf_conv2d_wgrad_f32": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_void_p]),
+    "mgf_style_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_style_bwd": (c_int, [c_void_p] * 6 + [c_float, c_float, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_modulate_weights": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p]),
+    "mgf_small_gemm": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_torgb_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]),
+    "mgf_torgb_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int64, c_int, c_void_p]),
+    "mgf_act_bwd": (c_int, [c_void_p] * 7 + [c_float, c_float, c_int, c_int, c_int64, c_int, c_void_p]),
+    "mgf_upfir2_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_upfir2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_attn_fwd": (c_int, [c_void_p] * 9 + [c_float, c_float, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "mgf_attn_bwd": (c_int, [c_void_p] * 10 + [c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "mgf_lpips_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mgf_lpips_prep_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
+    "mgf_maxpool2_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_maxpool2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_lpips_head": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
+    "mgf_adam_noise_step": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int64, c_void_p]),
     "mgf_fma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
 }
 

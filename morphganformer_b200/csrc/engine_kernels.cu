@@ -1,0 +1,428 @@
+// engine_kernels.cu -- the small / HBM-bound kernels of the bf16 synthesis engine (everything around the tcgen05 convs):
+//   style affine + demodulation coefficients (networks.py:1022, :288-293) and their backward,
+//   per-sample weight modulation into bf16 GEMM operands (the "fused_modconv" weights, networks.py:288-293),
+//   tiny batched GEMM for the attention value/modulation fold, ToRGB forward/backward (networks.py:1054-1065),
+//   leaky-ReLU backward with the demodulation-gradient reduction, NHWC FIR up-sampling (+ residual add) and its adjoint
+//   (resnet skip path, networks.py:245-250, upfirdn2d.py:300-335).
+// Activations are NHWC bf16; all math in fp32.
+#include "common.cuh"
+
+namespace mgf {
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (w == 0) { t = warp_sum(t); if (l == 0) red[0] = t; }
+  __syncthreads();
+  return red[0];
+}
+
+// ---- styles s[b,i] = (wg[b,:] . A[i,:]) * again + abias[i] * bgain, then *sgain; d[b,o] = rsqrt(sum_i s^2 Wsq[o,i] + 1e-8)
+__global__ void __launch_bounds__(256) style_fwd_kernel(const float* wg, long long wg_stride, const float* A, const float* abias,
+                                                        float again, float sgain, const float* Wsq, float* s_out, float* d_out,
+                                                        int Cin, int O, int wdim) {
+  extern __shared__ float sm[];
+  float* s = sm;                 // [Cin]
+  float* w = sm + Cin;           // [wdim]
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < wdim; j += blockDim.x) w[j] = wg[(long long)b * wg_stride + j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < wdim; j++) acc = fmaf(w[j], A[i * wdim + j], acc);
+    const float v = (acc * again + abias[i]) * sgain;
+    s[i] = v; s_out[(long long)b * Cin + i] = v;
+  }
+  __syncthreads();
+  if (Wsq) {
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+      float acc = 0.f;
+      const float* wr = Wsq + (long long)o * Cin;
+      for (int i = 0; i < Cin; i++) acc = fmaf(s[i] * s[i], wr[i], acc);
+      d_out[(long long)b * O + o] = rsqrtf(acc + 1e-8f);
+    }
+  }
+}
+
+// backward: ds_total[i] = ds[i] - sum_o R[o] d[o]^2 s[i] Wsq[o,i]   (R[o] = sum_p dy*y, so dL/dd = R/d and dd/ds_i = -d^3 s_i Wsq)
+//           dwg[j] += sgain * again * sum_i ds_total[i] A[i,j]
+__global__ void __launch_bounds__(256) style_bwd_kernel(const float* ds, const float* R, const float* s, const float* d, const float* Wsq,
+                                                        const float* A, float again, float sgain, float* dwg, long long dwg_stride,
+                                                        int Cin, int O, int wdim) {
+  extern __shared__ float sm[];
+  float* dst = sm;               // [Cin]
+  float* rd2 = sm + Cin;         // [O]
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  if (R) for (int o = threadIdx.x; o < O; o += blockDim.x) { const float dv = d[(long long)b * O + o]; rd2[o] = R[(long long)b * O + o] * dv * dv; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
+    float t = ds ? ds[(long long)b * Cin + i] : 0.f;
+    if (R) {
+      float acc = 0.f;
+      for (int o = 0; o < O; o++) acc = fmaf(rd2[o], Wsq[(long long)o * Cin + i], acc);
+      t -= acc * s[(long long)b * Cin + i];
+    }
+    dst[i] = t;
+  }
+  __syncthreads();
+  for (int j = 0; j < wdim; j++) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < Cin; i += blockDim.x) acc = fmaf(dst[i], A[i * wdim + j], acc);
+    acc = block_sum_256(acc, red);
+    if (threadIdx.x == 0) dwg[(long long)b * dwg_stride + j] += acc * again * sgain;
+  }
+}
+
+// ---- per-sample operand weights: out[b][t][n][k] = base[t][n][k] * rs[b][n % nmod] * cs[b][k]   (bf16)
+__global__ void __launch_bounds__(256) modulate_kernel(const float* base, const float* rs, int nmod, const float* cs,
+                                                       __nv_bfloat16* out, long long TN, int K, int NT) {
+  const long long b = blockIdx.y;
+  const long long per = TN * K;
+  const int k4 = K >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TN * k4; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / k4; const int k = (int)(i % k4) * 4;
+    const float4 w = *reinterpret_cast<const float4*>(base + row * K + k);
+    float r = 1.f;
+    if (rs) r = rs[b * nmod + (int)((row % NT) % nmod)];
+    float4 c = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (cs) c = *reinterpret_cast<const float4*>(cs + b * K + k);
+    uint2 o;
+    o.x = pack_bf16(w.x * r * c.x, w.y * r * c.y);
+    o.y = pack_bf16(w.z * r * c.z, w.w * r * c.w);
+    *reinterpret_cast<uint2*>(out + b * per + row * K + k) = o;
+  }
+}
+
+// ---- tiny batched GEMM: out[b,m,n] = sum_k A[b,m,k] * Bm[n,k] (+ bias[n]); A strided (sAb, sAm), optional accumulate into out
+__global__ void __launch_bounds__(256) small_gemm_kernel(const float* A, long long sAb, long long sAm, const float* Bm, const float* bias,
+                                                         float* out, long long sOb, long long sOm, int M, int N, int K, int accumulate) {
+  const int b = blockIdx.y;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * N; e += gridDim.x * blockDim.x) {
+    const int m = e / N, n = e % N;
+    const float* a = A + (long long)b * sAb + (long long)m * sAm;
+    const float* w = Bm + (long long)n * K;
+    float acc = bias ? bias[n] : 0.f;
+    for (int k = 0; k < K; k++) acc = fmaf(a[k], w[k], acc);
+    float* o = out + (long long)b * sOb + (long long)m * sOm + n;
+    *o = accumulate ? (*o + acc) : acc;
+  }
+}
+
+// ---- ToRGB: img[b,c,p] = sum_o y[b,p,o] * wrgb[c,o] * s[b,o] + bias[c]    (y NHWC bf16 -> img NCHW fp32, 3 channels)
+template <int C>
+__global__ void __launch_bounds__(256) torgb_fwd_kernel(const __nv_bfloat16* y, const float* wrgb, const float* s, const float* bias,
+                                                        float* img, long long HW, int nimg) {
+  __shared__ float ws[3 * C];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) ws[i] = wrgb[i] * s[(long long)b * C + (i % C)];
+  __syncthreads();
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    const uint4* yp = reinterpret_cast<const uint4*>(y + ((long long)b * HW + p) * C);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < C / 8; q++) {
+      const uint4 u = __ldg(yp + q);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float2 f = unpack_bf16(w4[e]);
+        const int o = q * 8 + e * 2;
+        a0 = fmaf(f.x, ws[o], a0); a0 = fmaf(f.y, ws[o + 1], a0);
+        a1 = fmaf(f.x, ws[C + o], a1); a1 = fmaf(f.y, ws[C + o + 1], a1);
+        a2 = fmaf(f.x, ws[2 * C + o], a2); a2 = fmaf(f.y, ws[2 * C + o + 1], a2);
+      }
+    }
+    float* ip = img + (long long)b * 3 * HW + p;
+    ip[0] = a0 + bias[0]; ip[HW] = a1 + bias[1]; ip[2 * HW] = a2 + bias[2];
+  }
+}
+
+// backward: dy[b,p,o] = sum_c dimg[b,c,p] wrgb[c,o] s[b,o];  ds[b,o] += sum_{p,c} dimg wrgb[c,o] y[b,p,o];  R[b,o] += sum_p dy*y
+// thread = (pixel lane, 8-channel vector); per-CTA shared accumulators, then one global atomic per channel per CTA.
+__global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* dimg, const __nv_bfloat16* y, const float* wrgb, const float* s,
+                                                        __nv_bfloat16* dy, float* ds, float* R, long long HW, int C, int pix_per_cta) {
+  extern __shared__ float sm[];
+  float* acc_ds = sm;        // [C]
+  float* acc_R = sm + C;     // [C]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lanes_c = C / 8, tp = 256 / lanes_c;
+  const int cv = threadIdx.x % lanes_c, pl = threadIdx.x / lanes_c;
+  float w0[8], w1[8], w2[8], sv[8], lds[8], lR[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const int o = cv * 8 + e;
+    w0[e] = wrgb[o]; w1[e] = wrgb[C + o]; w2[e] = wrgb[2 * C + o]; sv[e] = s[(long long)b * C + o]; lds[e] = 0.f; lR[e] = 0.f;
+  }
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  for (long long p = p0 + pl; p < p0 + pix_per_cta && p < HW; p += tp) {
+    const float* ip = dimg + (long long)b * 3 * HW + p;
+    const float g0 = __ldg(ip), g1 = __ldg(ip + HW), g2 = __ldg(ip + 2 * HW);
+    const long long off = ((long long)b * HW + p) * C + cv * 8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + off));
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o4[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float2 f = unpack_bf16(w4[e]);
+      const float t0 = g0 * w0[e * 2] + g1 * w1[e * 2] + g2 * w2[e * 2];
+      const float t1 = g0 * w0[e * 2 + 1] + g1 * w1[e * 2 + 1] + g2 * w2[e * 2 + 1];
+      const float d0 = t0 * sv[e * 2], d1 = t1 * sv[e * 2 + 1];
+      lds[e * 2] += t0 * f.x; lds[e * 2 + 1] += t1 * f.y;
+      lR[e * 2] += d0 * f.x; lR[e * 2 + 1] += d1 * f.y;
+      o4[e] = pack_bf16(d0, d1);
+    }
+    *reinterpret_cast<uint4*>(dy + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; e++) { atomicAdd(&acc_ds[cv * 8 + e], lds[e]); atomicAdd(&acc_R[cv * 8 + e], lR[e]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(&ds[(long long)b * C + i], acc_ds[i]); atomicAdd(&R[(long long)b * C + i], acc_R[i]); }
+}
+
+// ---- leaky-ReLU backward with demod-gradient reduction.  z = lrelu(y + noise*ns + bias) * gain (what the conv epilogue stored).
+// dy = dz * gain * (z > 0 ? 1 : alpha)  (mode 0) or dy = dz (mode 1: dz is already the pre-activation gradient);
+// R[b,o] += sum_p dy * y with y = lrelu^-1(z/gain) - noise*ns - bias.   One CTA per (pixel chunk, sample); C <= 512.
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, const __nv_bfloat16* z, __nv_bfloat16* dy, float* R,
+                                                      const float* noise, const float* nstr, const float* bias,
+                                                      float alpha, float gain, int mode, long long HW, int C, int pix_per_cta) {
+  extern __shared__ float racc[];   // [C]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) racc[i] = 0.f;
+  __syncthreads();
+  const int vecs = C / 8;                       // uint4 per pixel
+  const int lanes_c = vecs < 256 ? vecs : 256;  // threads along channels
+  const int tp = 256 / lanes_c;                 // pixels processed concurrently
+  const int cv = threadIdx.x % lanes_c, pl = threadIdx.x / lanes_c;
+  const float ns = (noise && nstr) ? *nstr : 0.f;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  float bsv[8], lr[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) { bsv[e] = bias ? bias[cv * 8 + e] : 0.f; lr[e] = 0.f; }
+  const float inv_gain = 1.f / gain, inv_alpha = 1.f / alpha;
+  if (pl < tp) {
+    for (long long p = p0 + pl; p < p0 + pix_per_cta && p < HW; p += tp) {
+      const long long off = ((long long)b * HW + p) * C + cv * 8;
+      const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + off));
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dz + off));
+      const float nz = noise ? noise[p] * ns : 0.f;
+      const uint32_t z4[4] = {uz.x, uz.y, uz.z, uz.w}, d4[4] = {ud.x, ud.y, ud.z, ud.w};
+      uint32_t o4[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float2 zf = unpack_bf16(z4[e]), df = unpack_bf16(d4[e]);
+        float g0 = df.x, g1 = df.y;
+        if (mode == 0) { g0 *= gain * (zf.x > 0.f ? 1.f : alpha); g1 *= gain * (zf.y > 0.f ? 1.f : alpha); }
+        const float u0 = zf.x * inv_gain, u1 = zf.y * inv_gain;
+        const float y0 = (u0 > 0.f ? u0 : u0 * inv_alpha) - nz - bsv[e * 2], y1 = (u1 > 0.f ? u1 : u1 * inv_alpha) - nz - bsv[e * 2 + 1];
+        lr[e * 2] += g0 * y0; lr[e * 2 + 1] += g1 * y1;
+        o4[e] = pack_bf16(g0, g1);
+      }
+      if (dy) *reinterpret_cast<uint4*>(dy + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) atomicAdd(&racc[cv * 8 + e], lr[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&R[(long long)b * C + i], racc[i]);
+}
+
+// ---- NHWC FIR up-sampling x2 with the 4-tap separable filter (zero-insert, pad [2,1,2,1], gain 4) + residual add:
+// out[b,Y,X,c] = add[b,Y,X,c] + g * sum_{fy,fx} fk[fy]*fk[fx] * v[b,(Y+fy-2)/2,(X+fx-2)/2,c]   over taps where the index is even
+// (reference Conv2dLayer.forward :245-250 -> conv2d_resample 1x1-up branch -> upfirdn2d(up=2, pad=[2,1,2,1], gain=4) -> bias_act gain).
+// fk = flipped normalised 1-D taps * 2 (gain 4 split per axis).
+__global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* v, const __nv_bfloat16* add, __nv_bfloat16* out,
+                                                         float4 fk, float g, int h, int w, int C) {
+  const int vecs = C / 8;
+  const long long total = (long long)gridDim.y * 0 + (long long)(2 * h) * (2 * w) * vecs;
+  const int b = blockIdx.y;
+  const float f[4] = {fk.x, fk.y, fk.z, fk.w};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vecs); long long t = i / vecs;
+    const int X = (int)(t % (2 * w)), Y = (int)(t / (2 * w));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e] = 0.f;
+    // taps with (Y + fy - 2) even: fy has the parity of Y
+    for (int fy = (Y & 1); fy < 4; fy += 2) {
+      const int iy = (Y + fy - 2) >> 1;
+      if (iy < 0 || iy >= h) continue;
+      for (int fx = (X & 1); fx < 4; fx += 2) {
+        const int ix = (X + fx - 2) >> 1;
+        if (ix < 0 || ix >= w) continue;
+        const float cf = f[fy] * f[fx];
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(v + (((long long)b * h + iy) * w + ix) * C + cv * 8));
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); acc[e * 2] = fmaf(cf, q.x, acc[e * 2]); acc[e * 2 + 1] = fmaf(cf, q.y, acc[e * 2 + 1]); }
+      }
+    }
+    const long long off = (((long long)b * 2 * h + Y) * 2 * w + X) * C + cv * 8;
+    float av[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) av[e] = 0.f;
+    if (add) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(add + off));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); av[e * 2] = q.x; av[e * 2 + 1] = q.y; }
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0] * g + av[0], acc[1] * g + av[1]); o.y = pack_bf16(acc[2] * g + av[2], acc[3] * g + av[3]);
+    o.z = pack_bf16(acc[4] * g + av[4], acc[5] * g + av[5]); o.w = pack_bf16(acc[6] * g + av[6], acc[7] * g + av[7]);
+    *reinterpret_cast<uint4*>(out + off) = o;
+  }
+}
+
+// adjoint of the above (without the add): dv[b,iy,ix,c] = g * sum_{fy,fx} fk[fy] fk[fx] dout[b, 2iy+2-fy, 2ix+2-fx, c]
+__global__ void __launch_bounds__(256) upfir2_bwd_kernel(const __nv_bfloat16* dout, __nv_bfloat16* dv, float4 fk, float g, int h, int w, int C) {
+  const int vecs = C / 8;
+  const long long total = (long long)h * w * vecs;
+  const int b = blockIdx.y;
+  const float f[4] = {fk.x, fk.y, fk.z, fk.w};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vecs); long long t = i / vecs;
+    const int ix = (int)(t % w), iy = (int)(t / w);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e] = 0.f;
+#pragma unroll
+    for (int fy = 0; fy < 4; fy++) {
+      const int Y = 2 * iy + 2 - fy;
+      if (Y < 0 || Y >= 2 * h) continue;
+#pragma unroll
+      for (int fx = 0; fx < 4; fx++) {
+        const int X = 2 * ix + 2 - fx;
+        if (X < 0 || X >= 2 * w) continue;
+        const float cf = f[fy] * f[fx];
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dout + (((long long)b * 2 * h + Y) * 2 * w + X) * C + cv * 8));
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); acc[e * 2] = fmaf(cf, q.x, acc[e * 2]); acc[e * 2 + 1] = fmaf(cf, q.y, acc[e * 2 + 1]); }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0] * g, acc[1] * g); o.y = pack_bf16(acc[2] * g, acc[3] * g);
+    o.z = pack_bf16(acc[4] * g, acc[5] * g); o.w = pack_bf16(acc[6] * g, acc[7] * g);
+    *reinterpret_cast<uint4*>(dv + (((long long)b * h + iy) * w + ix) * C + cv * 8) = o;
+  }
+}
+
+static inline unsigned grid_for(long long work, int per_block = 256, int waves = 8) {
+  long long blocks = (work + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace mgf
+
+using namespace mgf;
+
+extern "C" int mgf_style_fwd(const float* wg, int64_t wg_stride, const float* A, const float* abias, float again, float sgain,
+                             const float* Wsq, float* s_out, float* d_out, int B, int Cin, int O, int wdim, void* stream) {
+  if (!wg || !A || !abias || !s_out || (Wsq && !d_out)) MGF_FAIL(MGF_E_BADARG, "style_fwd: null tensor");
+  if (B <= 0) return 0;
+  style_fwd_kernel<<<B, 256, (Cin + wdim) * sizeof(float), (cudaStream_t)stream>>>(wg, wg_stride, A, abias, again, sgain, Wsq, s_out, d_out, Cin, O, wdim);
+  MGF_CHECK_LAUNCH("style_fwd");
+  return 0;
+}
+
+extern "C" int mgf_style_bwd(const float* ds, const float* R, const float* s, const float* d, const float* Wsq, const float* A,
+                             float again, float sgain, float* dwg, int64_t dwg_stride, int B, int Cin, int O, int wdim, void* stream) {
+  if (!A || !dwg || (R && (!s || !d || !Wsq))) MGF_FAIL(MGF_E_BADARG, "style_bwd: null tensor");
+  if (R && sgain != 1.f) MGF_FAIL(MGF_E_UNSUP, "style_bwd: demodulation with a style gain is not a case of the generator");
+  if (B <= 0) return 0;
+  style_bwd_kernel<<<B, 256, (Cin + O) * sizeof(float), (cudaStream_t)stream>>>(ds, R, s, d, Wsq, A, again, sgain, dwg, dwg_stride, Cin, O, wdim);
+  MGF_CHECK_LAUNCH("style_bwd");
+  return 0;
+}
+
+extern "C" int mgf_modulate_weights(const float* base, const float* rs, int nmod, const float* cs, void* out,
+                                    int B, int64_t T, int64_t NT, int64_t K, void* stream) {
+  if (!base || !out) MGF_FAIL(MGF_E_BADARG, "modulate_weights: null tensor");
+  if (K % 4) MGF_FAIL(MGF_E_SHAPE, "modulate_weights: K must be a multiple of 4");
+  if (B <= 0) return 0;
+  const long long TN = T * NT;
+  dim3 grid(grid_for(TN * (K / 4), 256, 4), B);
+  modulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(base, rs, nmod > 0 ? nmod : 1, cs, (__nv_bfloat16*)out, TN, (int)K, (int)NT);
+  MGF_CHECK_LAUNCH("modulate_weights");
+  return 0;
+}
+
+extern "C" int mgf_small_gemm(const float* A, int64_t sAb, int64_t sAm, const float* Bm, const float* bias, float* out,
+                              int64_t sOb, int64_t sOm, int B, int M, int N, int K, int accumulate, void* stream) {
+  if (!A || !Bm || !out) MGF_FAIL(MGF_E_BADARG, "small_gemm: null tensor");
+  if (B <= 0 || M * N == 0) return 0;
+  dim3 grid((M * N + 255) / 256, B);
+  small_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sAb, sAm, Bm, bias, out, sOb, sOm, M, N, K, accumulate);
+  MGF_CHECK_LAUNCH("small_gemm");
+  return 0;
+}
+
+extern "C" int mgf_torgb_fwd(const void* y, const float* wrgb, const float* s, const float* bias, float* img, int B, int64_t HW, int C, void* stream) {
+  if (!y || !wrgb || !s || !bias || !img) MGF_FAIL(MGF_E_BADARG, "torgb_fwd: null tensor");
+  dim3 grid(grid_for(HW, 256, 8), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 32) torgb_fwd_kernel<32><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, 3);
+  else if (C == 64) torgb_fwd_kernel<64><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, 3);
+  else if (C == 128) torgb_fwd_kernel<128><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, 3);
+  else MGF_FAIL(MGF_E_UNSUP, "torgb_fwd: C=%d not in {32,64,128}", C);
+  MGF_CHECK_LAUNCH("torgb_fwd");
+  return 0;
+}
+
+extern "C" int mgf_torgb_bwd(const float* dimg, const void* y, const float* wrgb, const float* s, void* dy, float* ds, float* R,
+                             int B, int64_t HW, int C, void* stream) {
+  if (!dimg || !y || !wrgb || !s || !dy || !ds || !R) MGF_FAIL(MGF_E_BADARG, "torgb_bwd: null tensor");
+  if (C % 8 || C / 8 > 256 || 256 % (C / 8)) MGF_FAIL(MGF_E_SHAPE, "torgb_bwd: C/8 must divide 256");
+  long long ppc = (HW * B + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8);
+  if (ppc < 16) ppc = 16;
+  dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
+  torgb_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dimg, (const __nv_bfloat16*)y, wrgb, s, (__nv_bfloat16*)dy, ds, R, HW, C, (int)ppc);
+  MGF_CHECK_LAUNCH("torgb_bwd");
+  return 0;
+}
+
+extern "C" int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, const float* noise, const float* nstr, const float* bias,
+                           float alpha, float gain, int mode, int B, int64_t HW, int C, void* stream) {
+  if (!dz || !z || !R) MGF_FAIL(MGF_E_BADARG, "act_bwd: null tensor");
+  if (C % 8 || C > 4096) MGF_FAIL(MGF_E_SHAPE, "act_bwd: C must be a multiple of 8");
+  if ((C / 8) < 256 && 256 % (C / 8)) MGF_FAIL(MGF_E_SHAPE, "act_bwd: C/8 must divide 256");
+  if ((C / 8) > 256) MGF_FAIL(MGF_E_SHAPE, "act_bwd: C too large");
+  // enough pixels per CTA that the per-CTA atomics stay cheap, enough CTAs to fill the machine
+  long long ppc = (HW * B + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8);
+  if (ppc < 16) ppc = 16;
+  dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
+  act_bwd_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)z, (__nv_bfloat16*)dy, R,
+                                                                        noise, nstr, bias, alpha, gain, mode, HW, C, (int)ppc);
+  MGF_CHECK_LAUNCH("act_bwd");
+  return 0;
+}
+
+extern "C" int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream) {
+  if (!v || !out || !fk4) MGF_FAIL(MGF_E_BADARG, "upfir2_add: null tensor");
+  if (C % 8) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: C must be a multiple of 8");
+  dim3 grid(grid_for((long long)4 * h * w * (C / 8), 256, 8), B);
+  upfir2_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)add, (__nv_bfloat16*)out,
+                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C);
+  MGF_CHECK_LAUNCH("upfir2_add");
+  return 0;
+}
+
+extern "C" int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream) {
+  if (!dout || !dv || !fk4) MGF_FAIL(MGF_E_BADARG, "upfir2_bwd: null tensor");
+  if (C % 8) MGF_FAIL(MGF_E_SHAPE, "upfir2_bwd: C must be a multiple of 8");
+  dim3 grid(grid_for((long long)h * w * (C / 8), 256, 8), B);
+  upfir2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dv,
+                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C);
+  MGF_CHECK_LAUNCH("upfir2_bwd");
+  return 0;
+}

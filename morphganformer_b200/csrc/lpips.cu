@@ -1,0 +1,317 @@
+// lpips.cu -- HBM-bound kernels of the projection loss (reference lpips/networks_basic.py:64-101, lpips/__init__.py:44-46,
+// torch.nn.MSELoss at 1024_example_percept_MSE.py:143,224) and the fused latent update (torch.optim.Adam + latent_noise,
+// 1024_example_percept_MSE.py:117,134-135,153).  The VGG16 convolutions themselves run on the tcgen05 kernel (conv_tc.cu).
+//   prep      : ScalingLayer + fp32 NCHW -> bf16 NHWC 3x3 im2col (27 -> 32 channels) for conv1_1 as a K=32 GEMM, + MSE partial sums
+//   prep_bwd  : col2im of the conv1_1 input gradient, / scale, + MSE gradient  -> d(img) fp32 NCHW
+//   maxpool   : 2x2 NHWC forward / backward (backward also adds the LPIPS tap gradient and applies the ReLU mask)
+//   head      : channel-unit-normalise, squared difference to the cached target features, 1x1 `lin`, spatial mean (fwd + bwd)
+//   adam      : Adam with coupled L2 on the [B,17,32] latents, lr / noise schedule read from device arrays (graph-capturable)
+#include "common.cuh"
+
+namespace mgf {
+
+__constant__ float c_shift[3] = {-.030f, -.088f, -.188f};
+__constant__ float c_scale[3] = {.458f, .448f, .450f};
+
+// one thread per pixel: reads the 3x3x3 neighbourhood (L1/L2 cached), writes 64 bytes
+__global__ void __launch_bounds__(256) lpips_prep_kernel(const float* img, const float* target, __nv_bfloat16* col, float* mse, int R, int do_col) {
+  const int b = blockIdx.y;
+  const long long HW = (long long)R * R;
+  float local = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(p / R), x = (int)(p % R);
+    const float* ib = img + (long long)b * 3 * HW;
+    if (target) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) { const float d = ib[c * HW + p] - target[((long long)b * 3 + c) * HW + p]; local = fmaf(d, d, local); }
+    }
+    if (do_col) {
+      float v[32];
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        const bool in = yy >= 0 && yy < R && xx >= 0 && xx < R;
+#pragma unroll
+        for (int c = 0; c < 3; c++) v[t * 3 + c] = in ? (__ldg(ib + c * HW + (long long)yy * R + xx) - c_shift[c]) / c_scale[c] : 0.f;
+      }
+#pragma unroll
+      for (int j = 27; j < 32; j++) v[j] = 0.f;
+      uint4* op = reinterpret_cast<uint4*>(col + ((long long)b * HW + p) * 32);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        uint4 u;
+        u.x = pack_bf16(v[q * 8], v[q * 8 + 1]); u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+        u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        op[q] = u;
+      }
+    }
+  }
+  if (target) {
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(&mse[b], local);
+  }
+}
+
+// dimg[b,c,Y,X] = (1/scale_c) * sum_t dcol[b, Y-dy_t, X-dx_t, t*3+c] + mcoef * (img - target)
+__global__ void __launch_bounds__(256) lpips_prep_bwd_kernel(const __nv_bfloat16* dcol, const float* img, const float* target, float mcoef,
+                                                             float* dimg, int R) {
+  const int b = blockIdx.y;
+  const long long HW = (long long)R * R;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    const int Y = (int)(p / R), X = (int)(p % R);
+    float g[3] = {0.f, 0.f, 0.f};
+    if (dcol) {
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        const int yy = Y - (t / 3 - 1), xx = X - (t % 3 - 1);
+        if (yy >= 0 && yy < R && xx >= 0 && xx < R) {
+          const __nv_bfloat16* cp = dcol + ((long long)b * HW + (long long)yy * R + xx) * 32 + t * 3;
+#pragma unroll
+          for (int c = 0; c < 3; c++) g[c] += __bfloat162float(cp[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const long long o = ((long long)b * 3 + c) * HW + p;
+      float v = g[c] / c_scale[c];
+      if (target) v = fmaf(mcoef, img[o] - target[o], v);
+      dimg[o] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, int H, int W, int C) {
+  const int b = blockIdx.y, vecs = C / 8, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)Ho * Wo * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vecs); long long t = i / vecs;
+    const int xo = (int)(t % Wo), yo = (int)(t / Wo);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) m[e] = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C + cv * 8));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); m[e * 2] = fmaxf(m[e * 2], f.x); m[e * 2 + 1] = fmaxf(m[e * 2 + 1], f.y); }
+    }
+    uint4 o;
+    o.x = pack_bf16(m[0], m[1]); o.y = pack_bf16(m[2], m[3]); o.z = pack_bf16(m[4], m[5]); o.w = pack_bf16(m[6], m[7]);
+    *reinterpret_cast<uint4*>(y + (((long long)b * Ho + yo) * Wo + xo) * C + cv * 8) = o;
+  }
+}
+
+// dx[b,y,x,c] = ((first arg-max of the 2x2 window ? dy : 0) + extra) * (x > 0)      (x is a post-ReLU tensor)
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* extra,
+                                                           __nv_bfloat16* dx, int H, int W, int C) {
+  const int b = blockIdx.y, vecs = C / 8, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)Ho * Wo * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vecs); long long t = i / vecs;
+    const int xo = (int)(t % Wo), yo = (int)(t / Wo);
+    float v[4][8], g[8];
+    {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)b * Ho + yo) * Wo + xo) * C + cv * 8));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); g[e * 2] = f.x; g[e * 2 + 1] = f.y; }
+    }
+    long long off[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      off[k] = (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C + cv * 8;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off[k]));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); v[k][e * 2] = f.x; v[k][e * 2 + 1] = f.y; }
+    }
+    int arg[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      int a = 0; float m = v[0][e];
+#pragma unroll
+      for (int k = 1; k < 4; k++) if (v[k][e] > m) { m = v[k][e]; a = k; }
+      arg[e] = a;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) o[e] = (arg[e] == k) ? g[e] : 0.f;
+      if (extra) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(extra + off[k]));
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); o[e * 2] += f.x; o[e * 2 + 1] += f.y; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) o[e] = v[k][e] > 0.f ? o[e] : 0.f;
+      uint4 u;
+      u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dx + off[k]) = u;
+    }
+  }
+}
+
+// warp per pixel.  mode 0: n1 = f/(|f|+eps) (target caching).  mode 1: val[b] += (1/HW) sum_c lin_c (f_c/(|f|+eps) - n1_c)^2.
+// mode 2: backward, df = coef[b]/HW * (g/(r+eps) - (g.f) f / (r (r+eps)^2)), g = 2 lin (n0 - n1); optional relu mask (df *= f > 0).
+template <int MODE>
+__global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f, const __nv_bfloat16* n1, const float* lin, const float* coef,
+                                                         __nv_bfloat16* outp, float* val, long long HW, int C, int relu_mask) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int vecs = C / 8;
+  const float eps = 1e-10f;
+  float vsum = 0.f;
+  const float cf = (MODE == 2) ? coef[b] / (float)HW : 0.f;
+  for (long long p = (long long)blockIdx.x * 8 + warp; p < HW; p += (long long)gridDim.x * 8) {
+    const long long row = ((long long)b * HW + p) * C;
+    float ss = 0.f, dot = 0.f;
+    // pass 1: norm
+    for (int vi = lane; vi < vecs; vi += 32) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + vi);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); }
+    }
+    ss = warp_sum(ss);
+    const float r = sqrtf(ss), inv = 1.f / (r + eps);
+    if (MODE == 0) {
+      for (int vi = lane; vi < vecs; vi += 32) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + vi);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); o4[e] = pack_bf16(q.x * inv, q.y * inv); }
+        reinterpret_cast<uint4*>(outp + row)[vi] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+      continue;
+    }
+    // pass 2 (row is L1-resident): weighted squared difference, and g.f for the backward
+    for (int vi = lane; vi < vecs; vi += 32) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + vi);
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(n1 + row) + vi);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w}, t4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float2 q = unpack_bf16(w4[e]), n = unpack_bf16(t4[e]);
+        const float l0 = lin[vi * 8 + e * 2], l1 = lin[vi * 8 + e * 2 + 1];
+        const float d0 = q.x * inv - n.x, d1 = q.y * inv - n.y;
+        if (MODE == 1) { vsum = fmaf(l0 * d0, d0, vsum); vsum = fmaf(l1 * d1, d1, vsum); }
+        else { dot = fmaf(2.f * l0 * d0, q.x, dot); dot = fmaf(2.f * l1 * d1, q.y, dot); }
+      }
+    }
+    if (MODE == 2) {
+      dot = warp_sum(dot);
+      const float k2 = (r > 0.f) ? dot * inv * inv / r : 0.f;
+      for (int vi = lane; vi < vecs; vi += 32) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + vi);
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(n1 + row) + vi);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w}, t4[4] = {t.x, t.y, t.z, t.w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 q = unpack_bf16(w4[e]), n = unpack_bf16(t4[e]);
+          const float l0 = lin[vi * 8 + e * 2], l1 = lin[vi * 8 + e * 2 + 1];
+          float g0 = cf * (2.f * l0 * (q.x * inv - n.x) * inv - k2 * q.x);
+          float g1 = cf * (2.f * l1 * (q.y * inv - n.y) * inv - k2 * q.y);
+          if (relu_mask) { g0 = q.x > 0.f ? g0 : 0.f; g1 = q.y > 0.f ? g1 : 0.f; }
+          o4[e] = pack_bf16(g0, g1);
+        }
+        reinterpret_cast<uint4*>(outp + row)[vi] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+  if (MODE == 1) {
+    vsum = warp_sum(vsum);
+    if (lane == 0) atomicAdd(&val[b], vsum / (float)HW);
+  }
+}
+
+// Adam (coupled L2, torch.optim.Adam semantics) on n latent floats, then the next step's noisy latent.
+// sched[step] = {lr, noise_strength_next}; step read from a device counter (so the whole step can live in a CUDA graph).
+__global__ void __launch_bounds__(256) adam_noise_kernel(float* latent, const float* grad, float* m, float* v, const float* noise_all,
+                                                         int noise_rows, float* latent_n, const float* sched, const int* step_ptr,
+                                                         float beta1, float beta2, float eps, float wd, long long n) {
+  const int step = *step_ptr;                 // 0-based index of the step being applied
+  const float lr = sched[2 * step], ns = sched[2 * step + 1];
+  const float t = (float)(step + 1);
+  const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
+  const float* noise_next = (noise_all && step + 1 < noise_rows) ? noise_all + (long long)(step + 1) * n : nullptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float p = latent[i];
+    const float g = grad[i] + wd * p;
+    const float mi = beta1 * m[i] + (1.f - beta1) * g;
+    const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p -= (lr / bc1) * (mi / denom);
+    latent[i] = p;
+    if (latent_n) latent_n[i] = p + (noise_next ? noise_next[i] * ns : 0.f);
+  }
+}
+__global__ void step_inc_kernel(int* step_ptr) { if (threadIdx.x == 0 && blockIdx.x == 0) *step_ptr += 1; }
+
+static inline unsigned gridp(long long work, int waves = 8) {
+  long long blocks = (work + 255) / 256; const long long cap = (long long)num_sms() * waves;
+  if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1; return (unsigned)blocks;
+}
+}  // namespace mgf
+
+using namespace mgf;
+
+extern "C" int mgf_lpips_prep(const float* img, const float* target, void* col, float* mse, int B, int R, void* stream) {
+  if (!img || (!col && !target) || (target && !mse)) MGF_FAIL(MGF_E_BADARG, "lpips_prep: null tensor");
+  dim3 grid(gridp((long long)R * R), B);
+  lpips_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, target, (__nv_bfloat16*)col, mse, R, col != nullptr);
+  MGF_CHECK_LAUNCH("lpips_prep");
+  return 0;
+}
+extern "C" int mgf_lpips_prep_bwd(const void* dcol, const float* img, const float* target, float mcoef, float* dimg, int B, int R, void* stream) {
+  if (!dimg || (target && !img)) MGF_FAIL(MGF_E_BADARG, "lpips_prep_bwd: null tensor");
+  dim3 grid(gridp((long long)R * R), B);
+  lpips_prep_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, img, target, mcoef, dimg, R);
+  MGF_CHECK_LAUNCH("lpips_prep_bwd");
+  return 0;
+}
+extern "C" int mgf_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  if (!x || !y) MGF_FAIL(MGF_E_BADARG, "maxpool2_fwd: null tensor");
+  if (C % 8 || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "maxpool2_fwd: C%%8, H%%2, W%%2 must be 0");
+  dim3 grid(gridp((long long)(H / 2) * (W / 2) * (C / 8)), B);
+  maxpool2_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C);
+  MGF_CHECK_LAUNCH("maxpool2_fwd");
+  return 0;
+}
+extern "C" int mgf_maxpool2_bwd(const void* x, const void* dy, const void* extra, void* dx, int B, int H, int W, int C, void* stream) {
+  if (!x || !dy || !dx) MGF_FAIL(MGF_E_BADARG, "maxpool2_bwd: null tensor");
+  if (C % 8 || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "maxpool2_bwd: C%%8, H%%2, W%%2 must be 0");
+  dim3 grid(gridp((long long)(H / 2) * (W / 2) * (C / 8)), B);
+  maxpool2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)extra, (__nv_bfloat16*)dx, H, W, C);
+  MGF_CHECK_LAUNCH("maxpool2_bwd");
+  return 0;
+}
+extern "C" int mgf_lpips_head(int mode, const void* f, const void* n1, const float* lin, const float* coef, void* out, float* val,
+                              int relu_mask, int B, int64_t HW, int C, void* stream) {
+  if (!f || (mode != 0 && (!n1 || !lin)) || (mode != 1 && !out) || (mode == 1 && !val) || (mode == 2 && !coef)) MGF_FAIL(MGF_E_BADARG, "lpips_head: null tensor");
+  if (C % 8) MGF_FAIL(MGF_E_SHAPE, "lpips_head: C must be a multiple of 8");
+  long long blocks = (HW + 7) / 8; const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16 *fp = (const __nv_bfloat16*)f, *np = (const __nv_bfloat16*)n1;
+  if (mode == 0) lpips_head_kernel<0><<<grid, 256, 0, st>>>(fp, np, lin, coef, (__nv_bfloat16*)out, val, HW, C, relu_mask);
+  else if (mode == 1) lpips_head_kernel<1><<<grid, 256, 0, st>>>(fp, np, lin, coef, (__nv_bfloat16*)out, val, HW, C, relu_mask);
+  else if (mode == 2) lpips_head_kernel<2><<<grid, 256, 0, st>>>(fp, np, lin, coef, (__nv_bfloat16*)out, val, HW, C, relu_mask);
+  else MGF_FAIL(MGF_E_BADARG, "lpips_head: mode %d", mode);
+  MGF_CHECK_LAUNCH("lpips_head");
+  return 0;
+}
+extern "C" int mgf_adam_noise_step(float* latent, const float* grad, float* m, float* v, const float* noise_all, int noise_rows, float* latent_n,
+                                   const float* sched, int* step_ptr, float beta1, float beta2, float eps, float weight_decay, int64_t n, void* stream) {
+  if (!latent || !grad || !m || !v || !sched || !step_ptr) MGF_FAIL(MGF_E_BADARG, "adam_noise_step: null tensor");
+  adam_noise_kernel<<<gridp(n, 1), 256, 0, (cudaStream_t)stream>>>(latent, grad, m, v, noise_all, noise_rows, latent_n, sched, step_ptr, beta1, beta2, eps, weight_decay, n);
+  MGF_CHECK_LAUNCH("adam_noise_step");
+  step_inc_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_ptr);
+  MGF_CHECK_LAUNCH("adam_noise_step(step)");
+  return 0;
+}
