@@ -1,0 +1,432 @@
+"""bf16 tcgen05 synthesis engine: G.synthesis(ws) forward and its explicit backward wrt ws.
+
+Host orchestration only -- every arithmetic step is a kernel of libmgf_sm100a.so called through the C ABI
+(include/mgf.h): tcgen05 implicit-GEMM convolutions (mgf_conv_tc), fused duplex attention (mgf_attn_*), and the
+HBM-bound helpers (style/demod, weight modulation, ToRGB, FIR up-sampling, activation backward).
+PyTorch supplies device memory, the stream and the autograd hook (one torch.autograd.Function around the whole
+synthesis network so the (tiny) mapping network can stay in eager PyTorch).
+
+Dataflow (reference training/networks.py:1244-1264, :1132-1174, :1010-1042, :252-328), activations NHWC bf16:
+  per layer   s = affine(w_global) ; d = rsqrt(sum (w s)^2 + 1e-8)                       mgf_style_fwd
+              Wf[b] = bf16(W * s[b] * d[b])   (demodulation folded into the weight tile)  mgf_modulate_weights
+              y = conv3x3(x, Wf[b])           (up-conv: 4 output phases, FIR folded in)    mgf_conv_tc  (+ noise/bias/lrelu epilogue)
+              attention layers (res <= 128):  z = lrelu(xn(y) * (1 + A VM + bm) + noise + b)  mgf_attn_fwd
+  resnet skip v = conv1x1(x_in) ; x_out = z1 + sqrt(.5) * FIRup2(v)                        mgf_conv_tc + mgf_upfir2_add
+  last block  yl = conv_last ; img = ToRGB(yl) (fp32 NCHW)                                  mgf_conv_tc + mgf_torgb_fwd
+Backward mirrors it with dgrad convs (the same kernel on transposed weights; up-conv dgrad = 36 taps over 4 strided phase
+views), d(styles) reduced in the dgrad epilogue (sum_p dxs * x), d(demod) from R[b,o] = sum_p dy * y.
+"""
+import ctypes
+import math
+import numpy as np
+import torch
+
+from . import _lib, tc
+
+SQRT2 = math.sqrt(2.0)
+SQRT_HALF = math.sqrt(0.5)
+LRELU_ALPHA = 0.2
+
+
+def _L():
+    return _lib.lib()
+
+
+def _s(dev):
+    return _lib.stream_ptr(dev)
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+# ------------------------------------------------------------------------------------------------ host-side constant folding
+def up_phase_matrix(f1d=(1, 3, 3, 1)):
+    """Cm[ph, t, k]: the up-sampling conv (conv_transpose2d stride 2 with the un-flipped 3x3 weights, then upfirdn2d(pad=1, gain=4),
+    reference conv2d_resample.py:117-134 as called from SynthesisLayer with up=2, padding=1, flip_weight=False) written as
+       y[2m+py, 2n+px] = sum_{t=(ty,tx)} sum_{k=(ky,kx)} Cm[ph, t, k] * w[k] * x[m+ty-1, n+tx-1],   ph = 2*py + px.
+    Computed numerically from the impulse response (pure numpy, no learned data involved)."""
+    f = np.asarray(f1d, dtype=np.float64)
+    f2 = np.outer(f, f); f2 /= f2.sum()
+    fflip = f2[::-1, ::-1] * 4.0          # upfirdn2d: true convolution (flipped taps), gain = up^2
+    H = 7; c = 3                           # impulse at (c, c) of an HxH input
+    Cm = np.zeros((4, 9, 9))
+    for ky in range(3):
+        for kx in range(3):
+            ct = np.zeros((2 * H + 1, 2 * H + 1))
+            ct[2 * c + ky, 2 * c + kx] = 1.0                       # conv_transpose2d, stride 2, padding 0: out[2m+ky] += x[m] w[ky]
+            pad = np.pad(ct, 1)
+            out = np.zeros((2 * H, 2 * H))
+            for fy in range(4):
+                for fx in range(4):
+                    out += pad[fy:fy + 2 * H, fx:fx + 2 * H] * fflip[fy, fx]
+            for py in range(2):
+                for px in range(2):
+                    for ty in range(3):
+                        for tx in range(3):
+                            m, n = c - (ty - 1), c - (tx - 1)      # output low-res position whose window tap (ty,tx) hits the impulse
+                            Cm[2 * py + px, ty * 3 + tx, ky * 3 + kx] = out[2 * m + py, 2 * n + px]
+            # the response must be fully covered by the 3x3 windows of the four phases
+            cover = np.zeros_like(out)
+            for ty in range(3):
+                for tx in range(3):
+                    m, n = c - (ty - 1), c - (tx - 1)
+                    cover[2 * m:2 * m + 2, 2 * n:2 * n + 2] = 1
+            assert np.abs(out * (1 - cover)).max() < 1e-12, "up-conv response leaves the 3x3 low-res window"
+    return Cm
+
+
+def _fc_gain(fc):
+    return float(fc.w_gain), float(fc.b_gain)
+
+
+class _Layer:
+    """Frozen, pre-folded parameters of one SynthesisLayer (+ its attention) on the device."""
+    pass
+
+
+class SynthesisEngine:
+    def __init__(self, synthesis):
+        self.net = synthesis
+        self.dev = next(synthesis.parameters()).device
+        if self.dev.type != "cuda":
+            raise _lib.MgfError("SynthesisEngine needs the module on a CUDA device (no CPU fallback)")
+        if synthesis.architecture != "resnet":
+            raise NotImplementedError("tc engine: only the resnet architecture of the GANformer-default generator is built")
+        self.res = synthesis.img_res
+        self.k = synthesis.k
+        self.num_ws = synthesis.num_ws
+        self.Cm = torch.from_numpy(up_phase_matrix()).float()
+        self.blocks = []
+        self._states = {}
+        self.refresh()
+
+    # -------------------------------------------------------------------------------------------- weight folding
+    @torch.no_grad()
+    def refresh(self):
+        """(Re)fold all weights; call again if the module's parameters change."""
+        dev = self.dev
+        self.blocks = []
+        w_idx = 0
+        for r in self.net.block_resolutions:
+            blk = getattr(self.net, f"b{r}")
+            e = {"res": r, "stem": blk.stem, "last": blk.is_last}
+            if blk.stem:
+                e["const"] = blk.const.detach().float().permute(1, 2, 0).contiguous().to(torch.bfloat16)   # [4,4,C]
+                e["conv1"] = self._fold_layer(blk.conv1, w_idx, gain=1.0); w_idx += 1
+            else:
+                e["conv0"] = self._fold_layer(blk.conv0, w_idx, gain=1.0); w_idx += 1
+                e["conv1"] = self._fold_layer(blk.conv1, w_idx, gain=SQRT_HALF); w_idx += 1
+                wsk = (blk.skip.weight.detach().float() * float(blk.skip.w_gain))[:, :, 0, 0]                 # [O, I]
+                e["skip_f"] = wsk.reshape(1, 1, *wsk.shape).to(torch.bfloat16).contiguous()                    # [1,1,O,I]
+                e["skip_b"] = wsk.t().reshape(1, 1, wsk.shape[1], wsk.shape[0]).to(torch.bfloat16).contiguous()  # [1,1,I,O]
+                f1 = np.array([1, 3, 3, 1], dtype=np.float64); f1 = f1 / f1.sum()
+                e["fk4"] = (ctypes.c_float * 4)(*[float(v) for v in f1[::-1]])
+                e["skip_gain"] = 4.0 * SQRT_HALF
+            if blk.is_last:
+                e["conv_last"] = self._fold_layer(blk.conv_last, w_idx, gain=1.0); w_idx += 1
+                tr = blk.torgb
+                C = tr.weight.shape[1]
+                e["rgb"] = dict(idx=w_idx, C=C, w=tr.weight.detach().float().reshape(3, C).contiguous(),
+                                A=tr.affine.weight.detach().float().contiguous(), ab=(tr.affine.bias.detach().float() * float(tr.affine.b_gain)).contiguous(),
+                                again=float(tr.affine.w_gain), sgain=float(tr.w_gain), bias=tr.biasAct.bias.detach().float().contiguous())
+            self.blocks.append(e)
+        self.pos = None
+
+    def _fold_layer(self, m, idx, gain):
+        dev = self.dev
+        L = _Layer()
+        L.idx, L.up, L.res = idx, m.up, m.out_res
+        W = (m.weight.detach().float() * float(m.w_gain))           # [O, I, 3, 3]
+        O, I = W.shape[:2]
+        L.O, L.I = O, I
+        L.Wsq = W.square().sum(dim=[2, 3]).contiguous()              # [O, I]
+        Wk = W.reshape(O, I, 9)
+        if m.up == 1:
+            L.Bf = Wk.permute(2, 0, 1).contiguous()                  # [9, O, I]
+            L.Bb = Wk.permute(2, 1, 0).contiguous()                  # [9, I, O]
+            L.taps_f = [(0, ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+            L.taps_b = [(0, 1 - ky, 1 - kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+            L.phases = 1
+        else:
+            Weff = torch.einsum("ptk,oik->ptoi", self.Cm.to(dev), Wk)                  # [4, 9, O, I]
+            L.Bf = Weff.permute(1, 0, 2, 3).reshape(9, 4 * O, I).contiguous()           # [9, 4*O, I]
+            L.Bb = Weff.permute(0, 1, 3, 2).reshape(36, I, O).contiguous()              # [36, I, O]
+            L.taps_f = [(0, ty - 1, tx - 1, ty * 3 + tx) for ty in range(3) for tx in range(3)]
+            L.taps_b = [(ph, 1 - ty, 1 - tx, ph * 9 + ty * 3 + tx) for ph in range(4) for ty in range(3) for tx in range(3)]
+            L.phases = 4
+        L.A = m.affine.weight.detach().float().contiguous()          # [I, 32]
+        L.ab = (m.affine.bias.detach().float() * float(m.affine.b_gain)).contiguous()
+        L.again = float(m.affine.w_gain)
+        L.has_noise = bool(m.local_noise)
+        L.noise = m.noise_const.detach().float().contiguous() if m.local_noise else None
+        L.nstr = m.noise_strength.detach().float().reshape(1).contiguous() if m.local_noise else None
+        L.has_bias = m.biasAct is not None
+        L.bias = (m.biasAct.bias.detach().float() * float(m.biasAct.b_gain)).contiguous() if L.has_bias else None
+        L.gain = SQRT2 * gain if L.has_bias else 1.0
+        L.attn = m.transformer is not None
+        if L.attn:
+            t = m.transformer
+            if not (t.kmeans and t.parametric and t.num_heads == 1 and t.integration == "mul" and t.norm == "layer"):
+                raise NotImplementedError("tc engine: attention variant outside the GANformer-default configuration")
+            C = O
+            rs = 1.0 / math.sqrt(float(t.size_head))
+            Wq = t.to_queries.weight.detach().float() * float(t.to_queries.w_gain)
+            bq = t.to_queries.bias.detach().float() * float(t.to_queries.b_gain)
+            aw = t.att_weight.detach().float().reshape(-1)
+            cen = t.centroids.detach().float()[0, 0]                                      # [16, 2C]
+            awc1, awc2 = cen[:, :C] * aw[:C], cen[:, C:] * aw[C:]
+            L.Kf = ((awc1 @ Wq) * rs).contiguous()                                        # [16, C]
+            gp = m.grid_pos.detach().float().reshape(-1, m.grid_pos.shape[-1])           # [HW, 32]
+            P = gp @ (t.from_pos_map.weight.detach().float() * float(t.from_pos_map.w_gain)).t() + t.from_pos_map.bias.detach().float() * float(t.from_pos_map.b_gain)
+            L.Sc = (((awc1 @ bq).unsqueeze(0) + P @ awc2.t()) * rs).contiguous()          # [HW, 16]
+            Wv = t.to_values.weight.detach().float() * float(t.to_values.w_gain)          # [C, 32]
+            bv = t.to_values.bias.detach().float() * float(t.to_values.b_gain)
+            Wm = t.modulation.weight.detach().float() * float(t.modulation.w_gain)        # [C, C]
+            L.WVM = (Wm @ Wv).contiguous()                                                # [C, 32]
+            L.bVM = (Wm @ bv).contiguous()
+            L.WVMt = L.WVM.t().contiguous()                                               # [32, C]
+            L.bm = (t.modulation.bias.detach().float() * float(t.modulation.b_gain)).contiguous()
+        return L
+
+    # -------------------------------------------------------------------------------------------- buffers
+    def _buf(self, st, name, shape, dtype=torch.bfloat16, zero=False):
+        t = st.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
+            st[name] = t
+        return t
+
+    def _state(self, B):
+        st = self._states.get(B)
+        if st is None:
+            st = {}
+            self._states[B] = st
+        return st
+
+    # -------------------------------------------------------------------------------------------- kernels
+    def _styles(self, L, ws, st, B):
+        s = self._buf(st, f"s{L.idx}", (B, L.I), torch.float32)
+        d = self._buf(st, f"d{L.idx}", (B, L.O), torch.float32)
+        wg = ws[:, -1, L.idx]                                   # [B, 32] strided view
+        _lib.check(_L().mgf_style_fwd(_p(wg), wg.stride(0), _p(L.A), _p(L.ab), L.again, 1.0, _p(L.Wsq), _p(s), _p(d),
+                                      B, L.I, L.O, wg.shape[1], _s(self.dev)), "mgf_style_fwd")
+        return s, d
+
+    def _modulate(self, base, rs, nmod, cs, out, B):
+        T, NT, K = base.shape
+        _lib.check(_L().mgf_modulate_weights(_p(base), _p(rs), nmod, _p(cs), _p(out), B, T, NT, K, _s(self.dev)), "mgf_modulate_weights")
+
+    def _layer_fwd(self, L, x_in, ws, maskbias, st, B, noise_on, add=None):
+        """x_in [B,h,w,I] bf16 -> z [B,H,W,O] bf16 (post noise/bias/act)."""
+        s, d = self._styles(L, ws, st, B)
+        Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape))
+        self._modulate(L.Bf, d, L.O, s, Wf, B)
+        h, w = x_in.shape[1], x_in.shape[2]
+        H, Wd = h * L.up, w * L.up
+        st[f"xin{L.idx}"] = x_in
+        noise = L.noise if (L.has_noise and noise_on) else None
+        nstr = L.nstr if noise is not None else None
+        kw = dict(osy=L.up, osx=L.up, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1))
+        if L.attn:
+            y = self._buf(st, f"y{L.idx}", (B, H, Wd, L.O))
+            tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, **kw)
+            VM = self._buf(st, f"VM{L.idx}", (B, 16, L.O), torch.float32)
+            comps = ws[:, :-1, L.idx]                           # [B,16,32] strided
+            _lib.check(_L().mgf_small_gemm(_p(comps), comps.stride(0), comps.stride(1), _p(L.WVM), _p(L.bVM), _p(VM),
+                                           16 * L.O, L.O, B, 16, L.O, comps.shape[2], 0, _s(self.dev)), "mgf_small_gemm")
+            z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O))
+            _lib.check(_L().mgf_attn_fwd(_p(y), _p(L.Kf), _p(L.Sc), _p(maskbias), _p(VM), _p(L.bm), _p(noise), _p(nstr), _p(L.bias),
+                                         L.gain, LRELU_ALPHA, _p(z), None, B, H * Wd, L.O, _s(self.dev)), "mgf_attn_fwd")
+        else:
+            z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O))
+            tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, z, noise=noise, noise_strength=nstr, bias=L.bias,
+                       act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, add=add, **kw)
+        return z
+
+    # -------------------------------------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward_raw(self, ws, mask=None, noise_mode="const"):
+        if noise_mode not in ("const", "none"):
+            raise NotImplementedError("tc engine: noise_mode='random' (per-sample noise planes) is not built; use 'const' or 'none'")
+        B = ws.shape[0]
+        st = self._state(B)
+        ws = ws.detach().to(torch.float32).contiguous()
+        st["ws"] = ws
+        if mask is None:
+            mask = torch.ones(B, self.k - 1, device=self.dev)
+        maskbias = ((1.0 - mask.to(torch.float32)) * -10000.0).contiguous()
+        st["maskbias"] = maskbias
+        st["noise_on"] = noise_on = noise_mode == "const"
+        x = None
+        for e in self.blocks:
+            r = e["res"]
+            if e["stem"]:
+                x_in = self._buf(st, "const", (B,) + tuple(e["const"].shape))
+                x_in.copy_(e["const"].unsqueeze(0).expand(B, -1, -1, -1))
+                x = self._layer_fwd(e["conv1"], x_in, ws, maskbias, st, B, noise_on)
+            else:
+                x_in = x
+                z0 = self._layer_fwd(e["conv0"], x_in, ws, maskbias, st, B, noise_on)
+                z1 = self._layer_fwd(e["conv1"], z0, ws, maskbias, st, B, noise_on)
+                O, I = e["conv0"].O, e["conv0"].I
+                h = x_in.shape[1]
+                v = self._buf(st, f"v{r}", (B, h, h, O))
+                tc.conv_tc([x_in], e["skip_f"], [(0, 0, 0, 0)], (B, h, h), 1, O, v)
+                x = self._buf(st, f"xout{r}", (B, r, r, O))
+                _lib.check(_L().mgf_upfir2_add(_p(v), _p(z1), _p(x), e["fk4"], e["skip_gain"], B, h, h, O, _s(self.dev)), "mgf_upfir2_add")
+            if e["last"]:
+                yl = self._layer_fwd(e["conv_last"], x, ws, maskbias, st, B, noise_on)
+                rgb = e["rgb"]
+                srgb = self._buf(st, "s_rgb", (B, rgb["C"]), torch.float32)
+                wg = ws[:, -1, rgb["idx"]]
+                _lib.check(_L().mgf_style_fwd(_p(wg), wg.stride(0), _p(rgb["A"]), _p(rgb["ab"]), rgb["again"], rgb["sgain"], None, _p(srgb), None,
+                                              B, rgb["C"], 0, wg.shape[1], _s(self.dev)), "mgf_style_fwd")
+                img = torch.empty(B, 3, r, r, dtype=torch.float32, device=self.dev)
+                _lib.check(_L().mgf_torgb_fwd(_p(yl), _p(rgb["w"]), _p(srgb), _p(rgb["bias"]), _p(img), B, r * r, rgb["C"], _s(self.dev)), "mgf_torgb_fwd")
+                st["yl"] = yl
+        return img
+
+    # -------------------------------------------------------------------------------------------- backward
+    def _dgrad(self, L, dy, st, B, out, add=None, actgrad_X=None, ag_gain=1.0):
+        """dy [B,H,W,O] (gradient wrt this layer's conv output) -> out [B,h,w,I] = d x_in; accumulates d(styles)."""
+        d = st[f"d{L.idx}"]; s = st[f"s{L.idx}"]
+        Wb = self._buf(st, f"Wb{L.idx}", (B,) + tuple(L.Bb.shape))
+        self._modulate(L.Bb, None, 1, d, Wb, B)
+        x_in = st[f"xin{L.idx}"]
+        h, w = x_in.shape[1], x_in.shape[2]
+        ds = self._buf(st, f"ds{L.idx}", (B, L.I), torch.float32)
+        ds.zero_()
+        acts = [dy] if L.up == 1 else [tc.phase_view(dy, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
+        tc.conv_tc(acts, Wb, L.taps_b, (B, h, w), 1, L.I, out, scale_n=s, reduce_out=ds, X=x_in, add=add,
+                   actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain, reduce_per_sample=True)
+        return ds
+
+    def _style_bwd(self, L, ds, R, st, dws, B):
+        d = st[f"d{L.idx}"]; s = st[f"s{L.idx}"]
+        dwg = dws[:, -1, L.idx]
+        _lib.check(_L().mgf_style_bwd(_p(ds), _p(R), _p(s), _p(d), _p(L.Wsq), _p(L.A), L.again, 1.0, _p(dwg), dwg.stride(0),
+                                      B, L.I, L.O, dwg.shape[1], _s(self.dev)), "mgf_style_bwd")
+
+    def _attn_bwd(self, L, dz, st, dws, B):
+        """dz: gradient wrt the layer output z.  Returns (dy, R): gradient wrt the conv output and sum_p dy*y."""
+        y = st[f"y{L.idx}"]
+        H, Wd = y.shape[1], y.shape[2]
+        noise_on = st["noise_on"]
+        noise = L.noise if (L.has_noise and noise_on) else None
+        nstr = L.nstr if noise is not None else None
+        dy = self._buf(st, f"dy{L.idx}", tuple(y.shape))
+        dVM = self._buf(st, f"dVM{L.idx}", (B, 16, L.O), torch.float32); dVM.zero_()
+        R = self._buf(st, f"R{L.idx}", (B, L.O), torch.float32); R.zero_()
+        _lib.check(_L().mgf_attn_bwd(_p(y), _p(dz), _p(L.Kf), _p(L.Sc), _p(st["maskbias"]), _p(st[f"VM{L.idx}"]), _p(L.bm), _p(noise), _p(nstr),
+                                     _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), B, H * Wd, L.O, _s(self.dev)), "mgf_attn_bwd")
+        dcomp = dws[:, :-1, L.idx]                                 # [B,16,32] strided, accumulate
+        _lib.check(_L().mgf_small_gemm(_p(dVM), 16 * L.O, L.O, _p(L.WVMt), None, _p(dcomp), dcomp.stride(0), dcomp.stride(1),
+                                       B, 16, dcomp.shape[2], L.O, 1, _s(self.dev)), "mgf_small_gemm")
+        return dy, R
+
+    def _act_bwd(self, L, dz, z, st, B, mode, want_dy=True):
+        H, Wd = z.shape[1], z.shape[2]
+        noise_on = st["noise_on"]
+        noise = L.noise if (L.has_noise and noise_on) else None
+        nstr = L.nstr if noise is not None else None
+        dy = self._buf(st, f"dy{L.idx}", tuple(z.shape)) if want_dy else None
+        R = self._buf(st, f"R{L.idx}", (B, L.O), torch.float32); R.zero_()
+        _lib.check(_L().mgf_act_bwd(_p(dz), _p(z), _p(dy), _p(R), _p(noise), _p(nstr), _p(L.bias), LRELU_ALPHA, L.gain, mode,
+                                    B, H * Wd, L.O, _s(self.dev)), "mgf_act_bwd")
+        return dy, R
+
+    @torch.no_grad()
+    def backward_raw(self, dimg):
+        """dimg [B,3,R,R] fp32 -> dws [B,k,num_ws,32] fp32 (gradient wrt the ws passed to the last forward_raw)."""
+        B = dimg.shape[0]
+        st = self._state(B)
+        ws = st["ws"]
+        dws = torch.zeros_like(ws)
+        dimg = dimg.to(torch.float32).contiguous()
+        g = None
+        for e in reversed(self.blocks):
+            r = e["res"]
+            if e["last"]:
+                rgb = e["rgb"]; Ll = e["conv_last"]
+                yl = st["yl"]
+                dyl = self._buf(st, "dyl", tuple(yl.shape))
+                ds_rgb = self._buf(st, "ds_rgb", (B, rgb["C"]), torch.float32); ds_rgb.zero_()
+                R_last = self._buf(st, f"R{Ll.idx}", (B, Ll.O), torch.float32); R_last.zero_()
+                _lib.check(_L().mgf_torgb_bwd(_p(dimg), _p(yl), _p(rgb["w"]), _p(st["s_rgb"]), _p(dyl), _p(ds_rgb), _p(R_last),
+                                              B, r * r, rgb["C"], _s(self.dev)), "mgf_torgb_bwd")
+                dwg = dws[:, -1, rgb["idx"]]
+                _lib.check(_L().mgf_style_bwd(_p(ds_rgb), None, None, None, None, _p(rgb["A"]), rgb["again"], rgb["sgain"], _p(dwg), dwg.stride(0),
+                                              B, rgb["C"], 0, dwg.shape[1], _s(self.dev)), "mgf_style_bwd")
+                g = self._buf(st, f"g{r}", tuple(st[f"xin{Ll.idx}"].shape))
+                ds = self._dgrad(Ll, dyl, st, B, g)
+                self._style_bwd(Ll, ds, R_last, st, dws, B)
+            if e["stem"]:
+                L1 = e["conv1"]
+                dy1, R1 = self._attn_bwd(L1, g, st, dws, B) if L1.attn else self._act_bwd(L1, g, st[f"z{L1.idx}"], st, B, 0)
+                scratch = self._buf(st, "gconst", tuple(st[f"xin{L1.idx}"].shape))
+                ds1 = self._dgrad(L1, dy1, st, B, scratch)
+                self._style_bwd(L1, ds1, R1, st, dws, B)
+                continue
+            L0, L1 = e["conv0"], e["conv1"]
+            x_in = st[f"xin{L0.idx}"]
+            h = x_in.shape[1]
+            # skip branch: d v = FIR^T(g) ; d x_in (skip part) = conv1x1^T
+            dv = self._buf(st, f"dv{r}", (B, h, h, L0.O))
+            _lib.check(_L().mgf_upfir2_bwd(_p(g), _p(dv), e["fk4"], e["skip_gain"], B, h, h, L0.O, _s(self.dev)), "mgf_upfir2_bwd")
+            gs = self._buf(st, f"gs{r}", tuple(x_in.shape))
+            tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs)
+            # conv1
+            z0 = st[f"z{L0.idx}"]
+            dy1, R1 = self._attn_bwd(L1, g, st, dws, B) if L1.attn else self._act_bwd(L1, g, st[f"z{L1.idx}"], st, B, 0)
+            dz0 = self._buf(st, f"dz{L0.idx}", tuple(z0.shape))
+            if L0.attn:
+                ds1 = self._dgrad(L1, dy1, st, B, dz0)
+                dy0, R0 = self._attn_bwd(L0, dz0, st, dws, B)
+            else:
+                # fuse conv0's leaky-ReLU backward into conv1's dgrad epilogue (X = z0 is both conv1's input and conv0's output)
+                ds1 = self._dgrad(L1, dy1, st, B, dz0, actgrad_X=z0, ag_gain=L0.gain)
+                dy0 = dz0
+                _, R0 = self._act_bwd(L0, dy0, z0, st, B, 1, want_dy=False)
+            self._style_bwd(L1, ds1, R1, st, dws, B)
+            # conv0 (up) dgrad, adding the skip-branch gradient in the epilogue -> gradient wrt the previous block's output
+            gprev = self._buf(st, f"g{r // 2}", tuple(x_in.shape))
+            ds0 = self._dgrad(L0, dy0, st, B, gprev, add=gs)
+            self._style_bwd(L0, ds0, R0, st, dws, B)
+            g = gprev
+        return dws
+
+    # -------------------------------------------------------------------------------------------- autograd entry
+    def __call__(self, ws, pos=None, mask=None, noise_mode="const", fused_modconv=None, **_ignored):
+        return _SynthesisFn.apply(ws, self, mask, noise_mode)
+
+
+class _SynthesisFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ws, eng, mask, noise_mode):
+        ctx.eng = eng
+        ctx.B = ws.shape[0]
+        return eng.forward_raw(ws, mask=mask, noise_mode=noise_mode)
+
+    @staticmethod
+    def backward(ctx, dimg):
+        return ctx.eng.backward_raw(dimg), None, None, None
+
+
+def smoke():
+    """tiny tc-engine forward+backward on cuda:0 (called from __graft_entry__.smoke)."""
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import util
+    G = util.build_G(64, 0, 2048, 64).cuda()
+    G.synthesis.engine = "tc"
+    ws = torch.randn(2, 17, G.num_ws, 32, device="cuda", requires_grad=True)
+    img, _ = G.synthesis(ws, pos=G.pos, mask=torch.ones(2, 16, device="cuda"), noise_mode="const")
+    img.square().mean().backward()
+    torch.cuda.synchronize()
+    G.synthesis.engine = "ops"
+    ref, _ = G.synthesis(ws.detach(), pos=G.pos, mask=torch.ones(2, 16, device="cuda"), noise_mode="const", return_att_maps=False)
+    err = (img.detach() - ref).abs().max().item()
+    assert err < 5e-2, "tc engine deviates from the ops engine: %g" % err
+    print("smoke ok: tc engine 64x64 fwd+bwd, max|img_tc - img_fp32| = %.3g, |dws| = %.3g" % (err, ws.grad.abs().max().item()))

@@ -1,0 +1,65 @@
+"""GPU parity: the bf16 tcgen05 engine behind G.synthesis (engine='tc') against the oracle (CPU fp32 restatement of the
+reference).  north_star tolerance for bf16 images: 1e-2 max-abs.  Gradients wrt ws: relative to the largest entry."""
+import numpy as np
+import pytest
+import torch
+from oracle import ganformer
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(res, cb, cm, B, seed=0):
+    G = util.build_G(res, seed, cb, cm)
+    sd = util.state_dict_cpu(G)
+    ws = util.case_tensor((B, 17, G.num_ws, 32), 11)
+    mask = torch.ones(B, 16)
+    return G, sd, ws, mask
+
+
+@pytest.mark.parametrize("cfg", [(64, 2048, 64, 2), (32, 32768, 128, 3)])
+def test_tc_engine_image_within_bf16_tolerance(cfg):
+    res, cb, cm, B = cfg
+    G, sd, ws, mask = _setup(res, cb, cm, B)
+    ref = ganformer.synthesis(sd, ws, sd["pos"], mask, res)
+    Gc = G.cuda(); Gc.synthesis.engine = "tc"
+    img, att = Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=mask.cuda(), noise_mode="const")
+    assert img.dtype == torch.float32 and tuple(img.shape) == (B, 3, res, res)
+    err = (img.cpu() - ref).abs().max().item()
+    print("img max-abs err", err, "scale", ref.abs().max().item())
+    assert err < 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_tc_engine_grads_wrt_ws():
+    res, cb, cm, B = 64, 2048, 64, 2
+    G, sd, ws, mask = _setup(res, cb, cm, B)
+    wsr = ws.clone().requires_grad_(True)
+    ref = ganformer.synthesis(sd, wsr, sd["pos"], mask, res)
+    tgt = torch.tanh(util.case_tensor(ref.shape, 12))
+    gref, = torch.autograd.grad((ref - tgt).square().mean(), [wsr])
+    Gc = G.cuda(); Gc.synthesis.engine = "tc"
+    wsg = ws.cuda().requires_grad_(True)
+    img, _ = Gc.synthesis(wsg, pos=Gc.pos, mask=mask.cuda(), noise_mode="const")
+    g, = torch.autograd.grad((img - tgt.cuda()).square().mean(), [wsg])
+    g = g.cpu()
+    scale = gref.abs().max().item()
+    err = (g - gref).abs().max().item()
+    # per-slot report helps locating a wrong layer
+    for l in range(G.num_ws):
+        e = (g[:, :, l] - gref[:, :, l]).abs().max().item(); s = gref[:, :, l].abs().max().item()
+        print("ws slot %2d  err %.3e  scale %.3e" % (l, e, s))
+    assert err < 3e-2 * scale, "dws err %g vs scale %g" % (err, scale)
+    cos = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
+    assert cos > 0.999, cos
+
+
+def test_tc_engine_noise_none_and_mask():
+    res, cb, cm, B = 64, 2048, 64, 2
+    G, sd, ws, mask = _setup(res, cb, cm, B)
+    mask[1, 5] = 0
+    ref = ganformer.synthesis(sd, ws, sd["pos"], mask, res, noise_mode="none")
+    Gc = G.cuda(); Gc.synthesis.engine = "tc"
+    img, _ = Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=mask.cuda(), noise_mode="none")
+    assert (img.cpu() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    with pytest.raises(NotImplementedError):
+        Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=mask.cuda(), noise_mode="random")

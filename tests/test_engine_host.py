@@ -1,0 +1,79 @@
+"""CPU: host-side constant folding of the bf16 engine against the oracle ops (no GPU needed)."""
+import math
+import numpy as np
+import torch
+import torch.nn.functional as F
+from oracle import ops as O
+import util
+
+
+def test_up_phase_matrix_reproduces_reference_upconv():
+    from morphganformer_b200.engine import up_phase_matrix
+    Cm = torch.from_numpy(up_phase_matrix()).float()                 # [4, 9, 9]
+    x = util.case_tensor((2, 5, 7, 6), 1)
+    w = util.case_tensor((4, 5, 3, 3), 2) * 0.3
+    f = O.setup_filter([1, 3, 3, 1])
+    ref = O.conv2d_resample(x, w, f=f, up=2, padding=1, flip_weight=False)
+    Weff = torch.einsum("ptk,oik->ptoi", Cm, w.reshape(4, 5, 9))     # [4, 9, O, I]
+    out = torch.zeros_like(ref)
+    for ph in range(4):
+        py, px = ph // 2, ph % 2
+        wk = Weff[ph].reshape(3, 3, 4, 5).permute(2, 3, 0, 1)        # [O, I, ty, tx] correlation taps
+        out[:, :, py::2, px::2] = F.conv2d(x, wk, padding=1)
+    assert (out - ref).abs().max() < 1e-5
+
+
+def test_skip_path_formula():
+    """1x1 conv then FIR up2 with flipped normalised taps and gain 4*sqrt(.5) (what mgf_upfir2_add computes)."""
+    x = util.case_tensor((1, 3, 5, 5), 3)
+    w = util.case_tensor((4, 3, 1, 1), 4)
+    f = O.setup_filter([1, 3, 3, 1])
+    ref = O.bias_act(O.conv2d_resample(x, w, f=f, up=2, padding=0, flip_weight=False), None, act="linear", gain=math.sqrt(0.5))
+    v = F.conv2d(x, w)
+    fk = (np.array([1, 3, 3, 1.0]) / 8)[::-1].copy()
+    h = 5
+    out = torch.zeros(1, 4, 10, 10)
+    for Y in range(10):
+        for X in range(10):
+            acc = 0
+            for fy in range(Y & 1, 4, 2):
+                iy = (Y + fy - 2) >> 1
+                if iy < 0 or iy >= h:
+                    continue
+                for fx in range(X & 1, 4, 2):
+                    ix = (X + fx - 2) >> 1
+                    if ix < 0 or ix >= h:
+                        continue
+                    acc = acc + fk[fy] * fk[fx] * v[:, :, iy, ix]
+            out[:, :, Y, X] = acc * 4 * math.sqrt(0.5)
+    assert (out - ref).abs().max() < 1e-5
+
+
+def test_attention_fold_matches_oracle_layer():
+    """S = X Kf^T + Sc and ctl = A VM + bm reproduce TransformerLayer.forward (oracle restatement) in fp64."""
+    from oracle import ganformer
+    G = util.build_G(32, 0, 512, 32)
+    sd = {k: v.double() for k, v in util.state_dict_cpu(G).items()}
+    pre = "synthesis.b8.conv1"
+    C, HW = 32, 64
+    X = util.case_tensor((2, HW, C), 5).double()
+    Y = util.case_tensor((2, 16, 32), 6).double()
+    mask = torch.ones(2, 16).double(); mask[1, 3] = 0
+    ref, probs = ganformer.transformer_layer(sd, pre + ".transformer", X, Y, sd[pre + ".grid_pos"], sd["pos"], mask.unsqueeze(1), HW, 16)
+    t = pre + ".transformer"
+    rs = 1 / math.sqrt(C)
+    Wq = sd[t + ".to_queries.weight"] / math.sqrt(C); bq = sd[t + ".to_queries.bias"]
+    aw = sd[t + ".att_weight"].reshape(-1); cen = sd[t + ".centroids"][0, 0]
+    a1, a2 = cen[:, :C] * aw[:C], cen[:, C:] * aw[C:]
+    Kf = (a1 @ Wq) * rs
+    P = sd[pre + ".grid_pos"].reshape(-1, 32) @ (sd[t + ".from_pos_map.weight"] / math.sqrt(32)).t() + sd[t + ".from_pos_map.bias"]
+    Sc = ((a1 @ bq).unsqueeze(0) + P @ a2.t()) * rs
+    S = X @ Kf.t() + Sc + ((1 - mask) * -10000.0).unsqueeze(1)
+    A = torch.softmax(S, -1)
+    assert (A - probs[:, 0]).abs().max() < 1e-9
+    Wv = sd[t + ".to_values.weight"] / math.sqrt(32); bv = sd[t + ".to_values.bias"]
+    Wm = sd[t + ".modulation.weight"] / math.sqrt(C); bm = sd[t + ".modulation.bias"]
+    VM = Y @ (Wm @ Wv).t() + Wm @ bv
+    ctl = A @ VM + bm
+    xn = X * torch.rsqrt(X.square().mean(-1, keepdim=True) + 1e-8)
+    assert (xn * (1 + ctl) - ref).abs().max() < 1e-9
