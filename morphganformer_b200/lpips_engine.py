@@ -1,0 +1,203 @@
+"""LPIPS-VGG16 perceptual distance on the tcgen05 convolution kernel, forward and backward wrt the generated image.
+
+Mirrors lpips.PerceptualLoss(model='net-lin', net='vgg') of the reference (lpips/__init__.py:13-41 -> dist_model.py:110-118 ->
+networks_basic.py:64-92; VGG16 slices pretrained_networks.py:97-135): ScalingLayer, 13 conv3x3+ReLU, 4 max-pools, five taps,
+channel-unit-normalisation, squared difference, 1x1 `lin` layers, spatial mean, sum over taps.  The target branch is constant
+during a projection, so its normalised tap features are computed once (set_target) instead of every step as the reference does.
+Also produces the MSE term of the projection loss in the same pass over the image (1024_example_percept_MSE.py:143).
+
+Everything arithmetic is a kernel of libmgf_sm100a.so: mgf_lpips_prep (scale + im2col of the 3-channel input so conv1_1 runs as
+a K=32 GEMM), mgf_conv_tc (all convolutions and their input gradients, bias+ReLU and ReLU-mask fused in the epilogue),
+mgf_maxpool2_*, mgf_lpips_head.
+"""
+import torch
+from . import _lib, tc
+
+# (cin, cout) per conv; 'P' = 2x2 max-pool.  Taps (relu1_2, relu2_2, relu3_3, relu4_3, relu5_3) follow conv indices 1,3,6,9,12.
+VGG = [(3, 64), (64, 64), "P", (64, 128), (128, 128), "P", (128, 256), (256, 256), (256, 256), "P",
+       (256, 512), (512, 512), (512, 512), "P", (512, 512), (512, 512), (512, 512)]
+TAP_AFTER = {1: 0, 3: 1, 6: 2, 9: 3, 12: 4}
+REF_NAMES = ["net.slice1.0", "net.slice1.2", "net.slice2.5", "net.slice2.7", "net.slice3.10", "net.slice3.12", "net.slice3.14",
+             "net.slice4.17", "net.slice4.19", "net.slice4.21", "net.slice5.24", "net.slice5.26", "net.slice5.28"]
+TAPS_B = [(0, 1 - ky, 1 - kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+
+
+def _L():
+    return _lib.lib()
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+class LpipsEngine:
+    def __init__(self, state_dict, device="cuda"):
+        """state_dict: reference PNetLin naming (net.sliceK.N.weight/bias, linK.model.1.weight)."""
+        self.dev = torch.device(device)
+        self.wf, self.wb, self.bias = [], [], []
+        for i, name in enumerate(REF_NAMES):
+            w = state_dict[name + ".weight"].detach().float().to(self.dev)          # [O, I, 3, 3]
+            b = state_dict[name + ".bias"].detach().float().to(self.dev).contiguous()
+            O, I = w.shape[:2]
+            if i == 0:
+                wc = torch.zeros(O, 32, device=self.dev)
+                wc[:, :27] = w.permute(0, 2, 3, 1).reshape(O, 27)                    # column index = (ky*3+kx)*3 + c
+                self.wf.append(wc.reshape(1, 1, O, 32).to(torch.bfloat16).contiguous())
+                self.wb.append(wc.t().reshape(1, 1, 32, O).to(torch.bfloat16).contiguous())
+            else:
+                wk = w.reshape(O, I, 9)
+                self.wf.append(wk.permute(2, 0, 1).reshape(1, 9, O, I).to(torch.bfloat16).contiguous())
+                self.wb.append(wk.permute(2, 1, 0).reshape(1, 9, I, O).to(torch.bfloat16).contiguous())
+            self.bias.append(b)
+        self.lin = [state_dict[f"lin{k}.model.1.weight"].detach().float().reshape(-1).to(self.dev).contiguous() for k in range(5)]
+        self._st = {}
+        self.n1 = None
+
+    def _buf(self, name, shape, dtype=torch.bfloat16):
+        t = self._st.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            self._st[name] = t
+        return t
+
+    def _features(self, img, target, mse, tag):
+        """Runs the VGG trunk; returns the list of conv outputs h[i] (post-ReLU, NHWC bf16) and pooled tensors."""
+        B, _, R, _ = img.shape
+        s = _lib.stream_ptr(self.dev)
+        col = self._buf(tag + "col", (B, R, R, 32))
+        _lib.check(_L().mgf_lpips_prep(_p(img), _p(target), _p(col), _p(mse), B, R, s), "mgf_lpips_prep")
+        h, x, res, ci = [], col, R, 0
+        pooled = {}
+        for item in VGG:
+            if item == "P":
+                y = self._buf(f"{tag}p{ci}", (B, res // 2, res // 2, x.shape[3]))
+                _lib.check(_L().mgf_maxpool2_fwd(_p(x), _p(y), B, res, res, x.shape[3], s), "mgf_maxpool2_fwd")
+                pooled[ci] = y
+                x, res = y, res // 2
+                continue
+            cin, cout = item
+            y = self._buf(f"{tag}h{ci}", (B, res, res, cout))
+            taps = [(0, 0, 0, 0)] if ci == 0 else tc.TAPS_3X3
+            tc.conv_tc([x], self.wf[ci], taps, (B, res, res), 1, cout, y, bias=self.bias[ci], act=2, gain=1.0)
+            h.append(y)
+            x = y
+            ci += 1
+        return h, pooled, col
+
+    @torch.no_grad()
+    def set_target(self, target):
+        """target [B,3,R,R] fp32 in [-1,1]; caches the unit-normalised tap features (the reference recomputes them every step)."""
+        target = target.to(self.dev, torch.float32).contiguous()
+        self.target = target
+        B = target.shape[0]
+        h, _, _ = self._features(target, None, None, "t")
+        self.n1 = []
+        s = _lib.stream_ptr(self.dev)
+        for ci, k in TAP_AFTER.items():
+            f = h[ci]
+            n = torch.empty_like(f)
+            _lib.check(_L().mgf_lpips_head(0, _p(f), None, None, None, _p(n), None, 0, B, f.shape[1] * f.shape[2], f.shape[3], s), "mgf_lpips_head")
+            self.n1.append(n)
+        for key in [k for k in self._st if k.startswith("t")]:
+            del self._st[key]
+
+    @torch.no_grad()
+    def forward(self, img, want_mse=True):
+        """img [B,3,R,R] fp32 -> (lpips [B], mse_sum [B] = sum of squared differences to the target)."""
+        assert self.n1 is not None, "call set_target first"
+        img = img.contiguous()
+        B = img.shape[0]
+        s = _lib.stream_ptr(self.dev)
+        val = self._buf("val", (B,), torch.float32); val.zero_()
+        mse = self._buf("mse", (B,), torch.float32); mse.zero_()
+        h, pooled, col = self._features(img, self.target if want_mse else None, mse if want_mse else None, "g")
+        self.h, self.pooled, self.img = h, pooled, img
+        for ci, k in TAP_AFTER.items():
+            f = h[ci]
+            _lib.check(_L().mgf_lpips_head(1, _p(f), _p(self.n1[k]), _p(self.lin[k]), None, None, _p(val), 0, B, f.shape[1] * f.shape[2], f.shape[3], s), "mgf_lpips_head")
+        return val, mse
+
+    @torch.no_grad()
+    def backward(self, coef, mse_coef):
+        """coef [B] fp32 = d(loss)/d(lpips_b); mse_coef = d(loss)/d(mse_sum_b) * 2 (scalar).  Returns d(loss)/d(img) fp32 NCHW."""
+        h, B = self.h, self.img.shape[0]
+        s = _lib.stream_ptr(self.dev)
+        R = self.img.shape[2]
+
+        def head_bwd(ci, relu_mask):
+            f = h[ci]; k = TAP_AFTER[ci]
+            out = self._buf(f"df{ci}", tuple(f.shape))
+            _lib.check(_L().mgf_lpips_head(2, _p(f), _p(self.n1[k]), _p(self.lin[k]), _p(coef), _p(out), None, int(relu_mask), B,
+                                           f.shape[1] * f.shape[2], f.shape[3], s), "mgf_lpips_head")
+            return out
+
+        # walk the trunk backwards; `g` is always the gradient wrt the PRE-activation of conv `ci` (ReLU mask already applied)
+        g = head_bwd(12, True)
+        ci = 12
+        items = [it for it in VGG]
+        # conv index -> is it directly preceded by a pool?
+        pos = len(items) - 1
+        while ci >= 1:
+            res = h[ci].shape[1]
+            cin = VGG_CIN[ci]
+            prev_is_pool = items[pos - 1] == "P"
+            if prev_is_pool:
+                # d(pooled input) -> route through the pool to conv ci-1's output, add its tap gradient, apply its ReLU mask
+                dp = self._buf(f"dp{ci}", (B, res, res, cin))
+                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, dp)
+                src = h[ci - 1]
+                extra = head_bwd(ci - 1, False) if (ci - 1) in TAP_AFTER else None
+                g2 = self._buf(f"dpre{ci - 1}", tuple(src.shape))
+                _lib.check(_L().mgf_maxpool2_bwd(_p(src), _p(dp), _p(extra), _p(g2), B, src.shape[1], src.shape[2], src.shape[3], s), "mgf_maxpool2_bwd")
+                g = g2
+                pos -= 2
+            else:
+                src = h[ci - 1]
+                g2 = self._buf(f"dpre{ci - 1}", tuple(src.shape))
+                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, g2, X=src, actgrad=True, ag_alpha=0.0, ag_gain=1.0)
+                g = g2
+                pos -= 1
+            ci -= 1
+        dcol = self._buf("dcol", (B, R, R, 32))
+        tc.conv_tc([g], self.wb[0], [(0, 0, 0, 0)], (B, R, R), 1, 32, dcol)
+        dimg = torch.empty_like(self.img)
+        _lib.check(_L().mgf_lpips_prep_bwd(_p(dcol), _p(self.img), _p(self.target), float(mse_coef), _p(dimg), B, R, s), "mgf_lpips_prep_bwd")
+        return dimg
+
+
+VGG_CIN = [c[0] for c in VGG if c != "P"]
+
+
+class PerceptualLoss(torch.nn.Module):
+    """API mirror of lpips.PerceptualLoss (reference lpips/__init__.py:13-41) for model='net-lin', net='vgg':
+    forward(pred, target) -> [N,1,1,1], differentiable wrt pred.  The target features are cached per target tensor."""
+
+    def __init__(self, state_dict, model="net-lin", net="vgg", use_gpu=True, **_unused):
+        super().__init__()
+        if model != "net-lin" or net not in ("vgg", "vgg16"):
+            raise NotImplementedError("only the LPIPS-VGG16 ('net-lin', 'vgg') variant is built (SURVEY.md 8f rank 2)")
+        self.engine = LpipsEngine(state_dict)
+        self._target_key = None
+
+    def forward(self, pred, target, normalize=False):
+        if normalize:
+            target, pred = 2 * target - 1, 2 * pred - 1
+        key = (target.data_ptr(), tuple(target.shape), target._version)
+        if key != self._target_key:
+            self.engine.set_target(target)
+            self._target_key = key
+        return _LpipsFn.apply(pred, self.engine).reshape(-1, 1, 1, 1)
+
+
+class _LpipsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, eng):
+        val, _ = eng.forward(pred.detach().float(), want_mse=False)
+        ctx.eng = eng
+        return val.clone()
+
+    @staticmethod
+    def backward(ctx, dval):
+        eng = ctx.eng
+        dimg = eng.backward(dval.contiguous().float(), 0.0)
+        return dimg, None

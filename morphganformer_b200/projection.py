@@ -1,0 +1,143 @@
+"""Per-image latent projection: Adam on the z latents [B,17,32] against lamda * LPIPS-VGG + (1 - lamda) * MSE.
+
+Restates the loop of the reference scripts (1024_example_percept_MSE.py:113-175; get_lr :62-67, latent_noise :70-72, latent
+statistics :212-216) with the gradient actually flowing through G (the reference detaches the image through NumPy, SURVEY.md
+section 0-4 -- the intended loop is built here, matching oracle/projection.py).  All images of a batch are independent jobs
+(per-image mean MSE, per-image LPIPS), so a batch can be sharded over GPUs with no per-step collective.
+
+One step = mapping network (eager PyTorch, ~0.1 MFLOP/img) -> tcgen05 synthesis engine forward -> LPIPS/MSE forward ->
+LPIPS/MSE backward -> synthesis backward -> mapping backward -> fused Adam + next-step latent noise (mgf_adam_noise_step).
+No host synchronisation inside a step: the lr / noise schedule lives in a device array indexed by a device step counter.
+"""
+import math
+import torch
+from . import _lib
+from .lpips_engine import LpipsEngine
+
+
+def get_lr(t, initial_lr, rampdown=0.25, rampup=0.05):
+    lr_ramp = min(1.0, (1.0 - t) / rampdown)
+    lr_ramp = 0.5 - 0.5 * math.cos(lr_ramp * math.pi)
+    return initial_lr * lr_ramp * min(1.0, t / rampup)
+
+
+def latent_stats(noise_sample):
+    mean = noise_sample.mean(0)
+    std = ((noise_sample - mean).pow(2).sum() / noise_sample.shape[0]) ** 0.5
+    return mean, std
+
+
+class Projector:
+    def __init__(self, G, lpips_state_dict, batch, steps, lr=0.1, lamda=0.5, noise=0.05, noise_ramp=0.75, lr_rampdown=0.25,
+                 lr_rampup=0.05, weight_decay=1e-4, latent_mean=None, latent_std=None, use_lpips=True, step_noise=None,
+                 noise_seed=3):
+        self.G = G
+        self.dev = next(G.parameters()).device
+        if self.dev.type != "cuda":
+            raise _lib.MgfError("Projector needs the generator on a CUDA device (no CPU fallback)")
+        G.synthesis.engine = "tc"
+        G.eval().requires_grad_(False)
+        self.B, self.steps, self.lamda, self.use_lpips = batch, steps, float(lamda), use_lpips
+        self.wd = float(weight_decay)
+        k, zd = G.k, G.z_dim
+        if latent_mean is None:
+            g = torch.Generator(device="cpu").manual_seed(1234)
+            latent_mean, latent_std = latent_stats(torch.randn(10000, k, zd, generator=g))
+        self.latent_mean = latent_mean.to(self.dev, torch.float32)
+        self.latent_std = float(latent_std)
+        # schedule: sched[i] = (lr of step i, noise strength of step i+1)
+        sched = []
+        for i in range(steps):
+            t, t1 = i / steps, (i + 1) / steps
+            ns1 = self.latent_std * noise * max(0.0, 1.0 - t1 / noise_ramp) ** 2
+            sched += [get_lr(t, lr, lr_rampdown, lr_rampup), ns1]
+        self.ns0 = self.latent_std * noise
+        self.sched = torch.tensor(sched, dtype=torch.float32, device=self.dev)
+        if step_noise is None:
+            g = torch.Generator(device=self.dev).manual_seed(noise_seed)
+            step_noise = torch.randn(steps, batch, k, zd, generator=g, device=self.dev)
+        self.step_noise = step_noise.to(self.dev, torch.float32).contiguous()
+        self.lp = LpipsEngine(lpips_state_dict, self.dev) if use_lpips else None
+        self.mask = torch.ones(batch, k - 1, device=self.dev)
+        self.reset()
+
+    def reset(self):
+        B = self.B
+        self.latent = self.latent_mean.unsqueeze(0).repeat(B, 1, 1).contiguous()
+        self.m = torch.zeros_like(self.latent)
+        self.v = torch.zeros_like(self.latent)
+        self.latent_n = (self.latent + self.step_noise[0] * self.ns0).contiguous()
+        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.losses = torch.zeros(self.steps, B, device=self.dev)
+        self.best_loss = torch.full((B,), float("inf"), device=self.dev)
+        self.best_latent = self.latent_n.clone()
+        self.i = 0
+
+    def set_targets(self, target):
+        """target [B,3,R,R] fp32 in [-1,1] (device or host)."""
+        self.target = target.to(self.dev, torch.float32).contiguous()
+        assert self.target.shape[0] == self.B
+        if self.lp is not None:
+            self.lp.set_target(self.target)
+        self.coef = torch.full((self.B,), self.lamda if self.use_lpips else 0.0, device=self.dev)
+
+    def _loss_and_grad(self, img):
+        R = img.shape[2]
+        n = 3 * R * R
+        if self.use_lpips:
+            val, mse_sum = self.lp.forward(img)
+            per_img = self.lamda * val + (1 - self.lamda) * mse_sum / n
+            dimg = self.lp.backward(self.coef, (1 - self.lamda) * 2.0 / n)
+        else:
+            lib, s = _lib.lib(), _lib.stream_ptr(self.dev)
+            mse_sum = torch.zeros(self.B, device=self.dev)
+            _lib.check(lib.mgf_lpips_prep(img.data_ptr(), self.target.data_ptr(), None, mse_sum.data_ptr(), self.B, R, s), "mgf_lpips_prep")
+            per_img = mse_sum / n
+            dimg = torch.empty_like(img)
+            _lib.check(lib.mgf_lpips_prep_bwd(None, img.data_ptr(), self.target.data_ptr(), 2.0 / n, dimg.data_ptr(), self.B, R, s), "mgf_lpips_prep_bwd")
+        return per_img, dimg
+
+    def step(self):
+        """One projection step for the whole batch; no host sync.  Returns the per-image loss tensor (device)."""
+        G = self.G
+        z = self.latent_n.detach().requires_grad_(True)
+        with torch.enable_grad():
+            ws = G.mapping(z, None, pos=G.pos, mask=self.mask)
+        eng = self._engine()
+        img = eng.forward_raw(ws, mask=self.mask, noise_mode="const")
+        per_img, dimg = self._loss_and_grad(img)
+        dws = eng.backward_raw(dimg)
+        (gz,) = torch.autograd.grad(ws, [z], grad_outputs=[dws])
+        # best-so-far bookkeeping (reference: keep latent_n of the lowest-loss step, :155-158)
+        better = per_img < self.best_loss
+        self.best_loss = torch.where(better, per_img, self.best_loss)
+        self.best_latent = torch.where(better.reshape(-1, 1, 1), self.latent_n, self.best_latent)
+        if self.i < self.steps:
+            self.losses[self.i] = per_img
+        lib = _lib.lib()
+        _lib.check(lib.mgf_adam_noise_step(self.latent.data_ptr(), gz.contiguous().data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                           self.step_noise.data_ptr(), self.steps, self.latent_n.data_ptr(), self.sched.data_ptr(),
+                                           self.step_ctr.data_ptr(), 0.9, 0.999, 1e-8, self.wd, self.latent.numel(),
+                                           _lib.stream_ptr(self.dev)), "mgf_adam_noise_step")
+        self.i += 1
+        self.last_img = img
+        return per_img
+
+    def _engine(self):
+        syn = self.G.synthesis
+        if syn._tc is None:
+            from . import engine as _engine
+            syn._tc = _engine.SynthesisEngine(syn)
+        return syn._tc
+
+    def run(self, steps=None):
+        for _ in range(steps or self.steps):
+            self.step()
+        return dict(latent=self.latent, best_latent=self.best_latent, best_loss=self.best_loss, losses=self.losses)
+
+
+def interpolate_pair(G, z1, z2, alpha=0.5):
+    """Pair morph (projection_example_v2_percept_morph.py:356-363): W = (1-alpha) z1 + alpha z2, then one forward."""
+    z = (1 - alpha) * z1 + alpha * z2
+    with torch.no_grad():
+        return G(z, noise_mode="const")[0]

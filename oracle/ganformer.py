@@ -168,7 +168,7 @@ def synthesis_layer(sd, pre, x, w, pos, mask, out_res, up=1, gain=1.0, attention
 
 
 def synthesis(sd, ws, pos, mask, res, architecture="resnet", end_res=8, noise_mode="const", return_att=False,
-              dtype=torch.float32):
+              dtype=torch.float32, trace=None):
     """SynthesisNetwork.forward networks.py:1244-1264 + SynthesisBlock.forward :1132-1174 (resnet architecture,
     const stem, ToRGB only on the last block).  ws [B,k,num_ws,w_dim]."""
     assert architecture == "resnet"
@@ -191,6 +191,8 @@ def synthesis(sd, ws, pos, mask, res, architecture="resnet", end_res=8, noise_mo
             x, a = synthesis_layer(sd, pre + ".conv1", x, ws[:, :, w_idx], pos, mask, r, attention=attn,
                                    noise_mode=noise_mode, f=f)
             atts.append(a)
+            if trace is not None:
+                trace[f"z{w_idx}"] = x
             w_idx += 1
         else:
             wsk = sd[pre + ".skip.weight"]
@@ -199,10 +201,16 @@ def synthesis(sd, ws, pos, mask, res, architecture="resnet", end_res=8, noise_mo
             y = ops.bias_act(y, None, act="linear", gain=math.sqrt(0.5))
             x, a0 = synthesis_layer(sd, pre + ".conv0", x, ws[:, :, w_idx], pos, mask, r, up=2, attention=attn,
                                     noise_mode=noise_mode, f=f)
+            if trace is not None:
+                trace[f"z{w_idx}"] = x
             x, a1 = synthesis_layer(sd, pre + ".conv1", x, ws[:, :, w_idx + 1], pos, mask, r, gain=math.sqrt(0.5),
                                     attention=attn, noise_mode=noise_mode, f=f)
             atts += [a0, a1]
+            if trace is not None:
+                trace[f"z{w_idx + 1}"] = x
             x = y + x
+            if trace is not None:
+                trace[f"xout{r}"] = x
             w_idx += 2
         if last:
             x, _ = synthesis_layer(sd, pre + ".conv_last", x, ws[:, :, w_idx], pos, mask, r, attention=False,
