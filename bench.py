@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: latent projection at 1024x1024 (MSE + LPIPS-VGG, Adam on the z latents), images*steps/sec.
+
+  python bench.py --gpus N --steps K --warmup W          # N>1: launched under torch.distributed.run, one rank per GPU
+  python bench.py --impl reference --steps K --warmup W  # the reference algorithm on the host CPU (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[3]): GANformer-default generator at 1024^2 (k=17 x 32-d latents, random-init weights, seed 0),
+LPIPS-VGG16 with torchvision-default random init (seed 4) + the reference's lin weights, lamda 0.5, lr 0.1, weight decay 1e-4,
+8 images per GPU (64 images over 8 GPUs), synthetic tanh(randn) targets.  A "step" is one Adam iteration on the whole batch:
+mapping -> synthesis forward -> LPIPS/MSE forward -> backward of all of it -> fused Adam + latent noise.
+Images are independent jobs: ranks share nothing per step; one NCCL all_gather of the final latents and losses ends the run.
+
+Prints ONE JSON line (rank 0).  `value` = images*steps/s with everything resident in HBM; `e2e` = the same loop driven through
+the public Projector API from host buffers (targets + per-step noise uploaded from pinned memory, per-step losses read back).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "projection_images_steps_per_sec_1024"
+UNIT = "images*steps/s"
+RES = 1024
+PER_GPU_BATCH = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--res", type=int, default=RES)
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
+    ap.add_argument("--no-lpips", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-res", type=int, default=None, help="resolution of the CPU baseline sample (default: same as --res)")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return "latent_projection_%d_%s_adam_b%d_per_gpu" % (args.res, "mse" if args.no_lpips else "mse+lpips_vgg", args.batch)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        hi = [v for v in sm if smax and v > 0.5 * smax] or sm
+        return {"sm_mhz": statistics.median(hi) if hi else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_projection_step_time(res, steps, warmup, use_lpips=True):
+    """One image x one projection step of the reference algorithm (oracle/projection.py restatement, PyTorch CPU fp32, all host
+    threads), timed per step.  Returns (seconds per image*step list, cores)."""
+    import torch
+    import util
+    from oracle import ganformer, lpips_ref, projection as oproj
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    G = util.build_G(res, 0)
+    gsd = util.state_dict_cpu(G)
+    lsd = util.build_vgg_lpips_sd(4) if use_lpips else None
+    mean, std = oproj.latent_stats(util.case_tensor((2000, 17, 32), 70))
+    tgt = torch.tanh(util.case_tensor((1, 3, res, res), 72))
+    latent = mean.clone().unsqueeze(0).requires_grad_(True)
+    opt = torch.optim.Adam([latent], lr=0.1, weight_decay=1e-4)
+    f1 = None
+    if use_lpips:   # the reference recomputes the target branch every step; keep that (it is the reference's cost)
+        pass
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        z = latent + torch.randn_like(latent) * oproj.noise_strength(i / 1000.0, std)
+        img, _ = ganformer.generator(gsd, z, res)
+        mse = (img - tgt).pow(2).mean(dim=[1, 2, 3])
+        loss = 0.5 * lpips_ref.lpips(lsd, img, tgt).reshape(1) + 0.5 * mse if use_lpips else mse
+        opt.zero_grad()
+        loss.sum().backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = args.cpu_res or args.res
+    times, cores = cpu_projection_step_time(res, args.steps, args.warmup, not args.no_lpips)
+    total = sum(times)
+    value = len(times) / total
+    sample = "1 image x 1 Adam step per timed step at %dx%d (same loss, same generator); torch %s CPU fp32" % (res, res, __import__("torch").__version__)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args), "sample_res": res, "sample_batch": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import util
+    from morphganformer_b200 import _lib, tc
+    from morphganformer_b200.projection import Projector, latent_stats
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, R, K, W = args.batch, args.res, args.steps, args.warmup
+    use_lpips = not args.no_lpips
+
+    G = util.build_G(R, 0).to(dev)
+    lsd = util.build_vgg_lpips_sd(4) if use_lpips else None
+    mean, std = latent_stats(util.case_tensor((2000, 17, 32), 70))
+    total_steps = max(1000, W + K + 8)
+    gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    target_host = torch.tanh(torch.randn(B, 3, R, R, generator=gen)).pin_memory()
+    noise_host = torch.randn(W + 2 * K + 8, B, 17, 32, generator=gen).pin_memory()
+    step_noise = torch.zeros(total_steps, B, 17, 32)
+    step_noise[:noise_host.shape[0]] = noise_host
+    P = Projector(G, lsd, B, total_steps, latent_mean=mean, latent_std=std, use_lpips=use_lpips, step_noise=step_noise)
+    P.set_targets(target_host.to(dev))
+    lib = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region
+    for _ in range(W):
+        P.step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.mgf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        P.step()
+    if world > 1:   # the only collective of the job: gather the projected latents and their losses
+        lat = [torch.empty_like(P.best_latent) for _ in range(world)]
+        los = [torch.empty_like(P.best_loss) for _ in range(world)]
+        dist.all_gather(lat, P.best_latent.contiguous())
+        dist.all_gather(los, P.best_loss.contiguous())
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.mgf_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * K / (ms / 1000.0)
+    loss_now = float(P.losses[P.i - 1].mean().item())
+
+    # ---- end-to-end through the public API from host buffers (targets + per-step noise in, per-step losses out)
+    e2e = None
+    if not args.no_e2e:
+        P.reset()
+        barrier()
+        loss_host = torch.empty(B).pin_memory()
+        t0 = time.perf_counter()
+        e0.record()
+        P.set_targets(target_host.to(dev, non_blocking=True))               # target upload is part of a projection job
+        for i in range(K):
+            P.step_noise[P.i + 1].copy_(noise_host[W + K + i], non_blocking=True)   # this step's Adam kernel adds it for step i+1
+            per_img = P.step()
+            loss_host.copy_(per_img, non_blocking=True)
+            torch.cuda.current_stream().synchronize()                       # the caller reads the loss every step (tqdm in the reference)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        t = torch.tensor([ems], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+        h2d = B * 17 * 32 * 4 + target_host.numel() * 4 // K
+        e2e = {"value": world * B * K / (ems / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": B * 4,
+               "ms_per_step": ems / K}
+
+    # ---- roofline of the dominant kernel (conv_tc), measured live with CUDA events on the launching stream (2 extra steps)
+    roof = None
+    if rank == 0:
+        tc.PROFILE = []
+        for _ in range(2):
+            P.step()
+        torch.cuda.synchronize()
+        recs, tc.PROFILE = tc.PROFILE, None
+        tms = sum(a.elapsed_time(b) for (_, a, b, _, _) in recs)
+        alg = sum(r[3] for r in recs)
+        exe = sum(r[4] for r in recs)
+        pk, pk_src = peaks()
+        peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+        ach = alg / (tms / 1000.0) / 1e12
+        by_tag = {}
+        for (tag, a, b, fa, fe) in recs:
+            d = by_tag.setdefault(tag, [0.0, 0.0, 0.0, 0]); d[0] += a.elapsed_time(b); d[1] += fa; d[2] += fe; d[3] += 1
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes of one step)", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " bf16_tflops_sustained",
+                "executed_tflops": exe / (tms / 1000.0) / 1e12, "launches_per_step": len(recs) // 2, "kernel_ms_per_step": tms / 2,
+                "share_of_step": (tms / 2) / (ms / K),
+                "by_group": {k: {"ms_per_step": v[0] / 2, "alg_tflops": v[1] / (v[0] / 1000.0) / 1e12, "launches": v[3] // 2} for k, v in by_tag.items()}}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            cres = args.cpu_res or R
+            times, cores = cpu_projection_step_time(cres, 1, 1, use_lpips)
+            cpu = {"value": len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "1 image x 1 Adam step (after 1 warm-up step) of oracle/projection.py at %dx%d, PyTorch CPU fp32, %d threads" % (cres, cres, cores)}
+        except Exception as ex:   # never lose the GPU line because the host baseline failed
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args), "resolution": R, "images_per_gpu": B, "global_batch": B * world,
+                       "loss": "0.5*LPIPS_vgg16 + 0.5*MSE" if use_lpips else "MSE", "optimizer": "Adam(lr 0.1 schedule, wd 1e-4) on z [B,17,32]",
+                       "parallelism": "image-sharded x%d, no per-step collective" % world,
+                       "l2": "inputs_exceed_l2 (per-layer activations at 1024^2 x 8 images are 0.27-1.07 GB)", "weights": "random-init seed 0"},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "loss_mean_last_step": loss_now,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -230,7 +230,7 @@ class SynthesisEngine:
         kw = dict(osy=L.up, osx=L.up, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1))
         if L.attn:
             y = self._buf(st, f"y{L.idx}", (B, H, Wd, L.O))
-            tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, **kw)
+            tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
             VM = self._buf(st, f"VM{L.idx}", (B, 16, L.O), torch.float32)
             comps = ws[:, :-1, L.idx]                           # [B,16,32] strided
             _lib.check(_L().mgf_small_gemm(_p(comps), comps.stride(0), comps.stride(1), _p(L.WVM), _p(L.bVM), _p(VM),
@@ -241,7 +241,7 @@ class SynthesisEngine:
         else:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O))
             tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, z, noise=noise, noise_strength=nstr, bias=L.bias,
-                       act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, add=add, **kw)
+                       act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, add=add, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
         return z
 
     # -------------------------------------------------------------------------------------------- forward
@@ -272,7 +272,7 @@ class SynthesisEngine:
                 O, I = e["conv0"].O, e["conv0"].I
                 h = x_in.shape[1]
                 v = self._buf(st, f"v{r}", (B, h, h, O))
-                tc.conv_tc([x_in], e["skip_f"], [(0, 0, 0, 0)], (B, h, h), 1, O, v)
+                tc.conv_tc([x_in], e["skip_f"], [(0, 0, 0, 0)], (B, h, h), 1, O, v, tag="g.fwd")
                 x = self._buf(st, f"xout{r}", (B, r, r, O))
                 _lib.check(_L().mgf_upfir2_add(_p(v), _p(z1), _p(x), e["fk4"], e["skip_gain"], B, h, h, O, _s(self.dev)), "mgf_upfir2_add")
             if e["last"]:
@@ -299,7 +299,8 @@ class SynthesisEngine:
         ds.zero_()
         acts = [dy] if L.up == 1 else [tc.phase_view(dy, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
         tc.conv_tc(acts, Wb, L.taps_b, (B, h, w), 1, L.I, out, scale_n=s, reduce_out=ds, X=x_in, add=add,
-                   actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain, reduce_per_sample=True)
+                   actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain, reduce_per_sample=True,
+                   alg_scale=1.0 / L.phases, tag="g.bwd")
         return ds
 
     def _style_bwd(self, L, ds, R, st, dws, B):
@@ -375,7 +376,7 @@ class SynthesisEngine:
             dv = self._buf(st, f"dv{r}", (B, h, h, L0.O))
             _lib.check(_L().mgf_upfir2_bwd(_p(g), _p(dv), e["fk4"], e["skip_gain"], B, h, h, L0.O, _s(self.dev)), "mgf_upfir2_bwd")
             gs = self._buf(st, f"gs{r}", tuple(x_in.shape))
-            tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs)
+            tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd")
             # conv1
             z0 = st[f"z{L0.idx}"]
             dy1, R1 = self._attn_bwd(L1, g, st, dws, B) if L1.attn else self._act_bwd(L1, g, st[f"z{L1.idx}"], st, B, 0)

@@ -78,7 +78,8 @@ class LpipsEngine:
             cin, cout = item
             y = self._buf(f"{tag}h{ci}", (B, res, res, cout))
             taps = [(0, 0, 0, 0)] if ci == 0 else tc.TAPS_3X3
-            tc.conv_tc([x], self.wf[ci], taps, (B, res, res), 1, cout, y, bias=self.bias[ci], act=2, gain=1.0)
+            tc.conv_tc([x], self.wf[ci], taps, (B, res, res), 1, cout, y, bias=self.bias[ci], act=2, gain=1.0,
+                       alg_scale=27.0 / 32.0 if ci == 0 else 1.0, tag="vgg.fwd")
             h.append(y)
             x = y
             ci += 1
@@ -144,7 +145,7 @@ class LpipsEngine:
             if prev_is_pool:
                 # d(pooled input) -> route through the pool to conv ci-1's output, add its tap gradient, apply its ReLU mask
                 dp = self._buf(f"dp{ci}", (B, res, res, cin))
-                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, dp)
+                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, dp, tag="vgg.bwd")
                 src = h[ci - 1]
                 extra = head_bwd(ci - 1, False) if (ci - 1) in TAP_AFTER else None
                 g2 = self._buf(f"dpre{ci - 1}", tuple(src.shape))
@@ -154,12 +155,12 @@ class LpipsEngine:
             else:
                 src = h[ci - 1]
                 g2 = self._buf(f"dpre{ci - 1}", tuple(src.shape))
-                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, g2, X=src, actgrad=True, ag_alpha=0.0, ag_gain=1.0)
+                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, g2, X=src, actgrad=True, ag_alpha=0.0, ag_gain=1.0, tag="vgg.bwd")
                 g = g2
                 pos -= 1
             ci -= 1
         dcol = self._buf("dcol", (B, R, R, 32))
-        tc.conv_tc([g], self.wb[0], [(0, 0, 0, 0)], (B, R, R), 1, 32, dcol)
+        tc.conv_tc([g], self.wb[0], [(0, 0, 0, 0)], (B, R, R), 1, 32, dcol, alg_scale=27.0 / 32.0, tag="vgg.bwd")
         dimg = torch.empty_like(self.img)
         _lib.check(_L().mgf_lpips_prep_bwd(_p(dcol), _p(self.img), _p(self.target), float(mse_coef), _p(dimg), B, R, s), "mgf_lpips_prep_bwd")
         return dimg

@@ -47,9 +47,14 @@ def phase_view(t, py, px):
     return nhwc_view(t[:, py::2, px::2, :])
 
 
+# When set to a list, every launch appends (tag, start_event, end_event, algorithmic_flops, executed_flops); used by bench.py to
+# measure the dominant kernel live with CUDA events on the launching stream.
+PROFILE = None
+
+
 def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 0), ofx=(0, 0, 0, 0), scale_n=None,
             reduce_out=None, X=None, noise=None, noise_strength=None, bias=None, act=0, alpha=0.2, gain=1.0, add=None,
-            actgrad=False, ag_alpha=0.2, ag_gain=1.0, bn=0, reduce_per_sample=False):
+            actgrad=False, ag_alpha=0.2, ag_gain=1.0, bn=0, reduce_per_sample=False, alg_scale=1.0, tag=""):
     """acts: list of NHWC bf16 tensors or descriptor tuples; w: [G, T, NT, K] bf16 contiguous; taps: [(amap, dy, dx, wz)];
     grid: (NB, GH, GW); out: [NB, OH, OW, OC] bf16 contiguous."""
     d = ConvTcDesc()
@@ -78,8 +83,16 @@ def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 
     d.act, d.alpha, d.gain = act, alpha, gain
     d.actgrad, d.ag_alpha, d.ag_gain = int(bool(actgrad)), ag_alpha, ag_gain
     d.bn, d.reduce_per_sample = bn, int(bool(reduce_per_sample))
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().mgf_conv_tc(ctypes.byref(d), _lib.stream_ptr(out.device)), "mgf_conv_tc")
+    if prof is not None:
+        e1.record()
+        ex = 2.0 * d.NB * d.GH * d.GW * (phases * cout) * w.shape[3] * len(taps)
+        prof.append((tag, e0, e1, ex * alg_scale, ex))
     return out
 
 
