@@ -21,60 +21,70 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
   return red[0];
 }
 
-// ---- styles s[b,i] = (wg[b,:] . A[i,:]) * again + abias[i] * bgain, then *sgain; d[b,o] = rsqrt(sum_i s^2 Wsq[o,i] + 1e-8)
-__global__ void __launch_bounds__(256) style_fwd_kernel(const float* wg, long long wg_stride, const float* A, const float* abias,
-                                                        float again, float sgain, const float* Wsq, float* s_out, float* d_out,
-                                                        int Cin, int O, int wdim) {
-  extern __shared__ float sm[];
-  float* s = sm;                 // [Cin]
-  float* w = sm + Cin;           // [wdim]
-  const int b = blockIdx.x;
+// ---- styles s[b,i] = ((wg[b,:] . A[i,:]) * again + abias[i]) * sgain       grid (ceil(Cin/256), B)
+__global__ void __launch_bounds__(256) style_s_kernel(const float* wg, long long wg_stride, const float* A, const float* abias,
+                                                      float again, float sgain, float* s_out, int Cin, int wdim) {
+  __shared__ float w[64];
+  const int b = blockIdx.y;
   for (int j = threadIdx.x; j < wdim; j += blockDim.x) w[j] = wg[(long long)b * wg_stride + j];
   __syncthreads();
-  for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
-    float acc = 0.f;
-    for (int j = 0; j < wdim; j++) acc = fmaf(w[j], A[i * wdim + j], acc);
-    const float v = (acc * again + abias[i]) * sgain;
-    s[i] = v; s_out[(long long)b * Cin + i] = v;
-  }
-  __syncthreads();
-  if (Wsq) {
-    for (int o = threadIdx.x; o < O; o += blockDim.x) {
-      float acc = 0.f;
-      const float* wr = Wsq + (long long)o * Cin;
-      for (int i = 0; i < Cin; i++) acc = fmaf(s[i] * s[i], wr[i], acc);
-      d_out[(long long)b * O + o] = rsqrtf(acc + 1e-8f);
-    }
-  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cin) return;
+  float acc = 0.f;
+  for (int j = 0; j < wdim; j++) acc = fmaf(w[j], A[i * wdim + j], acc);
+  s_out[(long long)b * Cin + i] = (acc * again + abias[i]) * sgain;
+}
+// ---- demodulation d[b,o] = rsqrt(sum_i s[b,i]^2 Wsq[o,i] + 1e-8): one warp per (b,o), coalesced Wsq rows.  grid (ceil(O/8), B)
+__global__ void __launch_bounds__(256) style_d_kernel(const float* s, const float* Wsq, float* d_out, int Cin, int O) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= O) return;
+  const float* sr = s + (long long)b * Cin; const float* wr = Wsq + (long long)o * Cin;
+  float acc = 0.f;
+  for (int i = lane; i < Cin; i += 32) { const float v = sr[i]; acc = fmaf(v * v, wr[i], acc); }
+  acc = warp_sum(acc);
+  if (lane == 0) d_out[(long long)b * O + o] = rsqrtf(acc + 1e-8f);
 }
 
-// backward: ds_total[i] = ds[i] - sum_o R[o] d[o]^2 s[i] Wsq[o,i]   (R[o] = sum_p dy*y, so dL/dd = R/d and dd/ds_i = -d^3 s_i Wsq)
+// backward: ds_total[i] = ds[i] - s[i] * sum_o R[o] d[o]^2 Wsq[o,i]   (R[o] = sum_p dy*y, so dL/dd = R/d and dd/ds_i = -d^3 s_i Wsq)
 //           dwg[j] += sgain * again * sum_i ds_total[i] A[i,j]
+// block = (32 channels i, sample b): 8 warps split the o range, lane = channel (coalesced Wsq columns); partial dwg by atomics.
 __global__ void __launch_bounds__(256) style_bwd_kernel(const float* ds, const float* R, const float* s, const float* d, const float* Wsq,
                                                         const float* A, float again, float sgain, float* dwg, long long dwg_stride,
                                                         int Cin, int O, int wdim) {
-  extern __shared__ float sm[];
-  float* dst = sm;               // [Cin]
-  float* rd2 = sm + Cin;         // [O]
-  __shared__ float red[8];
-  const int b = blockIdx.x;
-  if (R) for (int o = threadIdx.x; o < O; o += blockDim.x) { const float dv = d[(long long)b * O + o]; rd2[o] = R[(long long)b * O + o] * dv * dv; }
-  __syncthreads();
-  for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
-    float t = ds ? ds[(long long)b * Cin + i] : 0.f;
-    if (R) {
-      float acc = 0.f;
-      for (int o = 0; o < O; o++) acc = fmaf(rd2[o], Wsq[(long long)o * Cin + i], acc);
-      t -= acc * s[(long long)b * Cin + i];
+  __shared__ float part[8][32];
+  __shared__ float dst[32];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (R && i < Cin) {
+    for (int o = warp; o < O; o += 8) {
+      const float dv = d[(long long)b * O + o];
+      acc = fmaf(R[(long long)b * O + o] * dv * dv, Wsq[(long long)o * Cin + i], acc);
     }
-    dst[i] = t;
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+    if (i < Cin) {
+      t = ds ? ds[(long long)b * Cin + i] : 0.f;
+      if (R) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) a += part[w][lane];
+        t -= a * s[(long long)b * Cin + i];
+      }
+    }
+    dst[lane] = t;
   }
   __syncthreads();
-  for (int j = 0; j < wdim; j++) {
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < Cin; i += blockDim.x) acc = fmaf(dst[i], A[i * wdim + j], acc);
-    acc = block_sum_256(acc, red);
-    if (threadIdx.x == 0) dwg[(long long)b * dwg_stride + j] += acc * again * sgain;
+  // dwg[j] partial over this block's 32 channels: thread j (< wdim)
+  for (int j = threadIdx.x; j < wdim; j += blockDim.x) {
+    float a = 0.f;
+#pragma unroll 8
+    for (int l = 0; l < 32; l++) { const int ii = blockIdx.x * 32 + l; if (ii < Cin) a = fmaf(dst[l], A[ii * wdim + j], a); }
+    atomicAdd(&dwg[(long long)b * dwg_stride + j], a * again * sgain);
   }
 }
 
@@ -108,6 +118,25 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* A, long lo
     const float* w = Bm + (long long)n * K;
     float acc = bias ? bias[n] : 0.f;
     for (int k = 0; k < K; k++) acc = fmaf(a[k], w[k], acc);
+    float* o = out + (long long)b * sOb + (long long)m * sOm + n;
+    *o = accumulate ? (*o + acc) : acc;
+  }
+}
+
+// long-K variant: one warp per output element, lanes stride over k
+__global__ void __launch_bounds__(256) small_gemm_warp_kernel(const float* A, long long sAb, long long sAm, const float* Bm, const float* bias,
+                                                              float* out, long long sOb, long long sOm, int M, int N, int K, int accumulate) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (e >= M * N) return;
+  const int m = e / N, n = e % N;
+  const float* a = A + (long long)b * sAb + (long long)m * sAm;
+  const float* w = Bm + (long long)n * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(a[k], w[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    acc += bias ? bias[n] : 0.f;
     float* o = out + (long long)b * sOb + (long long)m * sOm + n;
     *o = accumulate ? (*o + acc) : acc;
   }
@@ -329,9 +358,14 @@ using namespace mgf;
 extern "C" int mgf_style_fwd(const float* wg, int64_t wg_stride, const float* A, const float* abias, float again, float sgain,
                              const float* Wsq, float* s_out, float* d_out, int B, int Cin, int O, int wdim, void* stream) {
   if (!wg || !A || !abias || !s_out || (Wsq && !d_out)) MGF_FAIL(MGF_E_BADARG, "style_fwd: null tensor");
+  if (wdim > 64) MGF_FAIL(MGF_E_SHAPE, "style_fwd: w_dim %d > 64", wdim);
   if (B <= 0) return 0;
-  style_fwd_kernel<<<B, 256, (Cin + wdim) * sizeof(float), (cudaStream_t)stream>>>(wg, wg_stride, A, abias, again, sgain, Wsq, s_out, d_out, Cin, O, wdim);
-  MGF_CHECK_LAUNCH("style_fwd");
+  style_s_kernel<<<dim3((Cin + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(wg, wg_stride, A, abias, again, sgain, s_out, Cin, wdim);
+  MGF_CHECK_LAUNCH("style_fwd(s)");
+  if (Wsq) {
+    style_d_kernel<<<dim3((O + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(s_out, Wsq, d_out, Cin, O);
+    MGF_CHECK_LAUNCH("style_fwd(d)");
+  }
   return 0;
 }
 
@@ -340,7 +374,7 @@ extern "C" int mgf_style_bwd(const float* ds, const float* R, const float* s, co
   if (!A || !dwg || (R && (!s || !d || !Wsq))) MGF_FAIL(MGF_E_BADARG, "style_bwd: null tensor");
   if (R && sgain != 1.f) MGF_FAIL(MGF_E_UNSUP, "style_bwd: demodulation with a style gain is not a case of the generator");
   if (B <= 0) return 0;
-  style_bwd_kernel<<<B, 256, (Cin + O) * sizeof(float), (cudaStream_t)stream>>>(ds, R, s, d, Wsq, A, again, sgain, dwg, dwg_stride, Cin, O, wdim);
+  style_bwd_kernel<<<dim3((Cin + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(ds, R, s, d, Wsq, A, again, sgain, dwg, dwg_stride, Cin, O, wdim);
   MGF_CHECK_LAUNCH("style_bwd");
   return 0;
 }
@@ -361,8 +395,13 @@ extern "C" int mgf_small_gemm(const float* A, int64_t sAb, int64_t sAm, const fl
                               int64_t sOb, int64_t sOm, int B, int M, int N, int K, int accumulate, void* stream) {
   if (!A || !Bm || !out) MGF_FAIL(MGF_E_BADARG, "small_gemm: null tensor");
   if (B <= 0 || M * N == 0) return 0;
-  dim3 grid((M * N + 255) / 256, B);
-  small_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sAb, sAm, Bm, bias, out, sOb, sOm, M, N, K, accumulate);
+  if (K >= 128) {
+    dim3 grid((M * N + 7) / 8, B);
+    small_gemm_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sAb, sAm, Bm, bias, out, sOb, sOm, M, N, K, accumulate);
+  } else {
+    dim3 grid((M * N + 255) / 256, B);
+    small_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sAb, sAm, Bm, bias, out, sOb, sOm, M, N, K, accumulate);
+  }
   MGF_CHECK_LAUNCH("small_gemm");
   return 0;
 }

@@ -155,71 +155,84 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* 
   }
 }
 
-// warp per pixel.  mode 0: n1 = f/(|f|+eps) (target caching).  mode 1: val[b] += (1/HW) sum_c lin_c (f_c/(|f|+eps) - n1_c)^2.
+// mode 0: n1 = f/(|f|+eps) (target caching).  mode 1: val[b] += (1/HW) sum_c lin_c (f_c/(|f|+eps) - n1_c)^2.
 // mode 2: backward, df = coef[b]/HW * (g/(r+eps) - (g.f) f / (r (r+eps)^2)), g = 2 lin (n0 - n1); optional relu mask (df *= f > 0).
-template <int MODE>
+// A group of LPP = min(32, C/8) lanes owns one pixel (VPL = C/(8*LPP) 16-byte vectors per lane, kept in registers), so a warp
+// covers 32/LPP pixels and every lane is busy for all VGG widths (64..512); reductions are xor-shuffles inside the group.
+template <int MODE, int VPL>
 __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f, const __nv_bfloat16* n1, const float* lin, const float* coef,
                                                          __nv_bfloat16* outp, float* val, long long HW, int C, int relu_mask) {
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int vecs = C / 8;
+  const int lpp = (C / 8) / VPL;            // lanes per pixel: 8, 16 or 32
+  const int ppw = 32 / lpp;                 // pixels per warp
+  const int sub = lane / lpp, ll = lane % lpp;
   const float eps = 1e-10f;
   float vsum = 0.f;
   const float cf = (MODE == 2) ? coef[b] / (float)HW : 0.f;
-  for (long long p = (long long)blockIdx.x * 8 + warp; p < HW; p += (long long)gridDim.x * 8) {
-    const long long row = ((long long)b * HW + p) * C;
-    float ss = 0.f, dot = 0.f;
-    // pass 1: norm
-    for (int vi = lane; vi < vecs; vi += 32) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + vi);
+  float lw[VPL][8];
+  if (MODE != 0) {
+#pragma unroll
+    for (int q = 0; q < VPL; q++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) lw[q][e] = lin[(q * lpp + ll) * 8 + e];
+  }
+  for (long long p0 = ((long long)blockIdx.x * 8 + warp) * ppw; p0 < HW; p0 += (long long)gridDim.x * 8 * ppw) {
+    const long long p = p0 + sub;
+    const bool ok = p < HW;
+    const long long row = ((long long)b * HW + (ok ? p : 0)) * C;
+    float x[VPL][8], t[VPL][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < VPL; q++) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + q * lpp + ll);
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); }
+      for (int e = 0; e < 4; e++) { const float2 v = unpack_bf16(w4[e]); x[q][e * 2] = v.x; x[q][e * 2 + 1] = v.y; ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); }
+      if (MODE != 0) {
+        const uint4 un = __ldg(reinterpret_cast<const uint4*>(n1 + row) + q * lpp + ll);
+        const uint32_t n4[4] = {un.x, un.y, un.z, un.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float2 v = unpack_bf16(n4[e]); t[q][e * 2] = v.x; t[q][e * 2 + 1] = v.y; }
+      }
     }
-    ss = warp_sum(ss);
+    for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float r = sqrtf(ss), inv = 1.f / (r + eps);
     if (MODE == 0) {
-      for (int vi = lane; vi < vecs; vi += 32) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + vi);
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-        uint32_t o4[4];
+      if (ok) {
 #pragma unroll
-        for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); o4[e] = pack_bf16(q.x * inv, q.y * inv); }
-        reinterpret_cast<uint4*>(outp + row)[vi] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        for (int q = 0; q < VPL; q++) {
+          uint4 u;
+          u.x = pack_bf16(x[q][0] * inv, x[q][1] * inv); u.y = pack_bf16(x[q][2] * inv, x[q][3] * inv);
+          u.z = pack_bf16(x[q][4] * inv, x[q][5] * inv); u.w = pack_bf16(x[q][6] * inv, x[q][7] * inv);
+          reinterpret_cast<uint4*>(outp + row)[q * lpp + ll] = u;
+        }
       }
       continue;
     }
-    // pass 2 (row is L1-resident): weighted squared difference, and g.f for the backward
-    for (int vi = lane; vi < vecs; vi += 32) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + vi);
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(n1 + row) + vi);
-      const uint32_t w4[4] = {u.x, u.y, u.z, u.w}, t4[4] = {t.x, t.y, t.z, t.w};
+    float dot = 0.f, v1 = 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const float2 q = unpack_bf16(w4[e]), n = unpack_bf16(t4[e]);
-        const float l0 = lin[vi * 8 + e * 2], l1 = lin[vi * 8 + e * 2 + 1];
-        const float d0 = q.x * inv - n.x, d1 = q.y * inv - n.y;
-        if (MODE == 1) { vsum = fmaf(l0 * d0, d0, vsum); vsum = fmaf(l1 * d1, d1, vsum); }
-        else { dot = fmaf(2.f * l0 * d0, q.x, dot); dot = fmaf(2.f * l1 * d1, q.y, dot); }
+    for (int q = 0; q < VPL; q++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const float dd = x[q][e] * inv - t[q][e];
+        if (MODE == 1) v1 = fmaf(lw[q][e] * dd, dd, v1);
+        else dot = fmaf(2.f * lw[q][e] * dd, x[q][e], dot);
       }
-    }
-    if (MODE == 2) {
-      dot = warp_sum(dot);
-      const float k2 = (r > 0.f) ? dot * inv * inv / r : 0.f;
-      for (int vi = lane; vi < vecs; vi += 32) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + vi);
-        const uint4 t = __ldg(reinterpret_cast<const uint4*>(n1 + row) + vi);
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w}, t4[4] = {t.x, t.y, t.z, t.w};
-        uint32_t o4[4];
+    if (MODE == 1) { if (ok) vsum += v1; continue; }
+    for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float k2 = (r > 0.f) ? dot * inv * inv / r : 0.f;
+    if (ok) {
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const float2 q = unpack_bf16(w4[e]), n = unpack_bf16(t4[e]);
-          const float l0 = lin[vi * 8 + e * 2], l1 = lin[vi * 8 + e * 2 + 1];
-          float g0 = cf * (2.f * l0 * (q.x * inv - n.x) * inv - k2 * q.x);
-          float g1 = cf * (2.f * l1 * (q.y * inv - n.y) * inv - k2 * q.y);
-          if (relu_mask) { g0 = q.x > 0.f ? g0 : 0.f; g1 = q.y > 0.f ? g1 : 0.f; }
-          o4[e] = pack_bf16(g0, g1);
+      for (int q = 0; q < VPL; q++) {
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          g[e] = cf * (2.f * lw[q][e] * (x[q][e] * inv - t[q][e]) * inv - k2 * x[q][e]);
+          if (relu_mask) g[e] = x[q][e] > 0.f ? g[e] : 0.f;
         }
-        reinterpret_cast<uint4*>(outp + row)[vi] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        uint4 u;
+        u.x = pack_bf16(g[0], g[1]); u.y = pack_bf16(g[2], g[3]); u.z = pack_bf16(g[4], g[5]); u.w = pack_bf16(g[6], g[7]);
+        reinterpret_cast<uint4*>(outp + row)[q * lpp + ll] = u;
       }
     }
   }
@@ -294,15 +307,18 @@ extern "C" int mgf_maxpool2_bwd(const void* x, const void* dy, const void* extra
 extern "C" int mgf_lpips_head(int mode, const void* f, const void* n1, const float* lin, const float* coef, void* out, float* val,
                               int relu_mask, int B, int64_t HW, int C, void* stream) {
   if (!f || (mode != 0 && (!n1 || !lin)) || (mode != 1 && !out) || (mode == 1 && !val) || (mode == 2 && !coef)) MGF_FAIL(MGF_E_BADARG, "lpips_head: null tensor");
-  if (C % 8) MGF_FAIL(MGF_E_SHAPE, "lpips_head: C must be a multiple of 8");
-  long long blocks = (HW + 7) / 8; const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
+  if (!(C == 64 || C == 128 || C == 256 || C == 512)) MGF_FAIL(MGF_E_SHAPE, "lpips_head: C=%d must be 64, 128, 256 or 512", C);
+  if (mode < 0 || mode > 2) MGF_FAIL(MGF_E_BADARG, "lpips_head: mode %d", mode);
+  const int vpl = C == 512 ? 2 : 1, lpp = (C / 8) / vpl, ppw = 32 / lpp;
+  long long blocks = (HW + 8 * ppw - 1) / (8 * ppw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, B);
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *fp = (const __nv_bfloat16*)f, *np = (const __nv_bfloat16*)n1;
-  if (mode == 0) lpips_head_kernel<0><<<grid, 256, 0, st>>>(fp, np, lin, coef, (__nv_bfloat16*)out, val, HW, C, relu_mask);
-  else if (mode == 1) lpips_head_kernel<1><<<grid, 256, 0, st>>>(fp, np, lin, coef, (__nv_bfloat16*)out, val, HW, C, relu_mask);
-  else if (mode == 2) lpips_head_kernel<2><<<grid, 256, 0, st>>>(fp, np, lin, coef, (__nv_bfloat16*)out, val, HW, C, relu_mask);
-  else MGF_FAIL(MGF_E_BADARG, "lpips_head: mode %d", mode);
+  __nv_bfloat16* op = (__nv_bfloat16*)out;
+#define MGF_HEAD(M, V) lpips_head_kernel<M, V><<<grid, 256, 0, st>>>(fp, np, lin, coef, op, val, HW, C, relu_mask)
+  if (vpl == 1) { if (mode == 0) MGF_HEAD(0, 1); else if (mode == 1) MGF_HEAD(1, 1); else MGF_HEAD(2, 1); }
+  else { if (mode == 0) MGF_HEAD(0, 2); else if (mode == 1) MGF_HEAD(1, 2); else MGF_HEAD(2, 2); }
+#undef MGF_HEAD
   MGF_CHECK_LAUNCH("lpips_head");
   return 0;
 }
