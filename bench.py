@@ -156,7 +156,7 @@ def run_native(args):
     import torch
     import torch.distributed as dist
     import util
-    from morphganformer_b200 import _lib, tc
+    from morphganformer_b200 import _lib, tc, parallel
     from morphganformer_b200.projection import Projector, latent_stats
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,10 +201,7 @@ def run_native(args):
     for _ in range(K):
         P.step()
     if world > 1:   # the only collective of the job: gather the projected latents and their losses
-        lat = [torch.empty_like(P.best_latent) for _ in range(world)]
-        los = [torch.empty_like(P.best_loss) for _ in range(world)]
-        dist.all_gather(lat, P.best_latent.contiguous())
-        dist.all_gather(los, P.best_loss.contiguous())
+        parallel.gather_results(P.best_latent.contiguous(), P.best_loss.contiguous())
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)

@@ -14,10 +14,11 @@
 // TMA boxes {BK, BN, 1} of the [G][T][NT][K] weight tensor.  Both land in shared memory in the 128B (or 64B for
 // 32-channel layers) swizzled K-major layout that tcgen05.mma reads through shared-memory descriptors.
 //
-// CTA = 6 warps, persistent over output tiles:
-//   warp 4 (one lane): TMA producer, STAGES-deep mbarrier ring
-//   warp 5 (one lane): tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x BN columns)
-//   warps 0-3        : epilogue -- tcgen05.ld the accumulator, then the fused per-layer tail:
+// CTA = 10 warps, persistent over output tiles:
+//   warp 8 (one lane): TMA producer, STAGES-deep mbarrier ring (up to 20 stages so small tiles keep enough bytes in flight)
+//   warp 9 (one lane): tcgen05.mma issuer, accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 0-3 / 4-7  : two epilogue groups, group g drains accumulator stage g (alternate tiles) -- tcgen05.ld the
+//                      accumulator, then the fused per-layer tail:
 //                      * per-(sample, channel) scale           (dgrad: the style s[b,i])
 //                      * d(styles) partial sums                (sum over pixels of acc * X, warp-shuffle transpose-reduce + atomics)
 //                      * + noise * strength, + bias, leaky-ReLU/ReLU * gain     (networks.py:1036-1040, bias_act)
@@ -127,7 +128,7 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES = STAGES_RAW > 20 ? 20 : STAGES_RAW;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -147,7 +148,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
 }
 
 template <int BN, int BK>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ Params p) {
   using C = Cfg<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const int iters = p.kchunks * p.ntaps;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {   // ------------------------------------------------ TMA producer
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {   // ------------------------------------------------ MMA issuer
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -215,12 +216,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else {             // ---------------------------------------------------- epilogue warps 0..3
-    int as = 0; uint32_t aphase = 0;
-    const int r = warp * 32 + lane;          // accumulator row == TMEM lane == pixel index inside the A box
+  } else {             // ---------------------------------------------------- epilogue: two groups of 4 warps, group g owns accumulator stage g
+    const int as = warp >> 2; uint32_t aphase = 0;
+    const int wq = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = wq * 32 + lane;            // accumulator row == TMEM lane == pixel index inside the A box
     const int tx = r % p.TW, ty = (r / p.TW) % p.TH, tb = r / (p.TW * p.TH);
     const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BN);
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
       const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c * 32), raw);
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN + c * 32), raw);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
@@ -274,18 +276,18 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
           atomicAdd(p.reduce_out + (long long)t.b0 * p.NT + t.n0 + c * 32 + lane, s[0]);
         }
         if (p.scale_n) {
-          const float* sp = p.scale_n + (long long)(valid ? b : 0) * p.NT + t.n0 + c * 32;
+          const float4* sp = reinterpret_cast<const float4*>(p.scale_n + (long long)(valid ? b : 0) * p.NT + t.n0 + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] *= __ldg(sp + j);
+          for (int j = 0; j < 8; j++) { const float4 f = __ldg(sp + j); v[4 * j] *= f.x; v[4 * j + 1] *= f.y; v[4 * j + 2] *= f.z; v[4 * j + 3] *= f.w; }
         }
         if (p.noise) {
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] += nz;
         }
         if (p.bias) {
-          const float* bp = p.bias + co0 + c * 32;
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + co0 + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] += __ldg(bp + j);
+          for (int j = 0; j < 8; j++) { const float4 f = __ldg(bp + j); v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w; }
         }
         if (p.act == 1) {
 #pragma unroll
@@ -324,12 +326,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      aphase ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
@@ -372,7 +374,7 @@ static int launch(const Params& p, int grid, cudaStream_t st) {
     if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc: cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_tc_kernel<BN, BK><<<grid, 192, C::SMEM, st>>>(p);
+  conv_tc_kernel<BN, BK><<<grid, 320, C::SMEM, st>>>(p);
   MGF_CHECK_LAUNCH("conv_tc");
   return 0;
 }
