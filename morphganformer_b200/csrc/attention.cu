@@ -323,8 +323,14 @@ extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, con
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
   const int smem = attn_smem_fwd(C);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C > 256) { cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attn_fwd_kernel<2><<<grid, 256, smem, st>>>(p); }
-  else { cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attn_fwd_kernel<1><<<grid, 256, smem, st>>>(p); }
+  static bool cfg_done = false;
+  if (!cfg_done) {   // opt in once to > 48 KB dynamic shared memory (largest case C = 512), outside any stream capture
+    cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_fwd(512));
+    cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_fwd(256));
+    cfg_done = true;
+  }
+  if (C > 256) attn_fwd_kernel<2><<<grid, 256, smem, st>>>(p);
+  else attn_fwd_kernel<1><<<grid, 256, smem, st>>>(p);
   MGF_CHECK_LAUNCH("attn_fwd");
   return 0;
 }
@@ -343,8 +349,14 @@ extern "C" int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, cons
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
   const int smem = attn_smem_bwd(C);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C > 256) { cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attn_bwd_kernel<2><<<grid, 256, smem, st>>>(p); }
-  else { cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attn_bwd_kernel<1><<<grid, 256, smem, st>>>(p); }
+  static bool cfg_done = false;
+  if (!cfg_done) {
+    cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bwd(512));
+    cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bwd(256));
+    cfg_done = true;
+  }
+  if (C > 256) attn_bwd_kernel<2><<<grid, 256, smem, st>>>(p);
+  else attn_bwd_kernel<1><<<grid, 256, smem, st>>>(p);
   MGF_CHECK_LAUNCH("attn_bwd");
   return 0;
 }

@@ -63,23 +63,37 @@ class Projector:
 
     def reset(self):
         B = self.B
-        self.latent = self.latent_mean.unsqueeze(0).repeat(B, 1, 1).contiguous()
-        self.m = torch.zeros_like(self.latent)
-        self.v = torch.zeros_like(self.latent)
-        self.latent_n = (self.latent + self.step_noise[0] * self.ns0).contiguous()
-        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.losses = torch.zeros(self.steps, B, device=self.dev)
-        self.best_loss = torch.full((B,), float("inf"), device=self.dev)
-        self.best_latent = self.latent_n.clone()
+        if getattr(self, "latent", None) is None:      # allocate once: addresses stay fixed (CUDA-graph replay, repeated jobs)
+            self.latent = torch.empty(B, *self.latent_mean.shape, device=self.dev)
+            self.m, self.v, self.latent_n = torch.empty_like(self.latent), torch.empty_like(self.latent), torch.empty_like(self.latent)
+            self.best_loss = torch.empty(B, device=self.dev)
+            self.best_latent = torch.empty_like(self.latent)
+        self.latent.copy_(self.latent_mean.unsqueeze(0).expand(B, -1, -1))
+        self.m.zero_(); self.v.zero_()
+        self.latent_n.copy_(self.latent + self.step_noise[0] * self.ns0)
+        if getattr(self, "step_ctr", None) is None:
+            self.step_ctr = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self.step_idx = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            self.losses = torch.zeros(self.steps, B, device=self.dev)
+            self.graph = None
+        self.step_ctr.zero_(); self.losses.zero_()
+        self.best_loss.fill_(float("inf"))
+        self.best_latent.copy_(self.latent_n)
         self.i = 0
 
     def set_targets(self, target):
         """target [B,3,R,R] fp32 in [-1,1] (device or host)."""
-        self.target = target.to(self.dev, torch.float32).contiguous()
-        assert self.target.shape[0] == self.B
+        target = target.to(self.dev, torch.float32)
+        assert target.shape[0] == self.B
+        if getattr(self, "target", None) is not None and tuple(self.target.shape) == tuple(target.shape):
+            self.target.copy_(target)                   # same buffer: a captured graph keeps working for the next job
+        else:
+            self.target = target.contiguous().clone()
+            self.graph = None
         if self.lp is not None:
             self.lp.set_target(self.target)
-        self.coef = torch.full((self.B,), self.lamda if self.use_lpips else 0.0, device=self.dev)
+        if getattr(self, "coef", None) is None:
+            self.coef = torch.full((self.B,), self.lamda if self.use_lpips else 0.0, device=self.dev)
 
     def _loss_and_grad(self, img):
         R = img.shape[2]
@@ -97,8 +111,38 @@ class Projector:
             _lib.check(lib.mgf_lpips_prep_bwd(None, img.data_ptr(), self.target.data_ptr(), 2.0 / n, dimg.data_ptr(), self.B, R, s), "mgf_lpips_prep_bwd")
         return per_img, dimg
 
-    def step(self):
-        """One projection step for the whole batch; no host sync.  Returns the per-image loss tensor (device)."""
+    def step(self, use_graph=True):
+        """One projection step for the whole batch; no host sync.  Returns the per-image loss tensor (device).
+        After capture() the step is one CUDA-graph replay (use_graph=False forces the eager launch sequence)."""
+        if use_graph and self.graph is not None:
+            self.graph.replay()
+            self.i += 1
+            return self._graph_loss
+        return self._step_eager()
+
+    def capture(self):
+        """Captures one step (mapping fwd/bwd in PyTorch + every mgf kernel launch) into a CUDA graph.  The schedule and
+        the loss row are indexed by the device step counter, so replays advance exactly like eager steps."""
+        saved = [t.clone() for t in (self.latent, self.m, self.v, self.latent_n, self.best_loss, self.best_latent, self.step_ctr, self.losses)]
+        i_saved = self.i
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):                     # warm-up: allocates every persistent buffer, sets kernel attributes
+                self._step_eager()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.lib().mgf_launch_count()
+        with torch.cuda.graph(g):
+            self._graph_loss = self._step_eager()
+        self.launches_per_step = int(_lib.lib().mgf_launch_count() - n0)   # mgf kernels recorded in one step
+        for dst, src in zip((self.latent, self.m, self.v, self.latent_n, self.best_loss, self.best_latent, self.step_ctr, self.losses), saved):
+            dst.copy_(src)
+        self.i = i_saved
+        self.graph = g
+        return g
+
+    def _step_eager(self):
         G = self.G
         z = self.latent_n.detach().requires_grad_(True)
         with torch.enable_grad():
@@ -110,10 +154,10 @@ class Projector:
         (gz,) = torch.autograd.grad(ws, [z], grad_outputs=[dws])
         # best-so-far bookkeeping (reference: keep latent_n of the lowest-loss step, :155-158)
         better = per_img < self.best_loss
-        self.best_loss = torch.where(better, per_img, self.best_loss)
-        self.best_latent = torch.where(better.reshape(-1, 1, 1), self.latent_n, self.best_latent)
-        if self.i < self.steps:
-            self.losses[self.i] = per_img
+        self.best_loss.copy_(torch.where(better, per_img, self.best_loss))
+        self.best_latent.copy_(torch.where(better.reshape(-1, 1, 1), self.latent_n, self.best_latent))
+        self.step_idx.copy_(self.step_ctr)
+        self.losses.index_copy_(0, self.step_idx.clamp(max=self.steps - 1), per_img.unsqueeze(0))
         lib = _lib.lib()
         _lib.check(lib.mgf_adam_noise_step(self.latent.data_ptr(), gz.contiguous().data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                            self.step_noise.data_ptr(), self.steps, self.latent_n.data_ptr(), self.sched.data_ptr(),

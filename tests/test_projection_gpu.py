@@ -71,3 +71,26 @@ def test_projection_loss_trajectory_matches_oracle(use_lpips):
     dl = (P.latent.cpu() - ref["latent"]).abs().max().item()
     print("latent max diff after %d steps: %g" % (steps, dl))
     assert dl < 0.15
+
+
+def test_cuda_graph_replay_equals_eager():
+    from morphganformer_b200.projection import Projector, latent_stats
+    res, cb, cm, B, steps = 64, 2048, 64, 2, 5
+    lsd = util.build_vgg_lpips_sd(4)
+    mean, std = latent_stats(util.case_tensor((2000, 17, 32), 70))
+    noise = util.case_tensor((20, B, 17, 32), 71)
+    tgt = torch.tanh(util.case_tensor((B, 3, res, res), 73))
+    out = []
+    for graph in (False, True):
+        G = util.build_G(res, 0, cb, cm).cuda()
+        P = Projector(G, lsd, B, 20, latent_mean=mean, latent_std=std, step_noise=noise)
+        P.set_targets(tgt)
+        if graph:
+            P.capture()
+        for _ in range(steps):
+            P.step()
+        torch.cuda.synchronize()
+        out.append((P.losses[:steps].cpu(), P.latent.cpu(), P.best_loss.cpu()))
+    np.testing.assert_allclose(out[1][0].numpy(), out[0][0].numpy(), rtol=2e-3)     # float atomics reorder between runs
+    assert (out[1][1] - out[0][1]).abs().max() < 2e-2
+    np.testing.assert_allclose(out[1][2].numpy(), out[0][2].numpy(), rtol=2e-3)
