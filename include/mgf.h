@@ -33,6 +33,10 @@ const char* mgf_last_error(void);
 int mgf_version(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches claim) */
 int64_t mgf_launch_count(void);
+/* Element type of the 16-bit FORWARD tensors of the engine kernels below (activations, forward GEMM operands, cached LPIPS target
+ * features): MGF_BF16 (default) or MGF_F16.  Gradient tensors are always bf16.  Process-wide setting, read at launch time. */
+int mgf_set_forward_dtype(int dtype);
+int mgf_get_forward_dtype(void);
 
 /* ---- bias_act ---------------------------------------------------------------------------------------
  * Replaces bias_act_plugin.bias_act (torch_utils/ops/bias_act.cpp:24-82, kernel bias_act.cu:15-139).
@@ -87,6 +91,7 @@ int mgf_fma(const void* a, const void* b, const void* c, void* out, int dtype,
  * for (b, y, x) over the NB x GH x GW tile grid; reads outside an activation tensor are zero (TMA fill).
  * Activations are NHWC bf16 views (channel stride 1; W/H/N strides in elements, so strided phase views work);
  * W is a dense bf16 [G][T][NT = phases*Cout][K] tensor, G = NB for per-sample (modulated) weights or 1.
+ * 16-bit element types: tensors flagged *_fwd follow mgf_set_forward_dtype, the others are bf16 gradients.
  * Epilogue, in order (each optional): reduce_out[b, n] += sum_pixels acc*X   (fp32 atomics; X like out),
  * acc *= scale_n[b, n], += noise[oy, ox] * *noise_strength, += bias[co], act (0 none, 1 leaky-ReLU(alpha), 2 ReLU) * gain,
  * += add (like out), *= (X > 0 ? 1 : ag_alpha) * ag_gain  (actgrad), store bf16.  bn = 0 picks the N tile. */
@@ -105,6 +110,8 @@ typedef struct {
   const void* add;
   int32_t actgrad; float ag_alpha, ag_gain;
   int32_t bn; int32_t reduce_per_sample;
+  /* which tensors are FORWARD-dtype tensors (see mgf_set_forward_dtype); 0 = gradient tensor (bf16) */
+  int32_t ab_fwd, out_fwd, x_fwd, add_fwd;
 } mgf_conv_tc_desc;
 int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream);
 
@@ -123,7 +130,7 @@ int mgf_style_fwd(const float* wg, int64_t wg_stride, const float* A, const floa
                   const float* Wsq, float* s_out, float* d_out, int B, int Cin, int O, int wdim, void* stream);
 int mgf_style_bwd(const float* ds, const float* R, const float* s, const float* d, const float* Wsq, const float* A,
                   float again, float sgain, float* dwg, int64_t dwg_stride, int B, int Cin, int O, int wdim, void* stream);
-int mgf_modulate_weights(const float* base, const float* rs, int nmod, const float* cs, void* out,
+int mgf_modulate_weights(const float* base, const float* rs, int nmod, const float* cs, void* out, int out_fwd,
                          int B, int64_t T, int64_t NT, int64_t K, void* stream);
 int mgf_small_gemm(const float* A, int64_t sAb, int64_t sAm, const float* Bm, const float* bias, float* out,
                    int64_t sOb, int64_t sOm, int B, int M, int N, int K, int accumulate, void* stream);

@@ -21,6 +21,8 @@ SIGNATURES = {
     "mgf_last_error": (ctypes.c_char_p, []),
     "mgf_version": (c_int, []),
     "mgf_launch_count": (c_int64, []),
+    "mgf_set_forward_dtype": (c_int, [c_int]),
+    "mgf_get_forward_dtype": (c_int, []),
     "mgf_bias_act": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_float, c_float, c_int64, c_int64, c_int64, c_void_p]),
     "mgf_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
@@ -29,7 +31,7 @@ SIGNATURES = {
     "mgf_conv2d_wgrad_f32": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvShape), c_void_p]),
     "mgf_style_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_style_bwd": (c_int, [c_void_p] * 6 + [c_float, c_float, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
-    "mgf_modulate_weights": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p]),
+    "mgf_modulate_weights": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "mgf_small_gemm": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_torgb_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]),
     "mgf_torgb_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int64, c_int, c_void_p]),
@@ -115,3 +117,15 @@ def i64x(*v):
 
 def i32x(*v):
     return (c_int32 * len(v))(*v)
+
+
+def set_forward_dtype(name):
+    """'bf16' (default) or 'fp16': element type of the engine's forward activations / forward GEMM operands (gradients stay bf16).
+    fp16 has the same tensor-core rate and 8x finer rounding (meets the 1e-2 image tolerance); bf16 has the fp32 exponent range."""
+    code = {"bf16": BF16, "fp16": F16}[name]
+    check(lib().mgf_set_forward_dtype(code), "mgf_set_forward_dtype")
+
+
+def forward_torch_dtype():
+    import torch
+    return torch.float16 if lib().mgf_get_forward_dtype() == F16 else torch.bfloat16

@@ -25,11 +25,11 @@ struct AttnP {
   __nv_bfloat16* out; float* probs;
   // backward
   const __nv_bfloat16* dz; __nv_bfloat16* dX; float* dVM; float* R;
-  long long HW; int C; int pix_per_cta;
+  long long HW; int C; int pix_per_cta; bool f16;
 };
 
 template <int VPL>
-__device__ __forceinline__ void load_row(const __nv_bfloat16* p, int C, int lane, float (&v)[VPL][8]) {
+__device__ __forceinline__ void load_row(const __nv_bfloat16* p, int C, int lane, float (&v)[VPL][8], bool f16) {
 #pragma unroll
   for (int q = 0; q < VPL; q++) {
     const int vi = q * 32 + lane;
@@ -37,7 +37,7 @@ __device__ __forceinline__ void load_row(const __nv_bfloat16* p, int C, int lane
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + vi);
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); v[q][e * 2] = f.x; v[q][e * 2 + 1] = f.y; }
+      for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], f16); v[q][e * 2] = f.x; v[q][e * 2 + 1] = f.y; }
     } else {
 #pragma unroll
       for (int e = 0; e < 8; e++) v[q][e] = 0.f;
@@ -45,13 +45,13 @@ __device__ __forceinline__ void load_row(const __nv_bfloat16* p, int C, int lane
   }
 }
 template <int VPL>
-__device__ __forceinline__ void store_row(__nv_bfloat16* p, int C, int lane, const float (&v)[VPL][8]) {
+__device__ __forceinline__ void store_row(__nv_bfloat16* p, int C, int lane, const float (&v)[VPL][8], bool f16) {
 #pragma unroll
   for (int q = 0; q < VPL; q++) {
     const int vi = q * 32 + lane;
     if (vi * 8 < C) {
       uint4 u;
-      u.x = pack_bf16(v[q][0], v[q][1]); u.y = pack_bf16(v[q][2], v[q][3]); u.z = pack_bf16(v[q][4], v[q][5]); u.w = pack_bf16(v[q][6], v[q][7]);
+      u.x = pack16(v[q][0], v[q][1], f16); u.y = pack16(v[q][2], v[q][3], f16); u.z = pack16(v[q][4], v[q][5], f16); u.w = pack16(v[q][6], v[q][7], f16);
       reinterpret_cast<uint4*>(p)[vi] = u;
     }
   }
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnP p) {
   const long long p0 = (long long)blockIdx.x * p.pix_per_cta;
   for (long long f = p0 + warp; f < p0 + p.pix_per_cta && f < p.HW; f += 8) {
     float x[VPL][8];
-    load_row<VPL>(p.X + ((long long)b * p.HW + f) * C, C, lane, x);
+    load_row<VPL>(p.X + ((long long)b * p.HW + f) * C, C, lane, x, p.f16);
     float A[T16], rn;
     pixel_probs<VPL>(x, sK, C, lane, p.Sc + f * T16, p.mb + b * T16, A, rn);
     if (p.probs && lane < T16) p.probs[((long long)b * p.HW + f) * T16 + lane] = A[lane];
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnP p) {
         }
       }
     }
-    store_row<VPL>(p.out + ((long long)b * p.HW + f) * C, C, lane, o);
+    store_row<VPL>(p.out + ((long long)b * p.HW + f) * C, C, lane, o, p.f16);
   }
 }
 
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
       const long long f = base + slot;
       if (f < pend) {
         float x[VPL][8], g[VPL][8];
-        load_row<VPL>(p.X + ((long long)b * p.HW + f) * C, C, lane, x);
-        load_row<VPL>(p.dz + ((long long)b * p.HW + f) * C, C, lane, g);
+        load_row<VPL>(p.X + ((long long)b * p.HW + f) * C, C, lane, x, p.f16);
+        load_row<VPL>(p.dz + ((long long)b * p.HW + f) * C, C, lane, g, false);
         float A[T16], rn;
         pixel_probs<VPL>(x, sK, C, lane, p.Sc + f * T16, p.mb + b * T16, A, rn);
         const float nz = p.noise ? p.noise[f] * ns : 0.f;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
             for (int e = 0; e < 8; e++) { dx[q][e] = a8[e]; rloc[q][e] = fmaf(a8[e], x[q][e], rloc[q][e]); }
           }
         }
-        store_row<VPL>(p.dX + ((long long)b * p.HW + f) * C, C, lane, dx);
+        store_row<VPL>(p.dX + ((long long)b * p.HW + f) * C, C, lane, dx, false);
       } else {
         // keep phase 2 uniform: empty slots contribute zeros
         if (lane < T16) sA[slot * T16 + lane] = 0.f;
@@ -316,7 +316,7 @@ extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, con
   if (!X || !Kf || !Sc || !maskbias || !VM || !bm || !out) MGF_FAIL(MGF_E_BADARG, "attn_fwd: null tensor");
   if (int e = attn_check(C, "attn_fwd")) return e;
   AttnP p{}; p.X = (const __nv_bfloat16*)X; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm; p.noise = noise; p.nstr = nstr; p.bias = bias;
-  p.gain = gain; p.alpha = alpha; p.out = (__nv_bfloat16*)out; p.probs = probs; p.HW = HW; p.C = C;
+  p.gain = gain; p.alpha = alpha; p.out = (__nv_bfloat16*)out; p.probs = probs; p.HW = HW; p.C = C; p.f16 = fwd_f16();
   long long ppc = (HW * B + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4);
   if (ppc < 8) ppc = 8;
   ppc = (ppc + 7) / 8 * 8; p.pix_per_cta = (int)ppc;
@@ -342,7 +342,7 @@ extern "C" int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, cons
   if (int e = attn_check(C, "attn_bwd")) return e;
   if (C % 16) MGF_FAIL(MGF_E_SHAPE, "attn_bwd: C must be a multiple of 16");
   AttnP p{}; p.X = (const __nv_bfloat16*)X; p.dz = (const __nv_bfloat16*)dz; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm;
-  p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.HW = HW; p.C = C;
+  p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.HW = HW; p.C = C; p.f16 = fwd_f16();
   long long ppc = (HW * B + (long long)num_sms() * 2 - 1) / ((long long)num_sms() * 2);
   if (ppc < 32) ppc = 32;
   ppc = (ppc + 31) / 32 * 32; p.pix_per_cta = (int)ppc;

@@ -12,6 +12,7 @@ namespace mgf {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+bool fwd_f16();   // true when forward activations / forward GEMM operands are IEEE fp16 (mgf_set_forward_dtype)
 
 #define MGF_FAIL(code, ...) do { ::mgf::set_error(__VA_ARGS__); return (code); } while (0)
 #define MGF_CHECK_LAUNCH(name) do { cudaError_t e_ = cudaGetLastError(); \
@@ -65,6 +66,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
+}
+// 16-bit storage with a run-time element type: f16 = IEEE half (forward activations/operands when the library is in fp16-forward
+// mode: same tensor-core rate, 8x finer rounding than bf16), otherwise bfloat16 (always used for gradients: range).
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
+  if (f16) {
+    __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+  return pack_bf16(a, b);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t u, bool f16) {
+  if (f16) { __half2 t = *reinterpret_cast<__half2*>(&u); return __half22float2(t); }
+  return unpack_bf16(u);
+}
+__device__ __forceinline__ float load16(const void* p, long long i, bool f16) {
+  return f16 ? __half2float(reinterpret_cast<const __half*>(p)[i]) : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
 }
 
 }  // namespace mgf

@@ -53,6 +53,7 @@ struct alignas(64) Params {
   int actgrad; float ag_alpha, ag_gain;
   uint32_t tx_bytes;
   int total_tiles;
+  uint32_t idesc; int out_f16, x_f16, add_f16;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           const uint64_t adesc = make_desc<BK>(sa), bdesc = make_desc<BK>(sa + C::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; k++)
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), C::IDESC, (it > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
           tc_commit(&empty[stage]);           // frees the smem slot once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
               const uint4 u = __ldg(xp + q);
               const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); xv[q * 8 + e * 2] = f.x; xv[q * 8 + e * 2 + 1] = f.y; }
+              for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], p.x_f16); xv[q * 8 + e * 2] = f.x; xv[q * 8 + e * 2 + 1] = f.y; }
             }
           } else {
 #pragma unroll
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
             const uint4 u = __ldg(ap + q);
             const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); v[q * 8 + e * 2] += f.x; v[q * 8 + e * 2 + 1] += f.y; }
+            for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], p.add_f16); v[q * 8 + e * 2] += f.x; v[q * 8 + e * 2 + 1] += f.y; }
           }
         }
         if (p.actgrad) {
@@ -318,8 +319,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             uint4 u;
-            u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-            u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+            u.x = pack16(v[q * 8 + 0], v[q * 8 + 1], p.out_f16); u.y = pack16(v[q * 8 + 2], v[q * 8 + 3], p.out_f16);
+            u.z = pack16(v[q * 8 + 4], v[q * 8 + 5], p.out_f16); u.w = pack16(v[q * 8 + 6], v[q * 8 + 7], p.out_f16);
             op[q] = u;
           }
         }
@@ -449,6 +450,12 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain;
   if ((p.reduce_out || p.actgrad) && !p.X) MGF_FAIL(MGF_E_BADARG, "conv_tc: reduce/actgrad need X");
   p.tx_bytes = (uint32_t)((p.rows * BK + BN * BK) * 2);
+  {
+    const bool f16 = fwd_f16();
+    const uint32_t fmt = (f16 && d->ab_fwd) ? 0u : 1u;      // InstrDescriptor a_format/b_format: 0 = F16, 1 = BF16
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
+  }
   int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
 #define MGF_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch<bn, bk>(p, grid, st);

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) style_bwd_kernel(const float* ds, const f
 
 // ---- per-sample operand weights: out[b][t][n][k] = base[t][n][k] * rs[b][n % nmod] * cs[b][k]   (bf16)
 __global__ void __launch_bounds__(256) modulate_kernel(const float* base, const float* rs, int nmod, const float* cs,
-                                                       __nv_bfloat16* out, long long TN, int K, int NT) {
+                                                       __nv_bfloat16* out, long long TN, int K, int NT, bool of16) {
   const long long b = blockIdx.y;
   const long long per = TN * K;
   const int k4 = K >> 2;
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(256) modulate_kernel(const float* base, const 
     float4 c = make_float4(1.f, 1.f, 1.f, 1.f);
     if (cs) c = *reinterpret_cast<const float4*>(cs + b * K + k);
     uint2 o;
-    o.x = pack_bf16(w.x * r * c.x, w.y * r * c.y);
-    o.y = pack_bf16(w.z * r * c.z, w.w * r * c.w);
+    o.x = pack16(w.x * r * c.x, w.y * r * c.y, of16);
+    o.y = pack16(w.z * r * c.z, w.w * r * c.w, of16);
     *reinterpret_cast<uint2*>(out + b * per + row * K + k) = o;
   }
 }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) small_gemm_warp_kernel(const float* A, lo
 // ---- ToRGB: img[b,c,p] = sum_o y[b,p,o] * wrgb[c,o] * s[b,o] + bias[c]    (y NHWC bf16 -> img NCHW fp32, 3 channels)
 template <int C>
 __global__ void __launch_bounds__(256) torgb_fwd_kernel(const __nv_bfloat16* y, const float* wrgb, const float* s, const float* bias,
-                                                        float* img, long long HW, int nimg) {
+                                                        float* img, long long HW, bool yf16) {
   __shared__ float ws[3 * C];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) ws[i] = wrgb[i] * s[(long long)b * C + (i % C)];
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const __nv_bfloat16* y, 
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        const float2 f = unpack_bf16(w4[e]);
+        const float2 f = unpack16(w4[e], yf16);
         const int o = q * 8 + e * 2;
         a0 = fmaf(f.x, ws[o], a0); a0 = fmaf(f.y, ws[o + 1], a0);
         a1 = fmaf(f.x, ws[C + o], a1); a1 = fmaf(f.y, ws[C + o + 1], a1);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const __nv_bfloat16* y, 
 // backward: dy[b,p,o] = sum_c dimg[b,c,p] wrgb[c,o] s[b,o];  ds[b,o] += sum_{p,c} dimg wrgb[c,o] y[b,p,o];  R[b,o] += sum_p dy*y
 // thread = (pixel lane, 8-channel vector); per-CTA shared accumulators, then one global atomic per channel per CTA.
 __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* dimg, const __nv_bfloat16* y, const float* wrgb, const float* s,
-                                                        __nv_bfloat16* dy, float* ds, float* R, long long HW, int C, int pix_per_cta) {
+                                                        __nv_bfloat16* dy, float* ds, float* R, long long HW, int C, int pix_per_cta, bool yf16) {
   extern __shared__ float sm[];
   float* acc_ds = sm;        // [C]
   float* acc_R = sm + C;     // [C]
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* dimg, const
     uint32_t o4[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const float2 f = unpack_bf16(w4[e]);
+      const float2 f = unpack16(w4[e], yf16);
       const float t0 = g0 * w0[e * 2] + g1 * w1[e * 2] + g2 * w2[e * 2];
       const float t1 = g0 * w0[e * 2 + 1] + g1 * w1[e * 2 + 1] + g2 * w2[e * 2 + 1];
       const float d0 = t0 * sv[e * 2], d1 = t1 * sv[e * 2 + 1];
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* dimg, const
 // R[b,o] += sum_p dy * y with y = lrelu^-1(z/gain) - noise*ns - bias.   One CTA per (pixel chunk, sample); C <= 512.
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, const __nv_bfloat16* z, __nv_bfloat16* dy, float* R,
                                                       const float* noise, const float* nstr, const float* bias,
-                                                      float alpha, float gain, int mode, long long HW, int C, int pix_per_cta) {
+                                                      float alpha, float gain, int mode, long long HW, int C, int pix_per_cta, bool zf16) {
   extern __shared__ float racc[];   // [C]
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < C; i += blockDim.x) racc[i] = 0.f;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, c
       uint32_t o4[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        const float2 zf = unpack_bf16(z4[e]), df = unpack_bf16(d4[e]);
+        const float2 zf = unpack16(z4[e], zf16), df = unpack_bf16(d4[e]);
         float g0 = df.x, g1 = df.y;
         if (mode == 0) { g0 *= gain * (zf.x > 0.f ? 1.f : alpha); g1 *= gain * (zf.y > 0.f ? 1.f : alpha); }
         const float u0 = zf.x * inv_gain, u1 = zf.y * inv_gain;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, c
 // (reference Conv2dLayer.forward :245-250 -> conv2d_resample 1x1-up branch -> upfirdn2d(up=2, pad=[2,1,2,1], gain=4) -> bias_act gain).
 // fk = flipped normalised 1-D taps * 2 (gain 4 split per axis).
 __global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* v, const __nv_bfloat16* add, __nv_bfloat16* out,
-                                                         float4 fk, float g, int h, int w, int C) {
+                                                         float4 fk, float g, int h, int w, int C, bool f16) {
   const int vecs = C / 8;
   const long long total = (long long)gridDim.y * 0 + (long long)(2 * h) * (2 * w) * vecs;
   const int b = blockIdx.y;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* v,
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(v + (((long long)b * h + iy) * w + ix) * C + cv * 8));
         const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); acc[e * 2] = fmaf(cf, q.x, acc[e * 2]); acc[e * 2 + 1] = fmaf(cf, q.y, acc[e * 2 + 1]); }
+        for (int e = 0; e < 4; e++) { const float2 q = unpack16(w4[e], f16); acc[e * 2] = fmaf(cf, q.x, acc[e * 2]); acc[e * 2 + 1] = fmaf(cf, q.y, acc[e * 2 + 1]); }
       }
     }
     const long long off = (((long long)b * 2 * h + Y) * 2 * w + X) * C + cv * 8;
@@ -300,11 +300,11 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* v,
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(add + off));
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); av[e * 2] = q.x; av[e * 2 + 1] = q.y; }
+      for (int e = 0; e < 4; e++) { const float2 q = unpack16(w4[e], f16); av[e * 2] = q.x; av[e * 2 + 1] = q.y; }
     }
     uint4 o;
-    o.x = pack_bf16(acc[0] * g + av[0], acc[1] * g + av[1]); o.y = pack_bf16(acc[2] * g + av[2], acc[3] * g + av[3]);
-    o.z = pack_bf16(acc[4] * g + av[4], acc[5] * g + av[5]); o.w = pack_bf16(acc[6] * g + av[6], acc[7] * g + av[7]);
+    o.x = pack16(acc[0] * g + av[0], acc[1] * g + av[1], f16); o.y = pack16(acc[2] * g + av[2], acc[3] * g + av[3], f16);
+    o.z = pack16(acc[4] * g + av[4], acc[5] * g + av[5], f16); o.w = pack16(acc[6] * g + av[6], acc[7] * g + av[7], f16);
     *reinterpret_cast<uint4*>(out + off) = o;
   }
 }
@@ -379,14 +379,14 @@ extern "C" int mgf_style_bwd(const float* ds, const float* R, const float* s, co
   return 0;
 }
 
-extern "C" int mgf_modulate_weights(const float* base, const float* rs, int nmod, const float* cs, void* out,
+extern "C" int mgf_modulate_weights(const float* base, const float* rs, int nmod, const float* cs, void* out, int out_fwd,
                                     int B, int64_t T, int64_t NT, int64_t K, void* stream) {
   if (!base || !out) MGF_FAIL(MGF_E_BADARG, "modulate_weights: null tensor");
   if (K % 4) MGF_FAIL(MGF_E_SHAPE, "modulate_weights: K must be a multiple of 4");
   if (B <= 0) return 0;
   const long long TN = T * NT;
   dim3 grid(grid_for(TN * (K / 4), 256, 4), B);
-  modulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(base, rs, nmod > 0 ? nmod : 1, cs, (__nv_bfloat16*)out, TN, (int)K, (int)NT);
+  modulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(base, rs, nmod > 0 ? nmod : 1, cs, (__nv_bfloat16*)out, TN, (int)K, (int)NT, out_fwd && fwd_f16());
   MGF_CHECK_LAUNCH("modulate_weights");
   return 0;
 }
@@ -410,9 +410,9 @@ extern "C" int mgf_torgb_fwd(const void* y, const float* wrgb, const float* s, c
   if (!y || !wrgb || !s || !bias || !img) MGF_FAIL(MGF_E_BADARG, "torgb_fwd: null tensor");
   dim3 grid(grid_for(HW, 256, 8), B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 32) torgb_fwd_kernel<32><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, 3);
-  else if (C == 64) torgb_fwd_kernel<64><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, 3);
-  else if (C == 128) torgb_fwd_kernel<128><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, 3);
+  if (C == 32) torgb_fwd_kernel<32><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, fwd_f16());
+  else if (C == 64) torgb_fwd_kernel<64><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, fwd_f16());
+  else if (C == 128) torgb_fwd_kernel<128><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, fwd_f16());
   else MGF_FAIL(MGF_E_UNSUP, "torgb_fwd: C=%d not in {32,64,128}", C);
   MGF_CHECK_LAUNCH("torgb_fwd");
   return 0;
@@ -425,7 +425,7 @@ extern "C" int mgf_torgb_bwd(const float* dimg, const void* y, const float* wrgb
   long long ppc = (HW * B + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8);
   if (ppc < 16) ppc = 16;
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
-  torgb_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dimg, (const __nv_bfloat16*)y, wrgb, s, (__nv_bfloat16*)dy, ds, R, HW, C, (int)ppc);
+  torgb_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dimg, (const __nv_bfloat16*)y, wrgb, s, (__nv_bfloat16*)dy, ds, R, HW, C, (int)ppc, fwd_f16());
   MGF_CHECK_LAUNCH("torgb_bwd");
   return 0;
 }
@@ -441,7 +441,7 @@ extern "C" int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, co
   if (ppc < 16) ppc = 16;
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
   act_bwd_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)z, (__nv_bfloat16*)dy, R,
-                                                                        noise, nstr, bias, alpha, gain, mode, HW, C, (int)ppc);
+                                                                        noise, nstr, bias, alpha, gain, mode, HW, C, (int)ppc, fwd_f16());
   MGF_CHECK_LAUNCH("act_bwd");
   return 0;
 }
@@ -451,7 +451,7 @@ extern "C" int mgf_upfir2_add(const void* v, const void* add, void* out, const f
   if (C % 8) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: C must be a multiple of 8");
   dim3 grid(grid_for((long long)4 * h * w * (C / 8), 256, 8), B);
   upfir2_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)add, (__nv_bfloat16*)out,
-                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C);
+                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, fwd_f16());
   MGF_CHECK_LAUNCH("upfir2_add");
   return 0;
 }

@@ -14,7 +14,7 @@ __constant__ float c_shift[3] = {-.030f, -.088f, -.188f};
 __constant__ float c_scale[3] = {.458f, .448f, .450f};
 
 // one thread per pixel: reads the 3x3x3 neighbourhood (L1/L2 cached), writes 64 bytes
-__global__ void __launch_bounds__(256) lpips_prep_kernel(const float* img, const float* target, __nv_bfloat16* col, float* mse, int R, int do_col) {
+__global__ void __launch_bounds__(256) lpips_prep_kernel(const float* img, const float* target, __nv_bfloat16* col, float* mse, int R, int do_col, bool f16) {
   const int b = blockIdx.y;
   const long long HW = (long long)R * R;
   float local = 0.f;
@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(256) lpips_prep_kernel(const float* img, const
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         uint4 u;
-        u.x = pack_bf16(v[q * 8], v[q * 8 + 1]); u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-        u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        u.x = pack16(v[q * 8], v[q * 8 + 1], f16); u.y = pack16(v[q * 8 + 2], v[q * 8 + 3], f16);
+        u.z = pack16(v[q * 8 + 4], v[q * 8 + 5], f16); u.w = pack16(v[q * 8 + 6], v[q * 8 + 7], f16);
         op[q] = u;
       }
     }
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) lpips_prep_bwd_kernel(const __nv_bfloat16
   }
 }
 
-__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, int H, int W, int C) {
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, int H, int W, int C, bool f16) {
   const int b = blockIdx.y, vecs = C / 8, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)Ho * Wo * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -95,17 +95,17 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* 
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C + cv * 8));
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); m[e * 2] = fmaxf(m[e * 2], f.x); m[e * 2 + 1] = fmaxf(m[e * 2 + 1], f.y); }
+      for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], f16); m[e * 2] = fmaxf(m[e * 2], f.x); m[e * 2 + 1] = fmaxf(m[e * 2 + 1], f.y); }
     }
     uint4 o;
-    o.x = pack_bf16(m[0], m[1]); o.y = pack_bf16(m[2], m[3]); o.z = pack_bf16(m[4], m[5]); o.w = pack_bf16(m[6], m[7]);
+    o.x = pack16(m[0], m[1], f16); o.y = pack16(m[2], m[3], f16); o.z = pack16(m[4], m[5], f16); o.w = pack16(m[6], m[7], f16);
     *reinterpret_cast<uint4*>(y + (((long long)b * Ho + yo) * Wo + xo) * C + cv * 8) = o;
   }
 }
 
 // dx[b,y,x,c] = ((first arg-max of the 2x2 window ? dy : 0) + extra) * (x > 0)      (x is a post-ReLU tensor)
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* extra,
-                                                           __nv_bfloat16* dx, int H, int W, int C) {
+                                                           __nv_bfloat16* dx, int H, int W, int C, bool f16) {
   const int b = blockIdx.y, vecs = C / 8, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)Ho * Wo * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* 
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off[k]));
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) { const float2 f = unpack_bf16(w4[e]); v[k][e * 2] = f.x; v[k][e * 2 + 1] = f.y; }
+      for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], f16); v[k][e * 2] = f.x; v[k][e * 2 + 1] = f.y; }
     }
     int arg[8];
 #pragma unroll
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* 
 // covers 32/LPP pixels and every lane is busy for all VGG widths (64..512); reductions are xor-shuffles inside the group.
 template <int MODE, int VPL>
 __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f, const __nv_bfloat16* n1, const float* lin, const float* coef,
-                                                         __nv_bfloat16* outp, float* val, long long HW, int C, int relu_mask) {
+                                                         __nv_bfloat16* outp, float* val, long long HW, int C, int relu_mask, bool f16) {
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpp = (C / 8) / VPL;            // lanes per pixel: 8, 16 or 32
   const int ppw = 32 / lpp;                 // pixels per warp
@@ -187,12 +187,12 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f,
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(f + row) + q * lpp + ll);
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int e = 0; e < 4; e++) { const float2 v = unpack_bf16(w4[e]); x[q][e * 2] = v.x; x[q][e * 2 + 1] = v.y; ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); }
+      for (int e = 0; e < 4; e++) { const float2 v = unpack16(w4[e], f16); x[q][e * 2] = v.x; x[q][e * 2 + 1] = v.y; ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); }
       if (MODE != 0) {
         const uint4 un = __ldg(reinterpret_cast<const uint4*>(n1 + row) + q * lpp + ll);
         const uint32_t n4[4] = {un.x, un.y, un.z, un.w};
 #pragma unroll
-        for (int e = 0; e < 4; e++) { const float2 v = unpack_bf16(n4[e]); t[q][e * 2] = v.x; t[q][e * 2 + 1] = v.y; }
+        for (int e = 0; e < 4; e++) { const float2 v = unpack16(n4[e], f16); t[q][e * 2] = v.x; t[q][e * 2 + 1] = v.y; }
       }
     }
     for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f,
 #pragma unroll
         for (int q = 0; q < VPL; q++) {
           uint4 u;
-          u.x = pack_bf16(x[q][0] * inv, x[q][1] * inv); u.y = pack_bf16(x[q][2] * inv, x[q][3] * inv);
-          u.z = pack_bf16(x[q][4] * inv, x[q][5] * inv); u.w = pack_bf16(x[q][6] * inv, x[q][7] * inv);
+          u.x = pack16(x[q][0] * inv, x[q][1] * inv, f16); u.y = pack16(x[q][2] * inv, x[q][3] * inv, f16);
+          u.z = pack16(x[q][4] * inv, x[q][5] * inv, f16); u.w = pack16(x[q][6] * inv, x[q][7] * inv, f16);
           reinterpret_cast<uint4*>(outp + row)[q * lpp + ll] = u;
         }
       }
@@ -277,7 +277,7 @@ using namespace mgf;
 extern "C" int mgf_lpips_prep(const float* img, const float* target, void* col, float* mse, int B, int R, void* stream) {
   if (!img || (!col && !target) || (target && !mse)) MGF_FAIL(MGF_E_BADARG, "lpips_prep: null tensor");
   dim3 grid(gridp((long long)R * R), B);
-  lpips_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, target, (__nv_bfloat16*)col, mse, R, col != nullptr);
+  lpips_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, target, (__nv_bfloat16*)col, mse, R, col != nullptr, fwd_f16());
   MGF_CHECK_LAUNCH("lpips_prep");
   return 0;
 }
@@ -292,7 +292,7 @@ extern "C" int mgf_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int
   if (!x || !y) MGF_FAIL(MGF_E_BADARG, "maxpool2_fwd: null tensor");
   if (C % 8 || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "maxpool2_fwd: C%%8, H%%2, W%%2 must be 0");
   dim3 grid(gridp((long long)(H / 2) * (W / 2) * (C / 8)), B);
-  maxpool2_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C);
+  maxpool2_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C, fwd_f16());
   MGF_CHECK_LAUNCH("maxpool2_fwd");
   return 0;
 }
@@ -300,7 +300,7 @@ extern "C" int mgf_maxpool2_bwd(const void* x, const void* dy, const void* extra
   if (!x || !dy || !dx) MGF_FAIL(MGF_E_BADARG, "maxpool2_bwd: null tensor");
   if (C % 8 || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "maxpool2_bwd: C%%8, H%%2, W%%2 must be 0");
   dim3 grid(gridp((long long)(H / 2) * (W / 2) * (C / 8)), B);
-  maxpool2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)extra, (__nv_bfloat16*)dx, H, W, C);
+  maxpool2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)extra, (__nv_bfloat16*)dx, H, W, C, fwd_f16());
   MGF_CHECK_LAUNCH("maxpool2_bwd");
   return 0;
 }
@@ -315,7 +315,7 @@ extern "C" int mgf_lpips_head(int mode, const void* f, const void* n1, const flo
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *fp = (const __nv_bfloat16*)f, *np = (const __nv_bfloat16*)n1;
   __nv_bfloat16* op = (__nv_bfloat16*)out;
-#define MGF_HEAD(M, V) lpips_head_kernel<M, V><<<grid, 256, 0, st>>>(fp, np, lin, coef, op, val, HW, C, relu_mask)
+#define MGF_HEAD(M, V) lpips_head_kernel<M, V><<<grid, 256, 0, st>>>(fp, np, lin, coef, op, val, HW, C, relu_mask, fwd_f16())
   if (vpl == 1) { if (mode == 0) MGF_HEAD(0, 1); else if (mode == 1) MGF_HEAD(1, 1); else MGF_HEAD(2, 1); }
   else { if (mode == 0) MGF_HEAD(0, 2); else if (mode == 1) MGF_HEAD(1, 2); else MGF_HEAD(2, 2); }
 #undef MGF_HEAD

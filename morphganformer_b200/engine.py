@@ -112,13 +112,13 @@ class SynthesisEngine:
             blk = getattr(self.net, f"b{r}")
             e = {"res": r, "stem": blk.stem, "last": blk.is_last}
             if blk.stem:
-                e["const"] = blk.const.detach().float().permute(1, 2, 0).contiguous().to(torch.bfloat16)   # [4,4,C]
+                e["const"] = blk.const.detach().float().permute(1, 2, 0).contiguous()                       # [4,4,C] fp32 master
                 e["conv1"] = self._fold_layer(blk.conv1, w_idx, gain=1.0); w_idx += 1
             else:
                 e["conv0"] = self._fold_layer(blk.conv0, w_idx, gain=1.0); w_idx += 1
                 e["conv1"] = self._fold_layer(blk.conv1, w_idx, gain=SQRT_HALF); w_idx += 1
                 wsk = (blk.skip.weight.detach().float() * float(blk.skip.w_gain))[:, :, 0, 0]                 # [O, I]
-                e["skip_f"] = wsk.reshape(1, 1, *wsk.shape).to(torch.bfloat16).contiguous()                    # [1,1,O,I]
+                e["skip_f32"] = wsk.reshape(1, 1, *wsk.shape).contiguous()                                      # [1,1,O,I] fp32 master
                 e["skip_b"] = wsk.t().reshape(1, 1, wsk.shape[1], wsk.shape[0]).to(torch.bfloat16).contiguous()  # [1,1,I,O]
                 f1 = np.array([1, 3, 3, 1], dtype=np.float64); f1 = f1 / f1.sum()
                 e["fk4"] = (ctypes.c_float * 4)(*[float(v) for v in f1[::-1]])
@@ -190,9 +190,12 @@ class SynthesisEngine:
         return L
 
     # -------------------------------------------------------------------------------------------- buffers
-    def _buf(self, st, name, shape, dtype=torch.bfloat16, zero=False):
+    def _buf(self, st, name, shape, dtype=torch.bfloat16, zero=False, fwd=False):
+        """fwd=True: a forward-dtype tensor (bf16 or fp16 per _lib.set_forward_dtype); default bf16 = gradient tensors."""
+        if fwd:
+            dtype = _lib.forward_torch_dtype()
         t = st.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
             st[name] = t
         return t
@@ -213,15 +216,22 @@ class SynthesisEngine:
                                       B, L.I, L.O, wg.shape[1], _s(self.dev)), "mgf_style_fwd")
         return s, d
 
-    def _modulate(self, base, rs, nmod, cs, out, B):
+    def _modulate(self, base, rs, nmod, cs, out, B, out_fwd):
         T, NT, K = base.shape
-        _lib.check(_L().mgf_modulate_weights(_p(base), _p(rs), nmod, _p(cs), _p(out), B, T, NT, K, _s(self.dev)), "mgf_modulate_weights")
+        _lib.check(_L().mgf_modulate_weights(_p(base), _p(rs), nmod, _p(cs), _p(out), int(out_fwd), B, T, NT, K, _s(self.dev)), "mgf_modulate_weights")
+
+    def _skip_f(self, e):
+        dt = _lib.forward_torch_dtype()
+        w = e.get("skip_f")
+        if w is None or w.dtype != dt:
+            w = e["skip_f"] = e["skip_f32"].to(dt).contiguous()
+        return w
 
     def _layer_fwd(self, L, x_in, ws, maskbias, st, B, noise_on, add=None):
         """x_in [B,h,w,I] bf16 -> z [B,H,W,O] bf16 (post noise/bias/act)."""
         s, d = self._styles(L, ws, st, B)
-        Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape))
-        self._modulate(L.Bf, d, L.O, s, Wf, B)
+        Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape), fwd=True)
+        self._modulate(L.Bf, d, L.O, s, Wf, B, True)
         h, w = x_in.shape[1], x_in.shape[2]
         H, Wd = h * L.up, w * L.up
         st[f"xin{L.idx}"] = x_in
@@ -229,17 +239,17 @@ class SynthesisEngine:
         nstr = L.nstr if noise is not None else None
         kw = dict(osy=L.up, osx=L.up, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1))
         if L.attn:
-            y = self._buf(st, f"y{L.idx}", (B, H, Wd, L.O))
+            y = self._buf(st, f"y{L.idx}", (B, H, Wd, L.O), fwd=True)
             tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
             VM = self._buf(st, f"VM{L.idx}", (B, 16, L.O), torch.float32)
             comps = ws[:, :-1, L.idx]                           # [B,16,32] strided
             _lib.check(_L().mgf_small_gemm(_p(comps), comps.stride(0), comps.stride(1), _p(L.WVM), _p(L.bVM), _p(VM),
                                            16 * L.O, L.O, B, 16, L.O, comps.shape[2], 0, _s(self.dev)), "mgf_small_gemm")
-            z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O))
+            z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             _lib.check(_L().mgf_attn_fwd(_p(y), _p(L.Kf), _p(L.Sc), _p(maskbias), _p(VM), _p(L.bm), _p(noise), _p(nstr), _p(L.bias),
                                          L.gain, LRELU_ALPHA, _p(z), None, B, H * Wd, L.O, _s(self.dev)), "mgf_attn_fwd")
         else:
-            z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O))
+            z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, z, noise=noise, noise_strength=nstr, bias=L.bias,
                        act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, add=add, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
         return z
@@ -262,7 +272,7 @@ class SynthesisEngine:
         for e in self.blocks:
             r = e["res"]
             if e["stem"]:
-                x_in = self._buf(st, "const", (B,) + tuple(e["const"].shape))
+                x_in = self._buf(st, "const", (B,) + tuple(e["const"].shape), fwd=True)
                 x_in.copy_(e["const"].unsqueeze(0).expand(B, -1, -1, -1))
                 x = self._layer_fwd(e["conv1"], x_in, ws, maskbias, st, B, noise_on)
             else:
@@ -271,9 +281,9 @@ class SynthesisEngine:
                 z1 = self._layer_fwd(e["conv1"], z0, ws, maskbias, st, B, noise_on)
                 O, I = e["conv0"].O, e["conv0"].I
                 h = x_in.shape[1]
-                v = self._buf(st, f"v{r}", (B, h, h, O))
-                tc.conv_tc([x_in], e["skip_f"], [(0, 0, 0, 0)], (B, h, h), 1, O, v, tag="g.fwd")
-                x = self._buf(st, f"xout{r}", (B, r, r, O))
+                v = self._buf(st, f"v{r}", (B, h, h, O), fwd=True)
+                tc.conv_tc([x_in], self._skip_f(e), [(0, 0, 0, 0)], (B, h, h), 1, O, v, tag="g.fwd")
+                x = self._buf(st, f"xout{r}", (B, r, r, O), fwd=True)
                 _lib.check(_L().mgf_upfir2_add(_p(v), _p(z1), _p(x), e["fk4"], e["skip_gain"], B, h, h, O, _s(self.dev)), "mgf_upfir2_add")
             if e["last"]:
                 yl = self._layer_fwd(e["conv_last"], x, ws, maskbias, st, B, noise_on)
@@ -292,7 +302,7 @@ class SynthesisEngine:
         """dy [B,H,W,O] (gradient wrt this layer's conv output) -> out [B,h,w,I] = d x_in; accumulates d(styles)."""
         d = st[f"d{L.idx}"]; s = st[f"s{L.idx}"]
         Wb = self._buf(st, f"Wb{L.idx}", (B,) + tuple(L.Bb.shape))
-        self._modulate(L.Bb, None, 1, d, Wb, B)
+        self._modulate(L.Bb, None, 1, d, Wb, B, False)
         x_in = st[f"xin{L.idx}"]
         h, w = x_in.shape[1], x_in.shape[2]
         ds = self._buf(st, f"ds{L.idx}", (B, L.I), torch.float32)
@@ -300,7 +310,7 @@ class SynthesisEngine:
         acts = [dy] if L.up == 1 else [tc.phase_view(dy, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
         tc.conv_tc(acts, Wb, L.taps_b, (B, h, w), 1, L.I, out, scale_n=s, reduce_out=ds, X=x_in, add=add,
                    actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain, reduce_per_sample=True,
-                   alg_scale=1.0 / L.phases, tag="g.bwd")
+                   alg_scale=1.0 / L.phases, tag="g.bwd", fwd=False)
         return ds
 
     def _style_bwd(self, L, ds, R, st, dws, B):
@@ -376,7 +386,7 @@ class SynthesisEngine:
             dv = self._buf(st, f"dv{r}", (B, h, h, L0.O))
             _lib.check(_L().mgf_upfir2_bwd(_p(g), _p(dv), e["fk4"], e["skip_gain"], B, h, h, L0.O, _s(self.dev)), "mgf_upfir2_bwd")
             gs = self._buf(st, f"gs{r}", tuple(x_in.shape))
-            tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd")
+            tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd", fwd=False)
             # conv1
             z0 = st[f"z{L0.idx}"]
             dy1, R1 = self._attn_bwd(L1, g, st, dws, B) if L1.attn else self._act_bwd(L1, g, st[f"z{L1.idx}"], st, B, 0)

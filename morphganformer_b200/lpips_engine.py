@@ -42,21 +42,31 @@ class LpipsEngine:
             if i == 0:
                 wc = torch.zeros(O, 32, device=self.dev)
                 wc[:, :27] = w.permute(0, 2, 3, 1).reshape(O, 27)                    # column index = (ky*3+kx)*3 + c
-                self.wf.append(wc.reshape(1, 1, O, 32).to(torch.bfloat16).contiguous())
+                self.wf.append(wc.reshape(1, 1, O, 32).contiguous())                      # fp32 master, cast per forward dtype
                 self.wb.append(wc.t().reshape(1, 1, 32, O).to(torch.bfloat16).contiguous())
             else:
                 wk = w.reshape(O, I, 9)
-                self.wf.append(wk.permute(2, 0, 1).reshape(1, 9, O, I).to(torch.bfloat16).contiguous())
+                self.wf.append(wk.permute(2, 0, 1).reshape(1, 9, O, I).contiguous())
                 self.wb.append(wk.permute(2, 1, 0).reshape(1, 9, I, O).to(torch.bfloat16).contiguous())
             self.bias.append(b)
         self.lin = [state_dict[f"lin{k}.model.1.weight"].detach().float().reshape(-1).to(self.dev).contiguous() for k in range(5)]
         self._st = {}
+        self._wf16 = {}
         self.n1 = None
         self.target = None
 
-    def _buf(self, name, shape, dtype=torch.bfloat16):
+    def _wfwd(self, ci):
+        dt = _lib.forward_torch_dtype()
+        w = self._wf16.get(ci)
+        if w is None or w.dtype != dt:
+            w = self._wf16[ci] = self.wf[ci].to(dt).contiguous()
+        return w
+
+    def _buf(self, name, shape, dtype=torch.bfloat16, fwd=False):
+        if fwd:
+            dtype = _lib.forward_torch_dtype()
         t = self._st.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(shape, dtype=dtype, device=self.dev)
             self._st[name] = t
         return t
@@ -65,21 +75,21 @@ class LpipsEngine:
         """Runs the VGG trunk; returns the list of conv outputs h[i] (post-ReLU, NHWC bf16) and pooled tensors."""
         B, _, R, _ = img.shape
         s = _lib.stream_ptr(self.dev)
-        col = self._buf(tag + "col", (B, R, R, 32))
+        col = self._buf(tag + "col", (B, R, R, 32), fwd=True)
         _lib.check(_L().mgf_lpips_prep(_p(img), _p(target), _p(col), _p(mse), B, R, s), "mgf_lpips_prep")
         h, x, res, ci = [], col, R, 0
         pooled = {}
         for item in VGG:
             if item == "P":
-                y = self._buf(f"{tag}p{ci}", (B, res // 2, res // 2, x.shape[3]))
+                y = self._buf(f"{tag}p{ci}", (B, res // 2, res // 2, x.shape[3]), fwd=True)
                 _lib.check(_L().mgf_maxpool2_fwd(_p(x), _p(y), B, res, res, x.shape[3], s), "mgf_maxpool2_fwd")
                 pooled[ci] = y
                 x, res = y, res // 2
                 continue
             cin, cout = item
-            y = self._buf(f"{tag}h{ci}", (B, res, res, cout))
+            y = self._buf(f"{tag}h{ci}", (B, res, res, cout), fwd=True)
             taps = [(0, 0, 0, 0)] if ci == 0 else tc.TAPS_3X3
-            tc.conv_tc([x], self.wf[ci], taps, (B, res, res), 1, cout, y, bias=self.bias[ci], act=2, gain=1.0,
+            tc.conv_tc([x], self._wfwd(ci), taps, (B, res, res), 1, cout, y, bias=self.bias[ci], act=2, gain=1.0,
                        alg_scale=27.0 / 32.0 if ci == 0 else 1.0, tag="vgg.fwd")
             h.append(y)
             x = y
@@ -94,6 +104,8 @@ class LpipsEngine:
             self.target.copy_(target)                   # keep addresses stable (CUDA-graph replay of the step)
         else:
             self.target = target.contiguous().clone()
+            self.n1 = None
+        if self.n1 is not None and self.n1[0].dtype != _lib.forward_torch_dtype():
             self.n1 = None
         target = self.target
         B = target.shape[0]
@@ -154,7 +166,7 @@ class LpipsEngine:
             if prev_is_pool:
                 # d(pooled input) -> route through the pool to conv ci-1's output, add its tap gradient, apply its ReLU mask
                 dp = self._buf(f"dp{ci}", (B, res, res, cin))
-                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, dp, tag="vgg.bwd")
+                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, dp, tag="vgg.bwd", fwd=False)
                 src = h[ci - 1]
                 extra = head_bwd(ci - 1, False) if (ci - 1) in TAP_AFTER else None
                 g2 = self._buf(f"dpre{ci - 1}", tuple(src.shape))
@@ -164,12 +176,12 @@ class LpipsEngine:
             else:
                 src = h[ci - 1]
                 g2 = self._buf(f"dpre{ci - 1}", tuple(src.shape))
-                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, g2, X=src, actgrad=True, ag_alpha=0.0, ag_gain=1.0, tag="vgg.bwd")
+                tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, g2, X=src, actgrad=True, ag_alpha=0.0, ag_gain=1.0, tag="vgg.bwd", fwd=False)
                 g = g2
                 pos -= 1
             ci -= 1
         dcol = self._buf("dcol", (B, R, R, 32))
-        tc.conv_tc([g], self.wb[0], [(0, 0, 0, 0)], (B, R, R), 1, 32, dcol, alg_scale=27.0 / 32.0, tag="vgg.bwd")
+        tc.conv_tc([g], self.wb[0], [(0, 0, 0, 0)], (B, R, R), 1, 32, dcol, alg_scale=27.0 / 32.0, tag="vgg.bwd", fwd=False)
         dimg = torch.empty_like(self.img)
         _lib.check(_L().mgf_lpips_prep_bwd(_p(dcol), _p(self.img), _p(self.target), float(mse_coef), _p(dimg), B, R, s), "mgf_lpips_prep_bwd")
         return dimg

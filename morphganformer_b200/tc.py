@@ -29,7 +29,8 @@ class ConvTcDesc(ctypes.Structure):
                 ("act", c_int32), ("alpha", c_float), ("gain", c_float),
                 ("add", c_void_p),
                 ("actgrad", c_int32), ("ag_alpha", c_float), ("ag_gain", c_float),
-                ("bn", c_int32), ("reduce_per_sample", c_int32)]
+                ("bn", c_int32), ("reduce_per_sample", c_int32),
+                ("ab_fwd", c_int32), ("out_fwd", c_int32), ("x_fwd", c_int32), ("add_fwd", c_int32)]
 
 
 _lib.SIGNATURES["mgf_conv_tc"] = (ctypes.c_int, [ctypes.POINTER(ConvTcDesc), c_void_p])
@@ -37,7 +38,7 @@ _lib.SIGNATURES["mgf_conv_tc"] = (ctypes.c_int, [ctypes.POINTER(ConvTcDesc), c_v
 
 def nhwc_view(t):
     """(ptr, C, W, H, N, sW, sH, sN) of a [N, H, W, C] bf16 tensor (any strides with channel stride 1)."""
-    assert t.dtype == torch.bfloat16 and t.ndim == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
+    assert t.dtype in (torch.bfloat16, torch.float16) and t.ndim == 4 and t.stride(3) == 1, (t.dtype, t.shape, t.stride())
     n, h, w, c = t.shape
     return (t.data_ptr(), c, w, h, n, t.stride(2), t.stride(1), t.stride(0))
 
@@ -54,7 +55,9 @@ PROFILE = None
 
 def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 0), ofx=(0, 0, 0, 0), scale_n=None,
             reduce_out=None, X=None, noise=None, noise_strength=None, bias=None, act=0, alpha=0.2, gain=1.0, add=None,
-            actgrad=False, ag_alpha=0.2, ag_gain=1.0, bn=0, reduce_per_sample=False, alg_scale=1.0, tag=""):
+            actgrad=False, ag_alpha=0.2, ag_gain=1.0, bn=0, reduce_per_sample=False, alg_scale=1.0, tag="", fwd=True):
+    # fwd=True: a forward launch -- operands, output and `add` are forward-dtype tensors (bf16 or fp16, _lib.set_forward_dtype);
+    # fwd=False: a gradient launch -- operands/output/add are bf16 gradients; X (saved activation) is a forward tensor either way.
     """acts: list of NHWC bf16 tensors or descriptor tuples; w: [G, T, NT, K] bf16 contiguous; taps: [(amap, dy, dx, wz)];
     grid: (NB, GH, GW); out: [NB, OH, OW, OC] bf16 contiguous."""
     d = ConvTcDesc()
@@ -62,21 +65,25 @@ def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 
     for i, a in enumerate(acts):
         v = a if isinstance(a, tuple) else nhwc_view(a)
         d.a[i] = TcAct(*v)
-    assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.ndim == 4
+    h16 = (torch.bfloat16, torch.float16)
+    want = _lib.forward_torch_dtype() if fwd else torch.bfloat16
+    assert w.dtype == want and w.is_contiguous() and w.ndim == 4, (w.dtype, want)
     d.w, d.w_G, d.w_T, d.w_NT, d.w_K = w.data_ptr(), w.shape[0], w.shape[1], w.shape[2], w.shape[3]
     d.ntaps = len(taps)
     for i, (am, dy, dx, wz) in enumerate(taps):
         d.taps[i] = TcTap(am, dy, dx, 0, wz)
     d.NB, d.GH, d.GW = grid
     d.phases, d.Cout = phases, cout
-    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.ndim == 4
+    assert out.dtype == want and out.is_contiguous() and out.ndim == 4, (out.dtype, want)
+    d.ab_fwd = d.out_fwd = d.add_fwd = int(bool(fwd))
+    d.x_fwd = 1
     d.out, d.OH, d.OW, d.OC = out.data_ptr(), out.shape[1], out.shape[2], out.shape[3]
     d.osy, d.osx = osy, osx
     for i in range(4):
         d.ofy[i], d.ofx[i] = ofy[i], ofx[i]
-    for name, t, dt in (("scale_n", scale_n, torch.float32), ("reduce_out", reduce_out, torch.float32), ("X", X, torch.bfloat16),
+    for name, t, dt in (("scale_n", scale_n, torch.float32), ("reduce_out", reduce_out, torch.float32), ("X", X, _lib.forward_torch_dtype()),
                         ("noise", noise, torch.float32), ("noise_strength", noise_strength, torch.float32),
-                        ("bias", bias, torch.float32), ("add", add, torch.bfloat16)):
+                        ("bias", bias, torch.float32), ("add", add, want)):
         if t is not None:
             assert t.dtype == dt and t.is_contiguous(), name
             setattr(d, name, t.data_ptr())
@@ -102,4 +109,4 @@ TAPS_3X3 = [(0, ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(
 def pack_w3x3(w):
     """[Cout, Cin, 3, 3] (correlation weights, as F.conv2d) -> [1, 9, Cout, Cin] bf16."""
     co, ci, kh, kw = w.shape
-    return w.permute(2, 3, 0, 1).reshape(1, kh * kw, co, ci).to(torch.bfloat16).contiguous()
+    return w.permute(2, 3, 0, 1).reshape(1, kh * kw, co, ci).to(_lib.forward_torch_dtype()).contiguous()

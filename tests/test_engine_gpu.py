@@ -7,7 +7,17 @@ from oracle import ganformer
 import util
 
 pytestmark = pytest.mark.gpu
-BF16_MAXABS, BF16_RELRMS = 4e-2, 2e-2
+# (max-abs as a fraction of the image range, relative RMS).  fp16-forward mode meets the north_star's 1e-2 max-abs bar;
+# bf16 forward storage does not (2^-9 rounding of every stored tile, ~25 deep) -- its measured envelope is asserted instead.
+TOL = {"bf16": (4e-2, 2e-2), "fp16": (1e-2, 3e-3)}
+
+
+@pytest.fixture(params=["bf16", "fp16"])
+def fwd_dtype(request):
+    from morphganformer_b200 import _lib
+    _lib.set_forward_dtype(request.param)
+    yield request.param
+    _lib.set_forward_dtype("bf16")
 
 
 def _setup(res, cb, cm, B, seed=0):
@@ -19,7 +29,7 @@ def _setup(res, cb, cm, B, seed=0):
 
 
 @pytest.mark.parametrize("cfg", [(64, 2048, 64, 2), (32, 32768, 128, 3)])
-def test_tc_engine_image_within_bf16_tolerance(cfg):
+def test_tc_engine_image_within_tolerance(cfg, fwd_dtype):
     res, cb, cm, B = cfg
     G, sd, ws, mask = _setup(res, cb, cm, B)
     ref = ganformer.synthesis(sd, ws, sd["pos"], mask, res)
@@ -29,13 +39,11 @@ def test_tc_engine_image_within_bf16_tolerance(cfg):
     e = img.cpu() - ref
     err, rel_rms = e.abs().max().item(), (e.square().mean().sqrt() / ref.square().mean().sqrt()).item()
     print("img max-abs err", err, "scale", ref.abs().max().item(), "rel rms", rel_rms)
-    # bf16 storage of every activation/weight tile (2^-9 per rounding, ~25 roundings deep): measured 1.4e-2 rel-RMS / 2.7e-2 of
-    # the image range max-abs on these random-init nets.  The north_star's 1e-2 max-abs is NOT met by the bf16 engine yet
-    # ("precision"); the bound asserted here is the measured bf16 envelope so that real bugs (O(1) errors) fail.
-    assert err < BF16_MAXABS * max(1.0, ref.abs().max().item()) and rel_rms < BF16_RELRMS
+    maxabs, relrms = TOL[fwd_dtype]
+    assert err < maxabs * max(1.0, ref.abs().max().item()) and rel_rms < relrms, (fwd_dtype, err, rel_rms)
 
 
-def test_tc_engine_grads_wrt_ws():
+def test_tc_engine_grads_wrt_ws(fwd_dtype):
     res, cb, cm, B = 64, 2048, 64, 2
     G, sd, ws, mask = _setup(res, cb, cm, B)
     wsr = ws.clone().requires_grad_(True)
@@ -56,6 +64,7 @@ def test_tc_engine_grads_wrt_ws():
     # bf16 envelope: deepest slot (4x4 stem, 16 pixels, demodulation term cancels most of the direct style gradient) ~10 %
     assert err < 0.15 * scale, "dws err %g vs scale %g" % (err, scale)
     cos = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
+    print("dws cosine", cos, fwd_dtype)
     assert cos > 0.998, cos
 
 
@@ -66,6 +75,6 @@ def test_tc_engine_noise_none_and_mask():
     ref = ganformer.synthesis(sd, ws, sd["pos"], mask, res, noise_mode="none")
     Gc = G.cuda(); Gc.synthesis.engine = "tc"
     img, _ = Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=mask.cuda(), noise_mode="none")
-    assert (img.cpu() - ref).abs().max().item() < BF16_MAXABS * max(1.0, ref.abs().max().item())
+    assert (img.cpu() - ref).abs().max().item() < TOL["bf16"][0] * max(1.0, ref.abs().max().item())
     with pytest.raises(NotImplementedError):
         Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=mask.cuda(), noise_mode="random")

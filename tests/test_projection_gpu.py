@@ -42,13 +42,15 @@ def test_perceptual_loss_api_autograd():
     assert a.grad is not None and torch.isfinite(a.grad).all() and a.grad.abs().max() > 0
 
 
-@pytest.mark.parametrize("use_lpips", [False, True])
-def test_projection_loss_trajectory_matches_oracle(use_lpips):
+@pytest.mark.parametrize("use_lpips,fwd", [(False, "bf16"), (True, "bf16"), (True, "fp16")])
+def test_projection_loss_trajectory_matches_oracle(use_lpips, fwd):
     """N-step loss trajectory with injected noise.  The bf16 engine tracks the fp32 oracle to ~1.5e-2 relative
     per-step loss on this net (bf16 rounding of every stored activation; all 12 losses share one latent so the deviation is
     common-mode); asserted bound 3e-2.  The north_star's 1e-3 is met by the exact-fp32 ops path (test_synthesis_gpu.py),
     not yet by the bf16 engine -- DESIGN.md 'precision'."""
     from morphganformer_b200.projection import Projector, latent_stats
+    from morphganformer_b200 import _lib
+    _lib.set_forward_dtype(fwd)
     res, cb, cm, B, steps = 64, 2048, 64, 2, 6
     G = util.build_G(res, 0, cb, cm)
     gsd = util.state_dict_cpu(G)
@@ -65,9 +67,10 @@ def test_projection_loss_trajectory_matches_oracle(use_lpips):
         P.step()
     torch.cuda.synchronize()
     got = P.losses[:steps].cpu()
+    _lib.set_forward_dtype("bf16")
     print("oracle", ref["losses"].flatten().tolist())
-    print("engine", got.flatten().tolist())
-    np.testing.assert_allclose(got.numpy(), ref["losses"].numpy(), rtol=3e-2)
+    print("engine", fwd, got.flatten().tolist())
+    np.testing.assert_allclose(got.numpy(), ref["losses"].numpy(), rtol=3e-2 if fwd == "bf16" else 4e-3)
     dl = (P.latent.cpu() - ref["latent"]).abs().max().item()
     print("latent max diff after %d steps: %g" % (steps, dl))
     assert dl < 0.15
