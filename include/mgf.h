@@ -114,6 +114,8 @@ typedef struct {
   int32_t ab_fwd, out_fwd, x_fwd, add_fwd;
 } mgf_conv_tc_desc;
 int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream);
+/* debugging / A-B measurement: 0 disables the halo (shared-memory tap reuse) variant that mgf_conv_tc picks for C = 64/128 3x3 layers */
+int mgf_conv_tc_set_halo(int enabled);
 
 /* ---- bf16 synthesis-engine helpers (engine_kernels.cu); activations NHWC bf16, coefficients fp32 ------------------
  * style_fwd : s[b,i] = ((wg[b,:] . A[i,:]) * again + abias[i]) * sgain  (FullyConnectedLayer affine, networks.py:138-150, :1022,

@@ -54,6 +54,7 @@ struct alignas(64) Params {
   uint32_t tx_bytes;
   int total_tiles;
   uint32_t idesc; int out_f16, x_f16, add_f16;
+  int tiles_hw;      // halo kernel: tiles per image (tilesW * tilesH)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -148,96 +149,19 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
   return t;
 }
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ Params p) {
-  using C = Cfg<BN, BK>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
-  uint64_t* empty = full + C::STAGES;
-  uint64_t* tfull = empty + C::STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int iters = p.kchunks * p.ntaps;
-
-  if (warp == 8) {
-    if (lane == 0) {   // ------------------------------------------------ TMA producer
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BN);
-        const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
-        for (int kc = 0; kc < p.kchunks; kc++) {
-          for (int tp = 0; tp < p.ntaps; tp++) {
-            const Tap tap = p.taps[tp];
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], p.tx_bytes);
-            uint8_t* sa = smem + stage * C::STAGE;
-            tma_load_4d(&p.amap[tap.amap], &full[stage], sa, kc * BK, t.x0 + tap.dx, t.y0 + tap.dy, t.b0);
-            tma_load_3d(&p.bmap, &full[stage], sa + C::A_BYTES, kc * BK, t.n0, wbase + tap.wz);
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {   // ------------------------------------------------ MMA issuer
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int it = 0; it < iters; it++) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE);
-          const uint64_t adesc = make_desc<BK>(sa), bdesc = make_desc<BK>(sa + C::A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; k++)
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&empty[stage]);           // frees the smem slot once these MMAs have read it
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-        }
-        tc_commit(&tfull[as]);                // accumulator complete -> epilogue
-        if (++as == 2) { as = 0; aphase ^= 1; }
-      }
-    }
-  } else {             // ---------------------------------------------------- epilogue: two groups of 4 warps, group g owns accumulator stage g
-    const int as = warp >> 2; uint32_t aphase = 0;
-    const int wq = warp & 3;                 // TMEM lane quarter this warp may access
-    const int r = wq * 32 + lane;            // accumulator row == TMEM lane == pixel index inside the A box
-    const int tx = r % p.TW, ty = (r / p.TW) % p.TH, tb = r / (p.TW * p.TH);
-    const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
-    for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
-      const TileCoord t = decode_tile(p, tile, BN);
-      const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
-      const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
+// Fused layer tail for one 128 x BN accumulator tile (called by all four warps of an epilogue group after the tfull wait).
+// Row `valid`/(x, y, b) identify this thread's pixel; tacc = TMEM address of the tile (lane quarter already applied).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nstr) {
       const int phase_idx = t.n0 / p.Cout, co0 = t.n0 % p.Cout;
       const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
       const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
       const long long obase = pix * p.OC + co0;
       const float nz = (p.noise && valid) ? p.noise[oy * p.OW + ox] * nstr : 0.f;
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN + c * 32), raw);
+        tmem_ld32(tacc + (uint32_t)(c * 32), raw);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
@@ -325,6 +249,245 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           }
         }
       }
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ Params p) {
+  using C = Cfg<BN, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = p.kchunks * p.ntaps;
+
+  if (warp == 8) {
+    if (lane == 0) {   // ------------------------------------------------ TMA producer
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN);
+        const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
+        for (int kc = 0; kc < p.kchunks; kc++) {
+          for (int tp = 0; tp < p.ntaps; tp++) {
+            const Tap tap = p.taps[tp];
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], p.tx_bytes);
+            uint8_t* sa = smem + stage * C::STAGE;
+            tma_load_4d(&p.amap[tap.amap], &full[stage], sa, kc * BK, t.x0 + tap.dx, t.y0 + tap.dy, t.b0);
+            tma_load_3d(&p.bmap, &full[stage], sa + C::A_BYTES, kc * BK, t.n0, wbase + tap.wz);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {   // ------------------------------------------------ MMA issuer
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int it = 0; it < iters; it++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+          const uint64_t adesc = make_desc<BK>(sa), bdesc = make_desc<BK>(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++)
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty[stage]);           // frees the smem slot once these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[as]);                // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {             // ---------------------------------------------------- epilogue: two groups of 4 warps, group g owns accumulator stage g
+    const int as = warp >> 2; uint32_t aphase = 0;
+    const int wq = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = wq * 32 + lane;            // accumulator row == TMEM lane == pixel index inside the A box
+    const int tx = r % p.TW, ty = (r / p.TW) % p.TH, tb = r / (p.TW * p.TH);
+    const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
+    for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
+      const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr);
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      aphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+
+// ================================================================================================================
+// Halo variant for narrow layers (C = 64 or 128, 3x3 taps, large images).  The generic kernel above re-loads a shifted A tile
+// from L2 for each of the 9 taps and re-fetches the weight tile for every output tile; for C <= 128 that L2->shared-memory
+// traffic, not HBM or the tensor pipe, is the limiter (profiles/r01_conv_tc_ncu_full.md).  Here
+//   * ONE haloed activation tile {64 ch, 16 px, 18 rows} is loaded per channel chunk (the output tile is 8 px x 16 rows; the
+//     16-pixel pitch makes every 8-row core-matrix group start on a 1024-byte swizzle-atom boundary) and the 9 taps are just 9
+//     shared-memory descriptors into it: start = tile + (dy*16+dx)*128 B, SBO = 2048 B (swizzle phase follows the address bits),
+//   * the 3x3 weights of the current (sample, N-block) stay resident in shared memory across tiles (KC*9 tiles of BN x 64),
+//     re-loaded only when the CTA moves to another sample / N-block.
+// L2->SM traffic per 128-pixel tile drops from 9*(16+BN/8) KB to 36 KB per channel chunk.
+template <int BN, int KC>
+struct HaloCfg {
+  static constexpr int A_STAGE = 288 * 128;                       // 18 rows x 16 px x 128 B
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int B_BYTES = KC * 9 * B_TILE;
+  static constexpr int SMEM_MAX = 227 * 1024;
+  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2048) / A_STAGE;
+  static constexpr int NS = NS_RAW > 6 ? 6 : NS_RAW;
+  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static_assert(NS >= 2, "halo kernel needs at least two activation stages");
+};
+
+__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr) {
+  // K-major, 128B swizzle, rows of a core-matrix group 128 B apart, groups (8 px = one tile row) 2048 B apart.
+  // base_offset stays 0: measured on B200 (scripts/debug_halo.py) the swizzle XOR is taken from the shared-memory ADDRESS bits,
+  // exactly like the TMA write side, so a start address shifted by dx*128 B inside the atom needs no phase correction
+  // (setting base_offset = dx, as a literal reading of the descriptor format suggests, corrupts the dx != -1 taps).
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct HaloTile { int n0, x0, y0, b0, key; };
+__device__ __forceinline__ HaloTile decode_halo(const Params& p, int tile, int BN) {
+  HaloTile t;
+  const int m = tile % p.tiles_hw; t.key = tile / p.tiles_hw;      // key = b * n_tiles + n_blk: consecutive tiles share the weights
+  t.n0 = (t.key % p.n_tiles) * BN; t.b0 = t.key / p.n_tiles;
+  t.x0 = (m % p.tilesW) * 8; t.y0 = (m / p.tilesW) * 16;
+  return t;
+}
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant__ Params p) {
+  using C = HaloCfg<BN, KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + C::B_BYTES;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sA + C::NS * C::A_STAGE);
+  uint64_t* aempty = afull + C::NS;
+  uint64_t* bfull = aempty + C::NS;
+  uint64_t* tfull = bfull + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NS; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    mbar_init(bfull, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {   // ------------------------------------------------ TMA producer
+      int stage = 0; uint32_t phase = 0; int cur_key = -1; int last_stage = -1; uint32_t last_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const HaloTile t = decode_halo(p, tile, BN);
+        if (t.key != cur_key) {
+          // the resident weights are about to be overwritten: every MMA issued so far must have finished reading them.
+          // MMAs complete in order, so waiting for the consumption of the most recently issued activation stage is enough.
+          if (last_stage >= 0) mbar_wait(&aempty[last_stage], last_phase);
+          mbar_arrive_expect_tx(bfull, (uint32_t)C::B_BYTES);
+          const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
+          for (int kc = 0; kc < KC; kc++)
+            for (int tp = 0; tp < 9; tp++)
+              tma_load_3d(&p.bmap, bfull, sB + (kc * 9 + tp) * C::B_TILE, kc * 64, t.n0, wbase + p.taps[tp].wz);
+          cur_key = t.key;
+        }
+        for (int kc = 0; kc < KC; kc++) {
+          mbar_wait(&aempty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&afull[stage], (uint32_t)C::A_STAGE);
+          tma_load_4d(&p.amap[0], &afull[stage], sA + stage * C::A_STAGE, kc * 64, t.x0 - 1, t.y0 - 1, t.b0);
+          last_stage = stage; last_phase = phase;
+          if (++stage == C::NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {   // ------------------------------------------------ MMA issuer
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; int cur_key = -1; uint32_t bphase = 0;
+      const uint32_t sB_addr = smem_u32(sB);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const HaloTile t = decode_halo(p, tile, BN);
+        if (t.key != cur_key) { mbar_wait(bfull, bphase); bphase ^= 1; cur_key = t.key; }
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kc = 0; kc < KC; kc++) {
+          mbar_wait(&afull[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sA + stage * C::A_STAGE);
+#pragma unroll
+          for (int tp = 0; tp < 9; tp++) {
+            const int hy = p.taps[tp].dy + 1, hx = p.taps[tp].dx + 1;          // position of the tap inside the halo
+            const uint64_t adesc = make_desc_halo(sa + (uint32_t)((hy * 16 + hx) * 128));
+            const uint64_t bdesc = make_desc<64>(sB_addr + (uint32_t)((kc * 9 + tp) * C::B_TILE));
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc > 0 || tp > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&aempty[stage]);
+          if (++stage == C::NS) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {             // ---------------------------------------------------- epilogue groups
+    const int as = warp >> 2; uint32_t aphase = 0;
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const int tx = r & 7, ty = r >> 3;
+    const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
+    for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
+      const HaloTile h = decode_halo(p, tile, BN);
+      TileCoord t; t.n0 = h.n0; t.x0 = h.x0; t.y0 = h.y0; t.b0 = h.b0;
+      const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0;
+      const bool valid = x < p.GW && y < p.GH;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       aphase ^= 1;
@@ -380,8 +543,26 @@ static int launch(const Params& p, int grid, cudaStream_t st) {
   return 0;
 }
 
+template <int BN, int KC>
+static int launch_halo(const Params& p, int grid, cudaStream_t st) {
+  using C = HaloCfg<BN, KC>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc(halo): cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  conv_halo_kernel<BN, KC><<<grid, 320, C::SMEM, st>>>(p);
+  MGF_CHECK_LAUNCH("conv_tc(halo)");
+  return 0;
+}
+
+static bool g_halo_enabled = true;
+
 }  // namespace tc
 }  // namespace mgf
+
+extern "C" int mgf_conv_tc_set_halo(int enabled) { mgf::tc::g_halo_enabled = enabled != 0; return 0; }
 
 extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   using namespace mgf;
@@ -408,6 +589,68 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
 
   Params p;
   memset(&p, 0, sizeof(p));
+  // ---- halo variant: 3x3 taps in {-1,0,1}^2 on one activation map, C = 64 or 128, images large enough that a CTA keeps the
+  // resident weights for many tiles
+  // (measured: a win for C = 64 -- 0.95 -> 0.68 ms on 64->64 @1024^2 x8 -- but not for C = 128, where the generic kernel's
+  // 128-wide N tile beats two 64-wide halo passes; scripts/bench_conv_tc.py)
+  bool halo = g_halo_enabled && d->n_a == 1 && d->ntaps == 9 && Cc == 64 && d->bn == 0 && d->GW >= 16 &&
+              (long long)d->GH * d->GW >= 256LL * 256 && (per_sample || d->w_G == 1);
+  if (halo) {
+    int seen = 0;
+    for (int i = 0; i < 9; i++) {
+      const int dy = d->taps[i].dy, dx = d->taps[i].dx;
+      if (dy < -1 || dy > 1 || dx < -1 || dx > 1 || d->taps[i].amap != 0) { halo = false; break; }
+      seen |= 1 << ((dy + 1) * 3 + dx + 1);
+    }
+    if (seen != 0x1FF) halo = false;
+  }
+  if (halo) {
+    const int KC = (int)(Cc / 64);
+    int HBN = (d->Cout % 128 == 0 && KC == 1) ? 128 : (d->Cout % 64 == 0) ? 64 : 32;
+    p.TW = 8; p.TH = 16; p.TB = 1; p.rows = 128;
+    p.NB = d->NB; p.GH = d->GH; p.GW = d->GW;
+    p.tilesW = (d->GW + 7) / 8; p.tilesH = (d->GH + 15) / 16; p.tilesB = d->NB; p.tiles_hw = p.tilesW * p.tilesH;
+    p.NT = (int)NT; p.Cout = d->Cout; p.n_tiles = (int)(NT / HBN); p.per_sample = per_sample; p.w_T = (int)d->w_T;
+    const long long total = (long long)p.tiles_hw * d->NB * p.n_tiles;
+    if (total > 0x7fffffffLL) MGF_FAIL(MGF_E_SHAPE, "conv_tc: too many tiles");
+    p.total_tiles = (int)total; p.ntaps = 9; p.kchunks = KC;
+    for (int i = 0; i < 9; i++) { p.taps[i].amap = 0; p.taps[i].dy = d->taps[i].dy; p.taps[i].dx = d->taps[i].dx; p.taps[i].wz = d->taps[i].wz;
+      if (d->taps[i].wz < 0 || d->taps[i].wz >= d->w_T) MGF_FAIL(MGF_E_BADARG, "conv_tc: tap %d out of range", i); }
+    const mgf_tc_act& a = d->a[0];
+    if (!a.ptr || ((uintptr_t)a.ptr & 15) || (a.sW * 2) % 16 || (a.sH * 2) % 16 || (a.sN * 2) % 16) MGF_FAIL(MGF_E_ALIGN, "conv_tc: activation must be 16-byte aligned/strided");
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
+      cuuint64_t strides[3] = {(cuuint64_t)a.sW * 2, (cuuint64_t)a.sH * 2, (cuuint64_t)a.sN * 2};
+      cuuint32_t box[4] = {64, 16, 18, 1};
+      if (int e = encode(&p.amap[0], a.ptr, 4, dims, strides, box, 64)) return e;
+    }
+    {
+      if ((uintptr_t)d->w & 15) MGF_FAIL(MGF_E_ALIGN, "conv_tc: weights must be 16-byte aligned");
+      cuuint64_t dims[3] = {(cuuint64_t)d->w_K, (cuuint64_t)d->w_NT, (cuuint64_t)(d->w_G * d->w_T)};
+      cuuint64_t strides[2] = {(cuuint64_t)d->w_K * 2, (cuuint64_t)d->w_K * d->w_NT * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)HBN, 1};
+      if (int e = encode(&p.bmap, d->w, 3, dims, strides, box, 64)) return e;
+    }
+    p.out = d->out; p.OH = d->OH; p.OW = d->OW; p.OC = d->OC; p.osy = d->osy; p.osx = d->osx;
+    for (int i = 0; i < 4; i++) { p.ofy[i] = d->ofy[i]; p.ofx[i] = d->ofx[i]; }
+    p.scale_n = d->scale_n; p.reduce_out = d->reduce_out; p.X = (const __nv_bfloat16*)d->X;
+    p.noise = d->noise; p.noise_strength = d->noise_strength; p.bias = d->bias;
+    p.act = d->act; p.alpha = d->alpha; p.gain = d->gain; p.add = (const __nv_bfloat16*)d->add;
+    p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain;
+    if ((p.reduce_out || p.actgrad) && !p.X) MGF_FAIL(MGF_E_BADARG, "conv_tc: reduce/actgrad need X");
+    const bool f16 = fwd_f16();
+    const uint32_t fmt = (f16 && d->ab_fwd) ? 0u : 1u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(HBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
+    int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (KC == 1 && HBN == 128) return launch_halo<128, 1>(p, grid, st);
+    if (KC == 1 && HBN == 64) return launch_halo<64, 1>(p, grid, st);
+    if (KC == 1 && HBN == 32) return launch_halo<32, 1>(p, grid, st);
+    if (KC == 2 && HBN == 64) return launch_halo<64, 2>(p, grid, st);
+    if (KC == 2 && HBN == 32) return launch_halo<32, 2>(p, grid, st);
+    MGF_FAIL(MGF_E_UNSUP, "conv_tc: no halo kernel for BN=%d KC=%d", HBN, KC);
+  }
   // tile shape: TW x TH x TB pixels = at most 128 rows
   int TW = 1; while (TW * 2 <= d->GW && TW < 16) TW *= 2;
   int TH = 1; while (TH * 2 <= d->GH && TW * TH * 2 <= 128) TH *= 2;

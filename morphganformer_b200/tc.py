@@ -34,6 +34,7 @@ class ConvTcDesc(ctypes.Structure):
 
 
 _lib.SIGNATURES["mgf_conv_tc"] = (ctypes.c_int, [ctypes.POINTER(ConvTcDesc), c_void_p])
+_lib.SIGNATURES["mgf_conv_tc_set_halo"] = (ctypes.c_int, [ctypes.c_int])
 
 
 def nhwc_view(t):

@@ -104,3 +104,60 @@ def test_phase_output_and_multi_amap():
     bigc = big.float().cpu().permute(0, 3, 1, 2)
     ref2 = sum(F.conv2d(bigc[:, :, py::2, px::2], wt[ph].float(), padding=1) for ph, (py, px) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]))
     _check(out2, ref2)
+
+
+# ---- halo variant (C = 64/128, images >= 256^2): same contract, different kernel; also A/B against the generic kernel
+@pytest.mark.parametrize("cfg", [
+    # B, H, W, Cin, Cout
+    (1, 256, 256, 64, 64), (2, 256, 256, 64, 64), (1, 256, 256, 64, 128), (1, 272, 264, 64, 32), (1, 256, 512, 64, 256),
+])
+def test_conv3x3_halo_variant(cfg):
+    from morphganformer_b200 import tc, _lib
+    b, h, w, ci, co = cfg
+    x = _bf(util.case_tensor((b, h, w, ci), 1))
+    wt = _bf(util.case_tensor((co, ci, 3, 3), 2) * (1.0 / np.sqrt(9 * ci)))
+    bias = util.case_tensor((co,), 3)
+    outs = []
+    for halo in (1, 0):
+        _lib.lib().mgf_conv_tc_set_halo(halo)
+        out = torch.empty(b, h, w, co, dtype=torch.bfloat16, device="cuda")
+        tc.conv_tc([x.cuda()], tc.pack_w3x3(wt).cuda(), tc.TAPS_3X3, (b, h, w), 1, co, out, bias=bias.cuda(), act=2)
+        torch.cuda.synchronize()
+        outs.append(out)
+    _lib.lib().mgf_conv_tc_set_halo(1)
+    ref = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1))
+    _check(outs[1], ref, "generic " + str(cfg))
+    _check(outs[0], ref, "halo " + str(cfg))
+
+
+def test_halo_per_sample_dgrad_epilogue_and_phases():
+    from morphganformer_b200 import tc
+    b, h, w, ci, co = 2, 256, 256, 64, 64
+    dy = _bf(util.case_tensor((b, h, w, ci), 1))
+    wt = _bf(util.case_tensor((b, co, ci, 3, 3), 2) * (1.0 / np.sqrt(9 * ci)))
+    X = _bf(util.case_tensor((b, h, w, co), 3))
+    s = util.case_tensor((b, co), 4)
+    red = torch.zeros(b, co, device="cuda")
+    wp = wt.permute(0, 3, 4, 1, 2).reshape(b, 9, co, ci).contiguous()
+    taps_b = [(0, 1 - ky, 1 - kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]     # flipped taps, as the engine's dgrad uses
+    out = torch.empty(b, h, w, co, dtype=torch.bfloat16, device="cuda")
+    tc.conv_tc([dy.cuda()], wp.cuda(), taps_b, (b, h, w), 1, co, out, scale_n=s.cuda(), reduce_out=red, X=X.cuda(),
+               actgrad=True, ag_alpha=0.2, ag_gain=1.4, reduce_per_sample=True)
+    torch.cuda.synchronize()
+    acc = torch.cat([F.conv2d(dy[i:i + 1].float().permute(0, 3, 1, 2), wt[i].float().flip([2, 3]), padding=1) for i in range(b)])
+    Xn = X.float().permute(0, 3, 1, 2)
+    _check(out, acc * s.reshape(b, co, 1, 1) * torch.where(Xn > 0, 1.0, 0.2) * 1.4)
+    ref_red = (acc * Xn).sum(dim=[2, 3])
+    assert (red.cpu() - ref_red).abs().max() <= 2e-3 * ref_red.abs().max() + 1e-2
+    # four output phases (up-conv form) through the halo kernel: 64 -> 32 channels, 256^2 -> 512^2
+    co2 = 32
+    x = _bf(util.case_tensor((1, h, w, ci), 5))
+    w4 = _bf(util.case_tensor((4, co2, ci, 3, 3), 6) * (1.0 / np.sqrt(9 * ci)))
+    wp4 = w4.permute(3, 4, 0, 1, 2).reshape(1, 9, 4 * co2, ci).contiguous()
+    out4 = torch.zeros(1, 2 * h, 2 * w, co2, dtype=torch.bfloat16, device="cuda")
+    tc.conv_tc([x.cuda()], wp4.cuda(), tc.TAPS_3X3, (1, h, w), 4, co2, out4, osy=2, osx=2, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1))
+    torch.cuda.synchronize()
+    ref4 = torch.zeros(1, co2, 2 * h, 2 * w)
+    for ph, (py, px) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
+        ref4[:, :, py::2, px::2] = F.conv2d(x.float().permute(0, 3, 1, 2), w4[ph].float(), padding=1)
+    _check(out4, ref4)
