@@ -34,13 +34,15 @@ namespace tc {
 
 constexpr int MAX_TAPS = 40;
 constexpr int MAX_AMAPS = 4;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 192 * 1024;     // operand stages; + 2 x 16 KB epilogue staging + barriers stays under 227 KB
+constexpr int STG_BYTES = 128 * 128;        // one epilogue group's output staging tile: 128 pixels x 64 channels x 2 B
 
 struct Tap { int8_t amap, dy, dx, pad; int32_t wz; };
 
 struct alignas(64) Params {
   CUtensorMap amap[MAX_AMAPS];
   CUtensorMap bmap;
+  CUtensorMap omap[4];          // output tensor, one map per output phase (TMA store of the staged tile)
   Tap taps[MAX_TAPS];
   int ntaps, kchunks;
   int NB, GH, GW, TB, TH, TW, tilesB, tilesH, tilesW, rows;
@@ -89,6 +91,21 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+// one lane of a fully converged warp (keeps the surrounding loop warp-uniform, so the compiler stays on the uniform datapath
+// instead of wrapping every descriptor move in an ELECT/R2UR.BROADCAST retry loop, as it does inside an `if (lane == 0)` branch)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -132,7 +149,7 @@ struct Cfg {
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE;
   static constexpr int STAGES = STAGES_RAW > 20 ? 20 : STAGES_RAW;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;
+  static constexpr int SMEM = STAGES * STAGE + 2 * STG_BYTES + BAR_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // instruction descriptor (InstrDescriptor): D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A/B, N>>3 at 17, M>>4 at 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -152,7 +169,8 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
 // Fused layer tail for one 128 x BN accumulator tile (called by all four warps of an epilogue group after the tfull wait).
 // Row `valid`/(x, y, b) identify this thread's pixel; tacc = TMEM address of the tile (lane quarter already applied).
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nstr) {
+__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nstr,
+                                              uint8_t* stg, int group, int r) {
       const int phase_idx = t.n0 / p.Cout, co0 = t.n0 % p.Cout;
       const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
       const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
@@ -238,15 +256,30 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] *= (xv[j] > 0.f ? 1.f : p.ag_alpha) * p.ag_gain;
         }
-        if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c * 32);
+        // stage this thread's 32 outputs (64 B) into the swizzled shared-memory tile; a 64-channel group (or the whole tile for
+        // BN = 32) then leaves with ONE TMA store: fully coalesced, asynchronous, clipped at the image border by the hardware.
+        constexpr int GW32 = (BN >= 64) ? 2 : 1;           // 32-column chunks per staged group
+        const int h = c % GW32;
+        if (h == 0) {                                      // the previous store must have finished reading the staging tile
+          if (r == 0) tma_store_wait_read();
+          group_sync(group);
+        }
+        {
+          uint8_t* row = stg + r * (GW32 * 64);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             uint4 u;
             u.x = pack16(v[q * 8 + 0], v[q * 8 + 1], p.out_f16); u.y = pack16(v[q * 8 + 2], v[q * 8 + 3], p.out_f16);
             u.z = pack16(v[q * 8 + 4], v[q * 8 + 5], p.out_f16); u.w = pack16(v[q * 8 + 6], v[q * 8 + 7], p.out_f16);
-            op[q] = u;
+            const int j = h * 4 + q;
+            const int pos = (GW32 == 2) ? (j ^ (r & 7)) : (j ^ ((r >> 1) & 3));     // 128B / 64B swizzle, as the tensor map expects
+            *reinterpret_cast<uint4*>(row + pos * 16) = u;
           }
+        }
+        if (h == GW32 - 1) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          group_sync(group);
+          if (r == 0) tma_store_4d(&p.omap[phase_idx], stg, co0 + (c / GW32) * (GW32 * 32), t.x0, t.y0, t.b0);
         }
       }
 }
@@ -256,7 +289,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   using C = Cfg<BN, BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint8_t* stg_base = smem + C::STAGES * C::STAGE;                       // 2 x 16 KB epilogue staging, 1024-byte aligned
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg_base + 2 * STG_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -279,46 +313,53 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const int iters = p.kchunks * p.ntaps;
 
-  if (warp == 8) {
-    if (lane == 0) {   // ------------------------------------------------ TMA producer
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BN);
-        const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
-        for (int kc = 0; kc < p.kchunks; kc++) {
-          for (int tp = 0; tp < p.ntaps; tp++) {
-            const Tap tap = p.taps[tp];
-            mbar_wait(&empty[stage], phase ^ 1);
+  if (warp == 8) {     // ------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BN);
+      const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
+      for (int kc = 0; kc < p.kchunks; kc++) {
+        for (int tp = 0; tp < p.ntaps; tp++) {
+          const Tap tap = p.taps[tp];
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&full[stage], p.tx_bytes);
             uint8_t* sa = smem + stage * C::STAGE;
             tma_load_4d(&p.amap[tap.amap], &full[stage], sa, kc * BK, t.x0 + tap.dx, t.y0 + tap.dy, t.b0);
             tma_load_3d(&p.bmap, &full[stage], sa + C::A_BYTES, kc * BK, t.n0, wbase + tap.wz);
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 9) {
-    if (lane == 0) {   // ------------------------------------------------ MMA issuer
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
+  } else if (warp == 9) {   // ------------------------------------------------- MMA issuer (whole warp loops, one lane issues)
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int it = 0; it < iters; it++) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int it = 0; it < iters; it++) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::STAGE);
           const uint64_t adesc = make_desc<BK>(sa), bdesc = make_desc<BK>(sa + C::A_BYTES);
+          if (it > 0) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; k++)
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; k++) tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, k > 0 ? 1u : 0u);
+          }
           tc_commit(&empty[stage]);           // frees the smem slot once these MMAs have read it
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[as]);                // accumulator complete -> epilogue
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) tc_commit(&tfull[as]); // accumulator complete -> epilogue
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {             // ---------------------------------------------------- epilogue: two groups of 4 warps, group g owns accumulator stage g
     const int as = warp >> 2; uint32_t aphase = 0;
@@ -332,11 +373,13 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr);
+      epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr,
+                        stg_base + as * STG_BYTES, as, r);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       aphase ^= 1;
     }
+    if (r == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -364,9 +407,9 @@ struct HaloCfg {
   static constexpr int B_TILE = BN * 128;
   static constexpr int B_BYTES = KC * 9 * B_TILE;
   static constexpr int SMEM_MAX = 227 * 1024;
-  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2048) / A_STAGE;
+  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * STG_BYTES - 2048) / A_STAGE;
   static constexpr int NS = NS_RAW > 6 ? 6 : NS_RAW;
-  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 1024 + 256;
+  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 2 * STG_BYTES + 1024 + 256;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(NS >= 2, "halo kernel needs at least two activation stages");
 };
@@ -395,7 +438,8 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
   uint8_t* sA = smem + C::B_BYTES;
-  uint64_t* afull = reinterpret_cast<uint64_t*>(sA + C::NS * C::A_STAGE);
+  uint8_t* stg_base = sA + C::NS * C::A_STAGE;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(stg_base + 2 * STG_BYTES);
   uint64_t* aempty = afull + C::NS;
   uint64_t* bfull = aempty + C::NS;
   uint64_t* tfull = bfull + 1;
@@ -419,60 +463,69 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    if (lane == 0) {   // ------------------------------------------------ TMA producer
-      int stage = 0; uint32_t phase = 0; int cur_key = -1; int last_stage = -1; uint32_t last_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const HaloTile t = decode_halo(p, tile, BN);
-        if (t.key != cur_key) {
-          // the resident weights are about to be overwritten: every MMA issued so far must have finished reading them.
-          // MMAs complete in order, so waiting for the consumption of the most recently issued activation stage is enough.
-          if (last_stage >= 0) mbar_wait(&aempty[last_stage], last_phase);
+  if (warp == 8) {     // ------------------------------------------------------ TMA producer
+    int stage = 0; uint32_t phase = 0; int cur_key = -1; int last_stage = -1; uint32_t last_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const HaloTile t = decode_halo(p, tile, BN);
+      if (t.key != cur_key) {
+        // the resident weights are about to be overwritten: every MMA issued so far must have finished reading them.
+        // MMAs complete in order, so waiting for the consumption of the most recently issued activation stage is enough.
+        if (last_stage >= 0) mbar_wait(&aempty[last_stage], last_phase);
+        if (elect_one()) {
           mbar_arrive_expect_tx(bfull, (uint32_t)C::B_BYTES);
           const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
           for (int kc = 0; kc < KC; kc++)
             for (int tp = 0; tp < 9; tp++)
               tma_load_3d(&p.bmap, bfull, sB + (kc * 9 + tp) * C::B_TILE, kc * 64, t.n0, wbase + p.taps[tp].wz);
-          cur_key = t.key;
         }
-        for (int kc = 0; kc < KC; kc++) {
-          mbar_wait(&aempty[stage], phase ^ 1);
+        __syncwarp();
+        cur_key = t.key;
+      }
+      for (int kc = 0; kc < KC; kc++) {
+        mbar_wait(&aempty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&afull[stage], (uint32_t)C::A_STAGE);
           tma_load_4d(&p.amap[0], &afull[stage], sA + stage * C::A_STAGE, kc * 64, t.x0 - 1, t.y0 - 1, t.b0);
-          last_stage = stage; last_phase = phase;
-          if (++stage == C::NS) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        last_stage = stage; last_phase = phase;
+        if (++stage == C::NS) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 9) {
-    if (lane == 0) {   // ------------------------------------------------ MMA issuer
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; int cur_key = -1; uint32_t bphase = 0;
-      const uint32_t sB_addr = smem_u32(sB);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const HaloTile t = decode_halo(p, tile, BN);
-        if (t.key != cur_key) { mbar_wait(bfull, bphase); bphase ^= 1; cur_key = t.key; }
-        mbar_wait(&tempty[as], aphase ^ 1);
+  } else if (warp == 9) {   // ------------------------------------------------- MMA issuer
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; int cur_key = -1; uint32_t bphase = 0;
+    const uint32_t sB_addr = smem_u32(sB);
+    // tap -> byte offset of its shifted view inside the haloed tile (warp-uniform, hoisted out of the tile loop)
+    uint32_t tap_off[9];
+#pragma unroll
+    for (int tp = 0; tp < 9; tp++) tap_off[tp] = (uint32_t)(((p.taps[tp].dy + 1) * 16 + p.taps[tp].dx + 1) * 128);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const HaloTile t = decode_halo(p, tile, BN);
+      if (t.key != cur_key) { mbar_wait(bfull, bphase); bphase ^= 1; cur_key = t.key; }
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int kc = 0; kc < KC; kc++) {
+        mbar_wait(&afull[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kc = 0; kc < KC; kc++) {
-          mbar_wait(&afull[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(sA + stage * C::A_STAGE);
 #pragma unroll
           for (int tp = 0; tp < 9; tp++) {
-            const int hy = p.taps[tp].dy + 1, hx = p.taps[tp].dx + 1;          // position of the tap inside the halo
-            const uint64_t adesc = make_desc_halo(sa + (uint32_t)((hy * 16 + hx) * 128));
+            const uint64_t adesc = make_desc_halo(sa + tap_off[tp]);
             const uint64_t bdesc = make_desc<64>(sB_addr + (uint32_t)((kc * 9 + tp) * C::B_TILE));
 #pragma unroll
             for (int k = 0; k < 4; k++)
               tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc > 0 || tp > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&aempty[stage]);
-          if (++stage == C::NS) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[as]);
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == C::NS) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) tc_commit(&tfull[as]);
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {             // ---------------------------------------------------- epilogue groups
     const int as = warp >> 2; uint32_t aphase = 0;
@@ -487,11 +540,13 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       const bool valid = x < p.GW && y < p.GH;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr);
+      epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr,
+                        stg_base + as * STG_BYTES, as, r);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       aphase ^= 1;
     }
+    if (r == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -526,6 +581,23 @@ static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* d
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) MGF_FAIL(MGF_E_DRIVER, "conv_tc: cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=%llu,%llu,%llu box=%u,%u,%u",
                                   (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+  return 0;
+}
+
+
+// output tensor maps for the TMA-store epilogue: one per output phase, box = {64 or 32 channels, TW, TH, TB} of the phase grid
+static int encode_out_maps(Params& p, const mgf_conv_tc_desc* d, int BN, int TW, int TH, int TB) {
+  const int gwd = BN >= 64 ? 64 : 32;
+  if (((uintptr_t)d->out & 15) || (d->OC * 2) % 16) MGF_FAIL(MGF_E_ALIGN, "conv_tc: output must be 16-byte aligned with OC %% 8 == 0");
+  for (int ph = 0; ph < d->phases; ph++) {
+    const long long ofy = d->ofy[ph], ofx = d->ofx[ph];
+    if (ofy < 0 || ofx < 0 || ofy >= d->osy || ofx >= d->osx) MGF_FAIL(MGF_E_BADARG, "conv_tc: phase offset outside the output stride");
+    const char* base = (const char*)d->out + ((ofy * d->OW + ofx) * d->OC) * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)d->OC, (cuuint64_t)((d->OW - ofx + d->osx - 1) / d->osx), (cuuint64_t)((d->OH - ofy + d->osy - 1) / d->osy), (cuuint64_t)d->NB};
+    cuuint64_t strides[3] = {(cuuint64_t)d->osx * d->OC * 2, (cuuint64_t)d->osy * d->OW * d->OC * 2, (cuuint64_t)d->OH * d->OW * d->OC * 2};
+    cuuint32_t box[4] = {(cuuint32_t)gwd, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+    if (int e = encode(&p.omap[ph], base, 4, dims, strides, box, gwd)) return e;
+  }
   return 0;
 }
 
@@ -606,7 +678,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   }
   if (halo) {
     const int KC = (int)(Cc / 64);
-    int HBN = (d->Cout % 128 == 0 && KC == 1) ? 128 : (d->Cout % 64 == 0) ? 64 : 32;
+    int HBN = (d->Cout % 64 == 0) ? 64 : 32;
     p.TW = 8; p.TH = 16; p.TB = 1; p.rows = 128;
     p.NB = d->NB; p.GH = d->GH; p.GW = d->GW;
     p.tilesW = (d->GW + 7) / 8; p.tilesH = (d->GH + 15) / 16; p.tilesB = d->NB; p.tiles_hw = p.tilesW * p.tilesH;
@@ -642,13 +714,11 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     const uint32_t fmt = (f16 && d->ab_fwd) ? 0u : 1u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(HBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
+    if (int e = encode_out_maps(p, d, HBN, 8, 16, 1)) return e;
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
     cudaStream_t st = (cudaStream_t)stream;
-    if (KC == 1 && HBN == 128) return launch_halo<128, 1>(p, grid, st);
     if (KC == 1 && HBN == 64) return launch_halo<64, 1>(p, grid, st);
     if (KC == 1 && HBN == 32) return launch_halo<32, 1>(p, grid, st);
-    if (KC == 2 && HBN == 64) return launch_halo<64, 2>(p, grid, st);
-    if (KC == 2 && HBN == 32) return launch_halo<32, 2>(p, grid, st);
     MGF_FAIL(MGF_E_UNSUP, "conv_tc: no halo kernel for BN=%d KC=%d", HBN, KC);
   }
   // tile shape: TW x TH x TB pixels = at most 128 rows
@@ -699,6 +769,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
   }
+  if (int e = encode_out_maps(p, d, BN, TW, TH, TB)) return e;
   int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
 #define MGF_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch<bn, bk>(p, grid, st);
