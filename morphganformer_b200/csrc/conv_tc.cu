@@ -401,10 +401,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 //   * the 3x3 weights of the current (sample, N-block) stay resident in shared memory across tiles (KC*9 tiles of BN x 64),
 //     re-loaded only when the CTA moves to another sample / N-block.
 // L2->SM traffic per 128-pixel tile drops from 9*(16+BN/8) KB to 36 KB per channel chunk.
-template <int BN, int KC>
+template <int BN, int KC, int BK>
 struct HaloCfg {
-  static constexpr int A_STAGE = 288 * 128;                       // 18 rows x 16 px x 128 B
-  static constexpr int B_TILE = BN * 128;
+  static constexpr int A_STAGE = 288 * BK * 2;                    // 18 rows x 16 px x (128 B | 64 B for 32-channel layers)
+  static constexpr int B_TILE = BN * BK * 2;
   static constexpr int B_BYTES = KC * 9 * B_TILE;
   static constexpr int SMEM_MAX = 227 * 1024;
   static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * STG_BYTES - 2048) / A_STAGE;
@@ -414,12 +414,15 @@ struct HaloCfg {
   static_assert(NS >= 2, "halo kernel needs at least two activation stages");
 };
 
+template <int BK>
 __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr) {
   // K-major, 128B swizzle, rows of a core-matrix group 128 B apart, groups (8 px = one tile row) 2048 B apart.
   // base_offset stays 0: measured on B200 (scripts/debug_halo.py) the swizzle XOR is taken from the shared-memory ADDRESS bits,
   // exactly like the TMA write side, so a start address shifted by dx*128 B inside the atom needs no phase correction
   // (setting base_offset = dx, as a literal reading of the descriptor format suggests, corrupts the dx != -1 taps).
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t sbo = 16 * BK * 2;            // one tile row = 16 haloed pixels
+  constexpr uint64_t layout = (BK == 64) ? 2 : 4;  // 128B / 64B swizzle
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
 struct HaloTile { int n0, x0, y0, b0, key; };
@@ -431,9 +434,9 @@ __device__ __forceinline__ HaloTile decode_halo(const Params& p, int tile, int B
   return t;
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int BK>
 __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant__ Params p) {
-  using C = HaloCfg<BN, KC>;
+  using C = HaloCfg<BN, KC, BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
           const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
           for (int kc = 0; kc < KC; kc++)
             for (int tp = 0; tp < 9; tp++)
-              tma_load_3d(&p.bmap, bfull, sB + (kc * 9 + tp) * C::B_TILE, kc * 64, t.n0, wbase + p.taps[tp].wz);
+              tma_load_3d(&p.bmap, bfull, sB + (kc * 9 + tp) * C::B_TILE, kc * BK, t.n0, wbase + p.taps[tp].wz);
         }
         __syncwarp();
         cur_key = t.key;
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
         mbar_wait(&aempty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&afull[stage], (uint32_t)C::A_STAGE);
-          tma_load_4d(&p.amap[0], &afull[stage], sA + stage * C::A_STAGE, kc * 64, t.x0 - 1, t.y0 - 1, t.b0);
+          tma_load_4d(&p.amap[0], &afull[stage], sA + stage * C::A_STAGE, kc * BK, t.x0 - 1, t.y0 - 1, t.b0);
         }
         __syncwarp();
         last_stage = stage; last_phase = phase;
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
     // tap -> byte offset of its shifted view inside the haloed tile (warp-uniform, hoisted out of the tile loop)
     uint32_t tap_off[9];
 #pragma unroll
-    for (int tp = 0; tp < 9; tp++) tap_off[tp] = (uint32_t)(((p.taps[tp].dy + 1) * 16 + p.taps[tp].dx + 1) * 128);
+    for (int tp = 0; tp < 9; tp++) tap_off[tp] = (uint32_t)(((p.taps[tp].dy + 1) * 16 + p.taps[tp].dx + 1) * (BK * 2));
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const HaloTile t = decode_halo(p, tile, BN);
       if (t.key != cur_key) { mbar_wait(bfull, bphase); bphase ^= 1; cur_key = t.key; }
@@ -512,10 +515,10 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
           const uint32_t sa = smem_u32(sA + stage * C::A_STAGE);
 #pragma unroll
           for (int tp = 0; tp < 9; tp++) {
-            const uint64_t adesc = make_desc_halo(sa + tap_off[tp]);
-            const uint64_t bdesc = make_desc<64>(sB_addr + (uint32_t)((kc * 9 + tp) * C::B_TILE));
+            const uint64_t adesc = make_desc_halo<BK>(sa + tap_off[tp]);
+            const uint64_t bdesc = make_desc<BK>(sB_addr + (uint32_t)((kc * 9 + tp) * C::B_TILE));
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int k = 0; k < BK / 16; k++)
               tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kc > 0 || tp > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&aempty[stage]);
@@ -615,16 +618,16 @@ static int launch(const Params& p, int grid, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int BK>
 static int launch_halo(const Params& p, int grid, cudaStream_t st) {
-  using C = HaloCfg<BN, KC>;
+  using C = HaloCfg<BN, KC, BK>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, KC, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc(halo): cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_halo_kernel<BN, KC><<<grid, 320, C::SMEM, st>>>(p);
+  conv_halo_kernel<BN, KC, BK><<<grid, 320, C::SMEM, st>>>(p);
   MGF_CHECK_LAUNCH("conv_tc(halo)");
   return 0;
 }
@@ -665,7 +668,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   // resident weights for many tiles
   // (measured: a win for C = 64 -- 0.95 -> 0.68 ms on 64->64 @1024^2 x8 -- but not for C = 128, where the generic kernel's
   // 128-wide N tile beats two 64-wide halo passes; scripts/bench_conv_tc.py)
-  bool halo = g_halo_enabled && d->n_a == 1 && d->ntaps == 9 && Cc == 64 && d->bn == 0 && d->GW >= 16 &&
+  bool halo = g_halo_enabled && d->n_a == 1 && d->ntaps == 9 && (Cc == 64 || Cc == 32) && d->bn == 0 && d->GW >= 16 &&
               (long long)d->GH * d->GW >= 256LL * 256 && (per_sample || d->w_G == 1);
   if (halo) {
     int seen = 0;
@@ -677,7 +680,8 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     if (seen != 0x1FF) halo = false;
   }
   if (halo) {
-    const int KC = (int)(Cc / 64);
+    const int KC = 1;
+    const int HBK = (int)Cc;                      // 64 (128B-swizzled rows) or 32 (64B-swizzled rows)
     int HBN = (d->Cout % 64 == 0) ? 64 : 32;
     p.TW = 8; p.TH = 16; p.TB = 1; p.rows = 128;
     p.NB = d->NB; p.GH = d->GH; p.GW = d->GW;
@@ -693,15 +697,15 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     {
       cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
       cuuint64_t strides[3] = {(cuuint64_t)a.sW * 2, (cuuint64_t)a.sH * 2, (cuuint64_t)a.sN * 2};
-      cuuint32_t box[4] = {64, 16, 18, 1};
-      if (int e = encode(&p.amap[0], a.ptr, 4, dims, strides, box, 64)) return e;
+      cuuint32_t box[4] = {(cuuint32_t)HBK, 16, 18, 1};
+      if (int e = encode(&p.amap[0], a.ptr, 4, dims, strides, box, HBK)) return e;
     }
     {
       if ((uintptr_t)d->w & 15) MGF_FAIL(MGF_E_ALIGN, "conv_tc: weights must be 16-byte aligned");
       cuuint64_t dims[3] = {(cuuint64_t)d->w_K, (cuuint64_t)d->w_NT, (cuuint64_t)(d->w_G * d->w_T)};
       cuuint64_t strides[2] = {(cuuint64_t)d->w_K * 2, (cuuint64_t)d->w_K * d->w_NT * 2};
-      cuuint32_t box[3] = {64, (cuuint32_t)HBN, 1};
-      if (int e = encode(&p.bmap, d->w, 3, dims, strides, box, 64)) return e;
+      cuuint32_t box[3] = {(cuuint32_t)HBK, (cuuint32_t)HBN, 1};
+      if (int e = encode(&p.bmap, d->w, 3, dims, strides, box, HBK)) return e;
     }
     p.out = d->out; p.OH = d->OH; p.OW = d->OW; p.OC = d->OC; p.osy = d->osy; p.osx = d->osx;
     for (int i = 0; i < 4; i++) { p.ofy[i] = d->ofy[i]; p.ofx[i] = d->ofx[i]; }
@@ -717,8 +721,10 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     if (int e = encode_out_maps(p, d, HBN, 8, 16, 1)) return e;
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
     cudaStream_t st = (cudaStream_t)stream;
-    if (KC == 1 && HBN == 64) return launch_halo<64, 1>(p, grid, st);
-    if (KC == 1 && HBN == 32) return launch_halo<32, 1>(p, grid, st);
+    if (HBK == 64 && HBN == 64) return launch_halo<64, 1, 64>(p, grid, st);
+    if (HBK == 64 && HBN == 32) return launch_halo<32, 1, 64>(p, grid, st);
+    if (HBK == 32 && HBN == 64) return launch_halo<64, 1, 32>(p, grid, st);
+    if (HBK == 32 && HBN == 32) return launch_halo<32, 1, 32>(p, grid, st);
     MGF_FAIL(MGF_E_UNSUP, "conv_tc: no halo kernel for BN=%d KC=%d", HBN, KC);
   }
   // tile shape: TW x TH x TB pixels = at most 128 rows

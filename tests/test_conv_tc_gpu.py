@@ -110,6 +110,7 @@ def test_phase_output_and_multi_amap():
 @pytest.mark.parametrize("cfg", [
     # B, H, W, Cin, Cout
     (1, 256, 256, 64, 64), (2, 256, 256, 64, 64), (1, 256, 256, 64, 128), (1, 272, 264, 64, 32), (1, 256, 512, 64, 256),
+    (2, 256, 256, 32, 32), (1, 264, 272, 32, 64),
 ])
 def test_conv3x3_halo_variant(cfg):
     from morphganformer_b200 import tc, _lib
