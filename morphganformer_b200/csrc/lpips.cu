@@ -242,6 +242,92 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f,
   }
 }
 
+// Fused backward of an LPIPS tap that is followed by a max-pool (relu1_2, relu2_2, relu3_3, relu4_3):
+//   dx = ( route(dy through the 2x2 max-pool) + d(head)/dx ) * (x > 0)
+// replaces lpips_head<2> + maxpool2_bwd for those taps: x and n1 are read once, the head gradient never touches HBM
+// (7 tensor passes -> 3.25).  A group of LPP lanes owns one 2x2 window (4 pixels), channel vectors stay in registers.
+template <int VPL>
+__global__ void __launch_bounds__(256) lpips_tap_pool_bwd_kernel(const __nv_bfloat16* x, const __nv_bfloat16* n1, const float* lin, const float* coef,
+                                                                 const __nv_bfloat16* dy, __nv_bfloat16* dx, int H, int W, int C, bool f16) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpp = (C / 8) / VPL, wpw = 32 / lpp;                // lanes per window, windows per warp
+  const int sub = lane / lpp, ll = lane % lpp;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long nwin = (long long)Ho * Wo, HW = (long long)H * W;
+  const float eps = 1e-10f, cf = coef[b] / (float)HW;
+  float lw[VPL][8];
+#pragma unroll
+  for (int q = 0; q < VPL; q++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) lw[q][e] = lin[(q * lpp + ll) * 8 + e];
+  for (long long w0 = ((long long)blockIdx.x * 8 + warp) * wpw; w0 < nwin; w0 += (long long)gridDim.x * 8 * wpw) {
+    const long long wi = w0 + sub;
+    const bool ok = wi < nwin;
+    const int xo = (int)((ok ? wi : 0) % Wo), yo = (int)((ok ? wi : 0) / Wo);
+    float xv[4][VPL][8], gv[4][VPL][8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const long long row = (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C;
+      float tv[VPL][8];
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < VPL; q++) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row) + q * lpp + ll);
+        const uint4 un = __ldg(reinterpret_cast<const uint4*>(n1 + row) + q * lpp + ll);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w}, n4[4] = {un.x, un.y, un.z, un.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 v = unpack16(w4[e], f16), t = unpack16(n4[e], f16);
+          xv[k][q][e * 2] = v.x; xv[k][q][e * 2 + 1] = v.y; tv[q][e * 2] = t.x; tv[q][e * 2 + 1] = t.y;
+          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss);
+        }
+      }
+      for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float r = sqrtf(ss), inv = 1.f / (r + eps);
+      float dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < VPL; q++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) { gv[k][q][e] = 2.f * lw[q][e] * (xv[k][q][e] * inv - tv[q][e]); dot = fmaf(gv[k][q][e], xv[k][q][e], dot); }
+      for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const float k2 = (r > 0.f) ? dot * inv * inv / r : 0.f;
+#pragma unroll
+      for (int q = 0; q < VPL; q++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) gv[k][q][e] = cf * (gv[k][q][e] * inv - k2 * xv[k][q][e]);
+    }
+    if (!ok) continue;
+#pragma unroll
+    for (int q = 0; q < VPL; q++) {
+      float g[8];
+      {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)b * Ho + yo) * Wo + xo) * C) + q * lpp + ll);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float2 v = unpack_bf16(w4[e]); g[e * 2] = v.x; g[e * 2 + 1] = v.y; }
+      }
+      int arg[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        int a = 0; float m = xv[0][q][e];
+#pragma unroll
+        for (int k = 1; k < 4; k++) if (xv[k][q][e] > m) { m = xv[k][q][e]; a = k; }
+        arg[e] = a;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { const float v = ((arg[e] == k) ? g[e] : 0.f) + gv[k][q][e]; o[e] = xv[k][q][e] > 0.f ? v : 0.f; }
+        uint4 u;
+        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+        const long long row = (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C;
+        reinterpret_cast<uint4*>(dx + row)[q * lpp + ll] = u;
+      }
+    }
+  }
+}
+
 // Adam (coupled L2, torch.optim.Adam semantics) on n latent floats, then the next step's noisy latent.
 // sched[step] = {lr, noise_strength_next}; step read from a device counter (so the whole step can live in a CUDA graph).
 __global__ void __launch_bounds__(256) adam_noise_kernel(float* latent, const float* grad, float* m, float* v, const float* noise_all,
@@ -320,6 +406,20 @@ extern "C" int mgf_lpips_head(int mode, const void* f, const void* n1, const flo
   else { if (mode == 0) MGF_HEAD(0, 2); else if (mode == 1) MGF_HEAD(1, 2); else MGF_HEAD(2, 2); }
 #undef MGF_HEAD
   MGF_CHECK_LAUNCH("lpips_head");
+  return 0;
+}
+extern "C" int mgf_lpips_tap_pool_bwd(const void* x, const void* n1, const float* lin, const float* coef, const void* dy, void* dx,
+                                      int B, int H, int W, int C, void* stream) {
+  if (!x || !n1 || !lin || !coef || !dy || !dx) MGF_FAIL(MGF_E_BADARG, "lpips_tap_pool_bwd: null tensor");
+  if (!(C == 64 || C == 128 || C == 256 || C == 512) || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "lpips_tap_pool_bwd: C in {64,128,256,512}, even H/W");
+  const int vpl = C == 512 ? 2 : 1, lpp = (C / 8) / vpl, wpw = 32 / lpp;
+  const long long nwin = (long long)(H / 2) * (W / 2);
+  long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vpl == 1) lpips_tap_pool_bwd_kernel<1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, H, W, C, fwd_f16());
+  else lpips_tap_pool_bwd_kernel<2><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, H, W, C, fwd_f16());
+  MGF_CHECK_LAUNCH("lpips_tap_pool_bwd");
   return 0;
 }
 extern "C" int mgf_adam_noise_step(float* latent, const float* grad, float* m, float* v, const float* noise_all, int noise_rows, float* latent_n,

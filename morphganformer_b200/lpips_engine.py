@@ -168,9 +168,13 @@ class LpipsEngine:
                 dp = self._buf(f"dp{ci}", (B, res, res, cin))
                 tc.conv_tc([g], self.wb[ci], TAPS_B, (B, res, res), 1, cin, dp, tag="vgg.bwd", fwd=False)
                 src = h[ci - 1]
-                extra = head_bwd(ci - 1, False) if (ci - 1) in TAP_AFTER else None
                 g2 = self._buf(f"dpre{ci - 1}", tuple(src.shape))
-                _lib.check(_L().mgf_maxpool2_bwd(_p(src), _p(dp), _p(extra), _p(g2), B, src.shape[1], src.shape[2], src.shape[3], s), "mgf_maxpool2_bwd")
+                if (ci - 1) in TAP_AFTER:      # tap + pool: one fused kernel (head gradient + pool routing + ReLU mask)
+                    k = TAP_AFTER[ci - 1]
+                    _lib.check(_L().mgf_lpips_tap_pool_bwd(_p(src), _p(self.n1[k]), _p(self.lin[k]), _p(coef), _p(dp), _p(g2), B,
+                                                           src.shape[1], src.shape[2], src.shape[3], s), "mgf_lpips_tap_pool_bwd")
+                else:
+                    _lib.check(_L().mgf_maxpool2_bwd(_p(src), _p(dp), None, _p(g2), B, src.shape[1], src.shape[2], src.shape[3], s), "mgf_maxpool2_bwd")
                 g = g2
                 pos -= 2
             else:
