@@ -19,6 +19,11 @@ namespace mgf {
 
 constexpr int T16 = 16;
 
+// Shared-memory layout of the [16, C] coefficient tables: a lane owns 8 consecutive channels (one 16-byte bf16 vector of X) and reads
+// them as two float4; storing the two halves in separate planes makes both reads 16-byte-strided across lanes (conflict-free)
+// instead of 32-byte-strided (2-way bank conflict on every LDS.128: 42 M conflicts per launch in the first ncu capture).
+__device__ __forceinline__ int perm_idx(int t, int c, int C) { return t * C + ((c >> 2) & 1) * (C >> 1) + (c >> 3) * 4 + (c & 3); }
+
 struct AttnP {
   const __nv_bfloat16* X; const float* Kf; const float* Sc; const float* mb; const float* VM; const float* bm;
   const float* noise; const float* nstr; const float* bias; float gain, alpha;
@@ -73,7 +78,7 @@ __device__ __forceinline__ void pixel_probs(const float (&x)[VPL][8], const floa
       for (int e = 0; e < 8; e++) ss = fmaf(x[q][e], x[q][e], ss);
 #pragma unroll
       for (int t = 0; t < T16; t++) {
-        const float4 k0 = *reinterpret_cast<const float4*>(sK + t * C + c0), k1 = *reinterpret_cast<const float4*>(sK + t * C + c0 + 4);
+        const float4 k0 = *reinterpret_cast<const float4*>(sK + t * C + (c0 >> 1)), k1 = *reinterpret_cast<const float4*>(sK + t * C + (C >> 1) + (c0 >> 1));
         float a = S[t];
         a = fmaf(x[q][0], k0.x, a); a = fmaf(x[q][1], k0.y, a); a = fmaf(x[q][2], k0.z, a); a = fmaf(x[q][3], k0.w, a);
         a = fmaf(x[q][4], k1.x, a); a = fmaf(x[q][5], k1.y, a); a = fmaf(x[q][6], k1.z, a); a = fmaf(x[q][7], k1.w, a);
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnP p) {
   const int C = p.C;
   float* sK = smf; float* sV = sK + T16 * C; float* sb = sV + T16 * C; float* sm1 = sb + C;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < T16 * C; i += blockDim.x) { sK[i] = p.Kf[i]; sV[i] = p.VM[(long long)b * T16 * C + i]; }
+  for (int i = threadIdx.x; i < T16 * C; i += blockDim.x) { const int pi = perm_idx(i / C, i % C, C); sK[pi] = p.Kf[i]; sV[pi] = p.VM[(long long)b * T16 * C + i]; }
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sb[i] = p.bias ? p.bias[i] : 0.f; sm1[i] = 1.f + p.bm[i]; }
   __syncthreads();
   const float ns = (p.noise && p.nstr) ? *p.nstr : 0.f;
@@ -122,7 +127,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnP p) {
         for (int e = 0; e < 8; e++) ctl[e] = sm1[c0 + e];
 #pragma unroll
         for (int t = 0; t < T16; t++) {
-          const float4 v0 = *reinterpret_cast<const float4*>(sV + t * C + c0), v1 = *reinterpret_cast<const float4*>(sV + t * C + c0 + 4);
+          const float4 v0 = *reinterpret_cast<const float4*>(sV + t * C + (c0 >> 1)), v1 = *reinterpret_cast<const float4*>(sV + t * C + (C >> 1) + (c0 >> 1));
           ctl[0] = fmaf(A[t], v0.x, ctl[0]); ctl[1] = fmaf(A[t], v0.y, ctl[1]); ctl[2] = fmaf(A[t], v0.z, ctl[2]); ctl[3] = fmaf(A[t], v0.w, ctl[3]);
           ctl[4] = fmaf(A[t], v1.x, ctl[4]); ctl[5] = fmaf(A[t], v1.y, ctl[5]); ctl[6] = fmaf(A[t], v1.z, ctl[6]); ctl[7] = fmaf(A[t], v1.w, ctl[7]);
         }
@@ -142,15 +147,16 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnP p) {
 // write dX, stash A and dctl (bf16) in shared memory, accumulate R[c] += dX*X.
 // Phase 2 (whole CTA): dVM[t,c] += sum over the 32 pixels of A[p,t]*dctl[p,c], thread = (t, 32-channel group) register tile.
 template <int VPL>
-__global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
+__global__ void __launch_bounds__(256, VPL == 1 ? 2 : 1) attn_bwd_kernel(AttnP p) {
   extern __shared__ __align__(16) float smf[];
   const int C = p.C;
   float* sK = smf; float* sV = sK + T16 * C; float* sb = sV + T16 * C; float* sm1 = sb + C;
   float* sR = sm1 + C;                       // [C]
   float* sA = sR + C;                        // [32][16]
   __nv_bfloat16* sD = reinterpret_cast<__nv_bfloat16*>(sA + 32 * T16);   // [32][C] bf16
+  float* sDVM = reinterpret_cast<float*>(sD + 32 * C);                  // [16][C] fp32 dVM partial sums, each entry owned by one thread
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < T16 * C; i += blockDim.x) { sK[i] = p.Kf[i]; sV[i] = p.VM[(long long)b * T16 * C + i]; }
+  for (int i = threadIdx.x; i < T16 * C; i += blockDim.x) { const int pi = perm_idx(i / C, i % C, C); sK[pi] = p.Kf[i]; sV[pi] = p.VM[(long long)b * T16 * C + i]; }
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sb[i] = p.bias ? p.bias[i] : 0.f; sm1[i] = 1.f + p.bm[i]; sR[i] = 0.f; }
   __syncthreads();
   const float ns = (p.noise && p.nstr) ? *p.nstr : 0.f;
@@ -158,9 +164,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
   long long pend = p0 + p.pix_per_cta; if (pend > p.HW) pend = p.HW;
   // phase-2 ownership: t2 = tid % 16, channel group g2 = tid / 16 covering channels [g2*CG, g2*CG+CG), CG = C/16
   const int t2 = threadIdx.x & 15, g2 = threadIdx.x >> 4, CG = C / 16;
-  float acc[32];
-#pragma unroll
-  for (int j = 0; j < 32; j++) acc[j] = 0.f;
+  for (int j = 0; j < CG; j++) sDVM[t2 * C + g2 * CG + j] = 0.f;         // own entries only: no synchronisation needed
   float rloc[VPL][8];
 #pragma unroll
   for (int q = 0; q < VPL; q++)
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
             for (int e = 0; e < 8; e++) ctl[e] = sm1[c0 + e];
 #pragma unroll
             for (int t = 0; t < T16; t++) {
-              const float4 v0 = *reinterpret_cast<const float4*>(sV + t * C + c0), v1 = *reinterpret_cast<const float4*>(sV + t * C + c0 + 4);
+              const float4 v0 = *reinterpret_cast<const float4*>(sV + t * C + (c0 >> 1)), v1 = *reinterpret_cast<const float4*>(sV + t * C + (C >> 1) + (c0 >> 1));
               ctl[0] = fmaf(A[t], v0.x, ctl[0]); ctl[1] = fmaf(A[t], v0.y, ctl[1]); ctl[2] = fmaf(A[t], v0.z, ctl[2]); ctl[3] = fmaf(A[t], v0.w, ctl[3]);
               ctl[4] = fmaf(A[t], v1.x, ctl[4]); ctl[5] = fmaf(A[t], v1.y, ctl[5]); ctl[6] = fmaf(A[t], v1.z, ctl[6]); ctl[7] = fmaf(A[t], v1.w, ctl[7]);
             }
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
             }
 #pragma unroll
             for (int t = 0; t < T16; t++) {
-              const float4 v0 = *reinterpret_cast<const float4*>(sV + t * C + c0), v1 = *reinterpret_cast<const float4*>(sV + t * C + c0 + 4);
+              const float4 v0 = *reinterpret_cast<const float4*>(sV + t * C + (c0 >> 1)), v1 = *reinterpret_cast<const float4*>(sV + t * C + (C >> 1) + (c0 >> 1));
               float a = dA[t];
               a = fmaf(dctl[0], v0.x, a); a = fmaf(dctl[1], v0.y, a); a = fmaf(dctl[2], v0.z, a); a = fmaf(dctl[3], v0.w, a);
               a = fmaf(dctl[4], v1.x, a); a = fmaf(dctl[5], v1.y, a); a = fmaf(dctl[6], v1.z, a); a = fmaf(dctl[7], v1.w, a);
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
             for (int e = 0; e < 8; e++) a8[e] = rn * dxn[q][e] - x[q][e] * k3;
 #pragma unroll
             for (int t = 0; t < T16; t++) {
-              const float4 k0 = *reinterpret_cast<const float4*>(sK + t * C + c0), k1 = *reinterpret_cast<const float4*>(sK + t * C + c0 + 4);
+              const float4 k0 = *reinterpret_cast<const float4*>(sK + t * C + (c0 >> 1)), k1 = *reinterpret_cast<const float4*>(sK + t * C + (C >> 1) + (c0 >> 1));
               a8[0] = fmaf(dS[t], k0.x, a8[0]); a8[1] = fmaf(dS[t], k0.y, a8[1]); a8[2] = fmaf(dS[t], k0.z, a8[2]); a8[3] = fmaf(dS[t], k0.w, a8[3]);
               a8[4] = fmaf(dS[t], k1.x, a8[4]); a8[5] = fmaf(dS[t], k1.y, a8[5]); a8[6] = fmaf(dS[t], k1.z, a8[6]); a8[7] = fmaf(dS[t], k1.w, a8[7]);
             }
@@ -260,6 +264,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
     // ---------------- phase 2: dVM partial sums, thread (t2, g2) owns channels g2*CG .. +CG (CG <= 32)
     {
       const int npix = (int)((pend - base) < 32 ? (pend - base) : 32);
+      float acc[32];                                     // live only in this phase (keeps phase 1 under 128 registers)
+      float* own = sDVM + t2 * C + g2 * CG;
+#pragma unroll
+      for (int j = 0; j < 32; j++) acc[j] = (j < CG) ? own[j] : 0.f;
       for (int pp = 0; pp < npix; pp++) {
         const float a = sA[pp * T16 + t2];
         const __nv_bfloat16* drow = sD + (long long)pp * C + g2 * CG;
@@ -278,13 +286,13 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
           for (int j = 0; j < 4; j++) if (j < CG) acc[j] = fmaf(a, __bfloat162float(drow[j]), acc[j]);
         }
       }
+#pragma unroll
+      for (int j = 0; j < 32; j++) if (j < CG) own[j] = acc[j];
     }
     __syncthreads();
   }
   // flush
-#pragma unroll
-  for (int j = 0; j < 32; j++)
-    if (j < CG) atomicAdd(&p.dVM[((long long)b * T16 + t2) * C + g2 * CG + j], acc[j]);
+  for (int j = 0; j < CG; j++) atomicAdd(&p.dVM[((long long)b * T16 + t2) * C + g2 * CG + j], sDVM[t2 * C + g2 * CG + j]);
 #pragma unroll
   for (int q = 0; q < VPL; q++) {
     const int c0 = (q * 32 + lane) * 8;
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnP p) {
 }
 
 static int attn_smem_fwd(int C) { return (2 * T16 * C + 2 * C) * 4; }
-static int attn_smem_bwd(int C) { return (2 * T16 * C + 3 * C + 32 * T16) * 4 + 32 * C * 2; }
+static int attn_smem_bwd(int C) { return (2 * T16 * C + 3 * C + 32 * T16) * 4 + 32 * C * 2 + T16 * C * 4; }
 
 }  // namespace mgf
 

@@ -36,6 +36,7 @@ constexpr int MAX_TAPS = 40;
 constexpr int MAX_AMAPS = 4;
 constexpr int SMEM_BUDGET = 192 * 1024;     // operand stages; + 2 x 16 KB epilogue staging + barriers stays under 227 KB
 constexpr int STG_BYTES = 128 * 128;        // one epilogue group's output staging tile: 128 pixels x 64 channels x 2 B
+constexpr int RACC = 256;                   // floats per epilogue group for the per-CTA d(style) accumulation (BN <= 256)
 
 struct Tap { int8_t amap, dy, dx, pad; int32_t wz; };
 
@@ -149,7 +150,7 @@ struct Cfg {
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE;
   static constexpr int STAGES = STAGES_RAW > 20 ? 20 : STAGES_RAW;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM = STAGES * STAGE + 2 * STG_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM = STAGES * STAGE + 2 * STG_BYTES + 2 * RACC * 4 + BAR_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // instruction descriptor (InstrDescriptor): D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A/B, N>>3 at 17, M>>4 at 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -170,7 +171,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
 // Row `valid`/(x, y, b) identify this thread's pixel; tacc = TMEM address of the tile (lane quarter already applied).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nstr,
-                                              uint8_t* stg, int group, int r) {
+                                              uint8_t* stg, int group, int r, float* racc) {
       const int phase_idx = t.n0 / p.Cout, co0 = t.n0 % p.Cout;
       const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
       const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
@@ -215,8 +216,10 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
               s[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
           }
-          // lane L now holds the sum of column L over this warp's 32 rows (all rows of a tile share one sample: TB == 1)
-          atomicAdd(p.reduce_out + (long long)t.b0 * p.NT + t.n0 + c * 32 + lane, s[0]);
+          // lane L now holds the sum of column L over this warp's 32 rows (all rows of a tile share one sample: TB == 1).
+          // Accumulate per CTA in shared memory; global atomics only when the CTA moves to another (sample, N-block): at 1024^2
+          // that is 148 x BN global atomics per launch instead of 8.4 M onto the same few hundred addresses.
+          atomicAdd(racc + c * 32 + lane, s[0]);
         }
         if (p.scale_n) {
           const float4* sp = reinterpret_cast<const float4*>(p.scale_n + (long long)(valid ? b : 0) * p.NT + t.n0 + c * 32);
@@ -284,13 +287,25 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
       }
 }
 
+template <int BN>
+__device__ __forceinline__ void flush_reduce(const Params& p, float* racc, int key, int group, int r) {
+  group_sync(group);
+  const long long b0 = key / p.n_tiles; const int n0 = (key % p.n_tiles) * BN;
+  for (int j = r; j < BN; j += 128) {
+    const float v = racc[j];
+    if (v != 0.f) atomicAdd(p.reduce_out + b0 * p.NT + n0 + j, v);
+    racc[j] = 0.f;
+  }
+  group_sync(group);
+}
+
 template <int BN, int BK>
 __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ Params p) {
   using C = Cfg<BN, BK>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];                      // swizzled tiles need 1024-byte aligned bases
   uint8_t* stg_base = smem + C::STAGES * C::STAGE;                       // 2 x 16 KB epilogue staging, 1024-byte aligned
-  uint64_t* full = reinterpret_cast<uint64_t*>(stg_base + 2 * STG_BYTES);
+  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * STG_BYTES); // 2 x 256 floats: per-group d(style) partial sums
+  uint64_t* full = reinterpret_cast<uint64_t*>(racc_base + 2 * RACC);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -367,19 +382,27 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     const int r = wq * 32 + lane;            // accumulator row == TMEM lane == pixel index inside the A box
     const int tx = r % p.TW, ty = (r / p.TW) % p.TH, tb = r / (p.TW * p.TH);
     const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
+    float* racc = racc_base + as * RACC;
+    int red_key = -1;
+    if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
     for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BN);
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
       const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
+      if (p.reduce_out) {
+        const int key = t.b0 * p.n_tiles + t.n0 / BN;
+        if (key != red_key) { if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r); red_key = key; }
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr,
-                        stg_base + as * STG_BYTES, as, r);
+                        stg_base + as * STG_BYTES, as, r, racc);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       aphase ^= 1;
     }
-    if (r == 0) tma_store_wait_all();
+    if (p.reduce_out && red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
+    if (r == 0) tma_store_wait_all();       // the group's last TMA store must complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -407,9 +430,9 @@ struct HaloCfg {
   static constexpr int B_TILE = BN * BK * 2;
   static constexpr int B_BYTES = KC * 9 * B_TILE;
   static constexpr int SMEM_MAX = 227 * 1024;
-  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * STG_BYTES - 2048) / A_STAGE;
+  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * STG_BYTES - 2 * RACC * 4 - 512) / A_STAGE;
   static constexpr int NS = NS_RAW > 6 ? 6 : NS_RAW;
-  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 2 * STG_BYTES + 1024 + 256;
+  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 2 * STG_BYTES + 2 * RACC * 4 + 256;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(NS >= 2, "halo kernel needs at least two activation stages");
 };
@@ -437,12 +460,12 @@ __device__ __forceinline__ HaloTile decode_halo(const Params& p, int tile, int B
 template <int BN, int KC, int BK>
 __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant__ Params p) {
   using C = HaloCfg<BN, KC, BK>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sA = smem + C::B_BYTES;
   uint8_t* stg_base = sA + C::NS * C::A_STAGE;
-  uint64_t* afull = reinterpret_cast<uint64_t*>(stg_base + 2 * STG_BYTES);
+  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * STG_BYTES);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(racc_base + 2 * RACC);
   uint64_t* aempty = afull + C::NS;
   uint64_t* bfull = aempty + C::NS;
   uint64_t* tfull = bfull + 1;
@@ -536,19 +559,24 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
     const int r = wq * 32 + lane;
     const int tx = r & 7, ty = r >> 3;
     const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
+    float* racc = racc_base + as * RACC;
+    int red_key = -1;
+    if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
     for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const HaloTile h = decode_halo(p, tile, BN);
       TileCoord t; t.n0 = h.n0; t.x0 = h.x0; t.y0 = h.y0; t.b0 = h.b0;
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0;
       const bool valid = x < p.GW && y < p.GH;
+      if (p.reduce_out && h.key != red_key) { if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r); red_key = h.key; }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr,
-                        stg_base + as * STG_BYTES, as, r);
+                        stg_base + as * STG_BYTES, as, r, racc);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       aphase ^= 1;
     }
+    if (p.reduce_out && red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
     if (r == 0) tma_store_wait_all();
   }
   tc_fence_before();
