@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--no-lpips", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--fwd-dtype", default="bf16", choices=["bf16", "fp16"], help="16-bit type of forward activations/operands")
+    ap.add_argument("--fwd-dtype", default="fp16", choices=["bf16", "fp16"],
+                    help="16-bit type of forward activations/operands (gradients always bf16, fp32 accumulate); fp16 is the parity-green mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-res", type=int, default=None, help="resolution of the CPU baseline sample (default: same as --res)")
     return ap.parse_args()
@@ -283,7 +284,7 @@ def run_native(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.fwd_dtype, "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.fwd_dtype + "_fwd/bf16_grad/f32_acc", "data": "synthetic",
             "config": {"workload": workload_name(args), "resolution": R, "images_per_gpu": B, "global_batch": B * world,
                        "loss": "0.5*LPIPS_vgg16 + 0.5*MSE" if use_lpips else "MSE", "optimizer": "Adam(lr 0.1 schedule, wd 1e-4) on z [B,17,32]",
                        "parallelism": "image-sharded x%d, no per-step collective" % world, "cuda_graph": P.graph is not None,

@@ -30,7 +30,12 @@ def latent_stats(noise_sample):
 class Projector:
     def __init__(self, G, lpips_state_dict, batch, steps, lr=0.1, lamda=0.5, noise=0.05, noise_ramp=0.75, lr_rampdown=0.25,
                  lr_rampup=0.05, weight_decay=1e-4, latent_mean=None, latent_std=None, use_lpips=True, step_noise=None,
-                 noise_seed=3):
+                 noise_seed=3, forward_dtype=None):
+        """forward_dtype: None keeps the library's current setting; 'fp16' / 'bf16' select the 16-bit type of the engine's forward
+        activations and operands (gradients are always bf16).  fp16 meets the 1e-2 image / 1e-3 loss parity bars; bf16 has the
+        fp32 exponent range (use it for checkpoints whose activations may exceed 6.5e4).  Same speed."""
+        if forward_dtype is not None:
+            _lib.set_forward_dtype(forward_dtype)
         self.G = G
         self.dev = next(G.parameters()).device
         if self.dev.type != "cuda":

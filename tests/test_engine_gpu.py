@@ -78,3 +78,33 @@ def test_tc_engine_noise_none_and_mask():
     assert (img.cpu() - ref).abs().max().item() < TOL["bf16"][0] * max(1.0, ref.abs().max().item())
     with pytest.raises(NotImplementedError):
         Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=mask.cuda(), noise_mode="random")
+
+
+def test_full_size_1024_tc_engine_vs_exact_fp32_ops_engine():
+    """BASELINE full size (1024^2, the bench generator): the tcgen05 engine against the exact-fp32 ops engine on the same GPU
+    (the ops engine is itself pinned to the oracle/reference at 32^2 and 64^2).  fp16-forward mode, image within 1e-2 of the
+    range, d(ws) direction within 1e-3 (cosine)."""
+    from morphganformer_b200 import _lib
+    G = util.build_G(1024, 0).cuda()
+    ws = util.case_tensor((1, 17, G.num_ws, 32), 21).cuda()
+    mask = torch.ones(1, 16, device="cuda")
+    tgt = torch.tanh(util.case_tensor((1, 3, 1024, 1024), 22)).cuda()
+    G.synthesis.engine = "ops"
+    w0 = ws.clone().requires_grad_(True)
+    ref, _ = G.synthesis(w0, pos=G.pos, mask=mask, noise_mode="const", return_att_maps=False)
+    gref, = torch.autograd.grad((ref - tgt).square().mean(), [w0])
+    ref = ref.detach()
+    _lib.set_forward_dtype("fp16")
+    try:
+        G.synthesis.engine = "tc"
+        w1 = ws.clone().requires_grad_(True)
+        img, _ = G.synthesis(w1, pos=G.pos, mask=mask, noise_mode="const")
+        g, = torch.autograd.grad((img - tgt).square().mean(), [w1])
+    finally:
+        _lib.set_forward_dtype("bf16")
+    e = (img.detach() - ref)
+    rng = max(1.0, ref.abs().max().item())
+    cos = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
+    print("1024^2: max-abs %.4g of range %.3g, rel rms %.3g, dws cosine %.6f" % (e.abs().max().item(), rng, (e.square().mean().sqrt() / ref.square().mean().sqrt()).item(), cos))
+    assert e.abs().max().item() < 1e-2 * rng
+    assert cos > 0.999
