@@ -44,6 +44,7 @@ struct alignas(64) Params {
   CUtensorMap amap[MAX_AMAPS];
   CUtensorMap bmap;
   CUtensorMap omap[4];          // output tensor, one map per output phase (TMA store of the staged tile)
+  CUtensorMap xmap;             // saved activation X (dgrad epilogues), same geometry as omap[0]: TMA-loaded into the staging tile
   Tap taps[MAX_TAPS];
   int ntaps, kchunks;
   int NB, GH, GW, TB, TH, TW, tilesB, tilesH, tilesW, rows;
@@ -58,6 +59,7 @@ struct alignas(64) Params {
   int total_tiles;
   uint32_t idesc; int out_f16, x_f16, add_f16;
   int tiles_hw;      // halo kernel: tiles per image (tilesW * tilesH)
+  int x_tma; uint32_t x_bytes;   // X tile arrives by TMA (one 64/32-channel group per tile) instead of per-thread strided loads
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -149,7 +151,7 @@ struct Cfg {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE;
   static constexpr int STAGES = STAGES_RAW > 20 ? 20 : STAGES_RAW;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 6) * 8 + 16;
   static constexpr int SMEM = STAGES * STAGE + 2 * STG_BYTES + 2 * RACC * 4 + BAR_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // instruction descriptor (InstrDescriptor): D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A/B, N>>3 at 17, M>>4 at 24
@@ -171,7 +173,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
 // Row `valid`/(x, y, b) identify this thread's pixel; tacc = TMEM address of the tile (lane quarter already applied).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nstr,
-                                              uint8_t* stg, int group, int r, float* racc) {
+                                              uint8_t* stg, int group, int r, float* racc, uint64_t* xbar, uint32_t xphase) {
       const int phase_idx = t.n0 / p.Cout, co0 = t.n0 % p.Cout;
       const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
       const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
@@ -186,7 +188,22 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         for (int j = 0; j < 32; j++) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
         float xv[32];
         const bool needX = (p.X != nullptr) && (p.reduce_out != nullptr || p.actgrad);
-        if (needX) {
+        constexpr int GX32 = (BN >= 64) ? 2 : 1;
+        if (needX && p.x_tma) {
+          // the X tile of this (single-group) output tile was TMA-loaded into the staging buffer while the MMAs were running:
+          // read this thread's row (same swizzle as the store path); the outputs later overwrite exactly the slots read here.
+          if (c == 0) mbar_wait(xbar, xphase);
+          const uint8_t* row = stg + r * (GX32 * 64);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int j = (c % GX32) * 4 + q;
+            const int pos = (GX32 == 2) ? (j ^ (r & 7)) : (j ^ ((r >> 1) & 3));
+            const uint4 u = *reinterpret_cast<const uint4*>(row + pos * 16);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], p.x_f16); xv[q * 8 + e * 2] = valid ? f.x : 0.f; xv[q * 8 + e * 2 + 1] = valid ? f.y : 0.f; }
+          }
+        } else if (needX) {
           if (valid) {
             const uint4* xp = reinterpret_cast<const uint4*>(p.X + obase + c * 32);
 #pragma unroll
@@ -263,8 +280,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         // BN = 32) then leaves with ONE TMA store: fully coalesced, asynchronous, clipped at the image border by the hardware.
         constexpr int GW32 = (BN >= 64) ? 2 : 1;           // 32-column chunks per staged group
         const int h = c % GW32;
-        if (h == 0) {                                      // the previous store must have finished reading the staging tile
-          if (r == 0) tma_store_wait_read();
+        if (h == 0 && !p.x_tma) {                          // the previous store must have finished reading the staging tile
+          if (r == 0) tma_store_wait_read();               // (x_tma: the caller already did this before loading X into it)
           group_sync(group);
         }
         {
@@ -309,12 +326,13 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* xbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); mbar_init(&xbar[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -393,10 +411,18 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         const int key = t.b0 * p.n_tiles + t.n0 / BN;
         if (key != red_key) { if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r); red_key = key; }
       }
+      if (p.x_tma) {                          // prefetch the saved-activation tile into the staging buffer, hidden behind the MMAs
+        if (r == 0) tma_store_wait_read();
+        group_sync(as);
+        if (r == 0) {
+          mbar_arrive_expect_tx(&xbar[as], p.x_bytes);
+          tma_load_4d(&p.xmap, &xbar[as], stg_base + as * STG_BYTES, t.n0, t.x0, t.y0, t.b0);
+        }
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr,
-                        stg_base + as * STG_BYTES, as, r, racc);
+                        stg_base + as * STG_BYTES, as, r, racc, &xbar[as], aphase);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       aphase ^= 1;
@@ -470,13 +496,14 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   uint64_t* bfull = aempty + C::NS;
   uint64_t* tfull = bfull + 1;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* xbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NS; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     mbar_init(bfull, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); mbar_init(&xbar[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -568,10 +595,18 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0;
       const bool valid = x < p.GW && y < p.GH;
       if (p.reduce_out && h.key != red_key) { if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r); red_key = h.key; }
+      if (p.x_tma) {                          // prefetch the saved-activation tile into the staging buffer, hidden behind the MMAs
+        if (r == 0) tma_store_wait_read();
+        group_sync(as);
+        if (r == 0) {
+          mbar_arrive_expect_tx(&xbar[as], p.x_bytes);
+          tma_load_4d(&p.xmap, &xbar[as], stg_base + as * STG_BYTES, t.n0, t.x0, t.y0, t.b0);
+        }
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr,
-                        stg_base + as * STG_BYTES, as, r, racc);
+                        stg_base + as * STG_BYTES, as, r, racc, &xbar[as], aphase);
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       aphase ^= 1;
@@ -629,6 +664,21 @@ static int encode_out_maps(Params& p, const mgf_conv_tc_desc* d, int BN, int TW,
     cuuint32_t box[4] = {(cuuint32_t)gwd, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
     if (int e = encode(&p.omap[ph], base, 4, dims, strides, box, gwd)) return e;
   }
+  return 0;
+}
+
+// X (saved activation) tile by TMA when the tile is a single staging group (BN <= 64) and the output is not phase-interleaved
+static int encode_x_map(Params& p, const mgf_conv_tc_desc* d, int BN, int TW, int TH, int TB, int rows) {
+  p.x_tma = 0; p.x_bytes = 0;
+  const bool needX = d->X && (d->reduce_out || d->actgrad);
+  if (!needX || BN > 64 || d->phases != 1 || d->osx != 1 || d->osy != 1) return 0;
+  if ((uintptr_t)d->X & 15) MGF_FAIL(MGF_E_ALIGN, "conv_tc: X must be 16-byte aligned");
+  const int gwd = BN >= 64 ? 64 : 32;
+  cuuint64_t dims[4] = {(cuuint64_t)d->OC, (cuuint64_t)d->OW, (cuuint64_t)d->OH, (cuuint64_t)d->NB};
+  cuuint64_t strides[3] = {(cuuint64_t)d->OC * 2, (cuuint64_t)d->OW * d->OC * 2, (cuuint64_t)d->OH * d->OW * d->OC * 2};
+  cuuint32_t box[4] = {(cuuint32_t)gwd, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+  if (int e = encode(&p.xmap, d->X, 4, dims, strides, box, gwd)) return e;
+  p.x_tma = 1; p.x_bytes = (uint32_t)(rows * gwd * 2);
   return 0;
 }
 
@@ -747,6 +797,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(HBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
     if (int e = encode_out_maps(p, d, HBN, 8, 16, 1)) return e;
+    if (int e = encode_x_map(p, d, HBN, 8, 16, 1, 128)) return e;
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
     cudaStream_t st = (cudaStream_t)stream;
     if (HBK == 64 && HBN == 64) return launch_halo<64, 1, 64>(p, grid, st);
@@ -804,6 +855,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
   }
   if (int e = encode_out_maps(p, d, BN, TW, TH, TB)) return e;
+  if (int e = encode_x_map(p, d, BN, TW, TH, TB, p.rows)) return e;
   int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
 #define MGF_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch<bn, bk>(p, grid, st);
