@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-lpips", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dump-conv", action="store_true", help="print every conv launch of one step (CUDA-event time) to stderr")
     ap.add_argument("--fwd-dtype", default="fp16", choices=["bf16", "fp16"],
                     help="16-bit type of forward activations/operands (gradients always bf16, fp32 accumulate); fp16 is the parity-green mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
@@ -256,14 +257,17 @@ def run_native(args):
             P.step(use_graph=False)
         torch.cuda.synchronize()
         recs, tc.PROFILE = tc.PROFILE, None
-        tms = sum(a.elapsed_time(b) for (_, a, b, _, _) in recs)
+        if args.dump_conv:
+            for rec in recs[:len(recs) // 2]:
+                print("CONV %-8s %.3f ms  %7.1f alg TF/s  %s" % (rec[0], rec[1].elapsed_time(rec[2]), rec[3] / rec[1].elapsed_time(rec[2]) / 1e9, rec[5]), file=sys.stderr)
+        tms = sum(r[1].elapsed_time(r[2]) for r in recs)
         alg = sum(r[3] for r in recs)
         exe = sum(r[4] for r in recs)
         pk, pk_src = peaks()
         peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
         ach = alg / (tms / 1000.0) / 1e12
         by_tag = {}
-        for (tag, a, b, fa, fe) in recs:
+        for (tag, a, b, fa, fe, _desc) in recs:
             d = by_tag.setdefault(tag, [0.0, 0.0, 0.0, 0]); d[0] += a.elapsed_time(b); d[1] += fa; d[2] += fe; d[3] += 1
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes of one step)", "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " bf16_tflops_sustained",

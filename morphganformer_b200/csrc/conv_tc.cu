@@ -99,7 +99,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 // one lane of a fully converged warp (keeps the surrounding loop warp-uniform, so the compiler stays on the uniform datapath
@@ -149,10 +150,11 @@ struct Cfg {
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE;
+  static constexpr int NSTG = (BN <= 64) ? 2 : 1;        // staging tiles per epilogue group (double-buffered when a tile is one group)
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - (NSTG - 1) * 2 * STG_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 20 ? 20 : STAGES_RAW;
   static constexpr int BAR_BYTES = (2 * STAGES + 6) * 8 + 16;
-  static constexpr int SMEM = STAGES * STAGE + 2 * STG_BYTES + 2 * RACC * 4 + BAR_BYTES;
+  static constexpr int SMEM = STAGES * STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + BAR_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // instruction descriptor (InstrDescriptor): D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A/B, N>>3 at 17, M>>4 at 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -171,18 +173,21 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
 
 // Fused layer tail for one 128 x BN accumulator tile (called by all four warps of an epilogue group after the tfull wait).
 // Row `valid`/(x, y, b) identify this thread's pixel; tacc = TMEM address of the tile (lane quarter already applied).
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nstr,
-                                              uint8_t* stg, int group, int r, float* racc, uint64_t* xbar, uint32_t xphase) {
+template <int BN, int NSTG>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nz,
+                                              uint8_t* stg, int group, int r, float* racc, uint64_t* xbar, uint32_t xphase, uint64_t* tempty_bar) {
       const int phase_idx = t.n0 / p.Cout, co0 = t.n0 % p.Cout;
       const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
       const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
       const long long obase = pix * p.OC + co0;
-      const float nz = (p.noise && valid) ? p.noise[oy * p.OW + ox] * nstr : 0.f;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         uint32_t raw[32];
         tmem_ld32(tacc + (uint32_t)(c * 32), raw);
+        if (c == BN / 32 - 1) {          // the accumulator now lives in registers: hand the TMEM stage back to the MMA issuer at once
+          tc_fence_before();
+          mbar_arrive(tempty_bar);
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
@@ -281,7 +286,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         constexpr int GW32 = (BN >= 64) ? 2 : 1;           // 32-column chunks per staged group
         const int h = c % GW32;
         if (h == 0 && !p.x_tma) {                          // the previous store must have finished reading the staging tile
-          if (r == 0) tma_store_wait_read();               // (x_tma: the caller already did this before loading X into it)
+          if (r == 0) tma_store_wait_read<NSTG - 1>();     // (x_tma: the caller already did this before loading X into it)
           group_sync(group);
         }
         {
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   using C = Cfg<BN, BK>;
   extern __shared__ __align__(1024) uint8_t smem[];                      // swizzled tiles need 1024-byte aligned bases
   uint8_t* stg_base = smem + C::STAGES * C::STAGE;                       // 2 x 16 KB epilogue staging, 1024-byte aligned
-  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * STG_BYTES); // 2 x 256 floats: per-group d(style) partial sums
+  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * C::NSTG * STG_BYTES); // 2 x 256 floats: per-group d(style) partial sums
   uint64_t* full = reinterpret_cast<uint64_t*>(racc_base + 2 * RACC);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
@@ -411,20 +416,24 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         const int key = t.b0 * p.n_tiles + t.n0 / BN;
         if (key != red_key) { if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r); red_key = key; }
       }
+      uint8_t* stg = stg_base + (as * C::NSTG + (C::NSTG == 2 ? (int)aphase : 0)) * STG_BYTES;   // alternate staging tiles per tile
       if (p.x_tma) {                          // prefetch the saved-activation tile into the staging buffer, hidden behind the MMAs
-        if (r == 0) tma_store_wait_read();
+        if (r == 0) tma_store_wait_read<C::NSTG - 1>();
         group_sync(as);
         if (r == 0) {
           mbar_arrive_expect_tx(&xbar[as], p.x_bytes);
-          tma_load_4d(&p.xmap, &xbar[as], stg_base + as * STG_BYTES, t.n0, t.x0, t.y0, t.b0);
+          tma_load_4d(&p.xmap, &xbar[as], stg, t.n0, t.x0, t.y0, t.b0);
         }
+      }
+      float nz = 0.f;                         // noise value of this thread's pixel, fetched before the accumulator wait
+      if (p.noise && valid) {
+        const int ph = t.n0 / p.Cout;
+        nz = __ldg(p.noise + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr,
-                        stg_base + as * STG_BYTES, as, r, racc, &xbar[as], aphase);
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      epilogue_tile<BN, C::NSTG>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz,
+                                 stg, as, r, racc, &xbar[as], aphase, &tempty[as]);
       aphase ^= 1;
     }
     if (p.reduce_out && red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
@@ -456,9 +465,10 @@ struct HaloCfg {
   static constexpr int B_TILE = BN * BK * 2;
   static constexpr int B_BYTES = KC * 9 * B_TILE;
   static constexpr int SMEM_MAX = 227 * 1024;
-  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * STG_BYTES - 2 * RACC * 4 - 512) / A_STAGE;
+  static constexpr int NSTG = 2;
+  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * NSTG * STG_BYTES - 2 * RACC * 4 - 512) / A_STAGE;
   static constexpr int NS = NS_RAW > 6 ? 6 : NS_RAW;
-  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 2 * STG_BYTES + 2 * RACC * 4 + 256;
+  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + 256;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(NS >= 2, "halo kernel needs at least two activation stages");
 };
@@ -490,7 +500,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   uint8_t* sB = smem;
   uint8_t* sA = smem + C::B_BYTES;
   uint8_t* stg_base = sA + C::NS * C::A_STAGE;
-  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * STG_BYTES);
+  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * C::NSTG * STG_BYTES);
   uint64_t* afull = reinterpret_cast<uint64_t*>(racc_base + 2 * RACC);
   uint64_t* aempty = afull + C::NS;
   uint64_t* bfull = aempty + C::NS;
@@ -595,20 +605,24 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0;
       const bool valid = x < p.GW && y < p.GH;
       if (p.reduce_out && h.key != red_key) { if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r); red_key = h.key; }
+      uint8_t* stg = stg_base + (as * C::NSTG + (C::NSTG == 2 ? (int)aphase : 0)) * STG_BYTES;   // alternate staging tiles per tile
       if (p.x_tma) {                          // prefetch the saved-activation tile into the staging buffer, hidden behind the MMAs
-        if (r == 0) tma_store_wait_read();
+        if (r == 0) tma_store_wait_read<C::NSTG - 1>();
         group_sync(as);
         if (r == 0) {
           mbar_arrive_expect_tx(&xbar[as], p.x_bytes);
-          tma_load_4d(&p.xmap, &xbar[as], stg_base + as * STG_BYTES, t.n0, t.x0, t.y0, t.b0);
+          tma_load_4d(&p.xmap, &xbar[as], stg, t.n0, t.x0, t.y0, t.b0);
         }
+      }
+      float nz = 0.f;                         // noise value of this thread's pixel, fetched before the accumulator wait
+      if (p.noise && valid) {
+        const int ph = t.n0 / p.Cout;
+        nz = __ldg(p.noise + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nstr,
-                        stg_base + as * STG_BYTES, as, r, racc, &xbar[as], aphase);
-      tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      epilogue_tile<BN, C::NSTG>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz,
+                                 stg, as, r, racc, &xbar[as], aphase, &tempty[as]);
       aphase ^= 1;
     }
     if (p.reduce_out && red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);

@@ -100,7 +100,8 @@ def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 
     if prof is not None:
         e1.record()
         ex = 2.0 * d.NB * d.GH * d.GW * (phases * cout) * w.shape[3] * len(taps)
-        prof.append((tag, e0, e1, ex * alg_scale, ex))
+        prof.append((tag, e0, e1, ex * alg_scale, ex, "B%d %dx%d C%d->%d x%d taps%d %s" % (d.NB, d.GH, d.GW, w.shape[3], cout, phases, len(taps),
+                     "+".join(k for k, v in (("red", reduce_out), ("X", X), ("add", add), ("noise", noise), ("bias", bias)) if v is not None))))
     return out
 
 
