@@ -134,6 +134,8 @@ int mgf_style_bwd(const float* ds, const float* R, const float* s, const float* 
                   float again, float sgain, float* dwg, int64_t dwg_stride, int B, int Cin, int O, int wdim, void* stream);
 int mgf_modulate_weights(const float* base, const float* rs, int nmod, const float* cs, void* out, int out_fwd,
                          int B, int64_t T, int64_t NT, int64_t K, void* stream);
+/* out[b,p,c] = x[b,p,c] * sc[b,c] on an NHWC 16-bit tensor (is_fwd: forward-dtype tensor, else bf16 gradient) */
+int mgf_scale_channels(const void* x, const float* sc, void* out, int is_fwd, int B, int64_t HW, int C, void* stream);
 int mgf_small_gemm(const float* A, int64_t sAb, int64_t sAm, const float* Bm, const float* bias, float* out,
                    int64_t sOb, int64_t sOm, int B, int M, int N, int K, int accumulate, void* stream);
 int mgf_torgb_fwd(const void* y, const float* wrgb, const float* s, const float* bias, float* img, int B, int64_t HW, int C, void* stream);

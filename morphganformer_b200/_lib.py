@@ -32,6 +32,7 @@ SIGNATURES = {
     "mgf_style_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_style_bwd": (c_int, [c_void_p] * 6 + [c_float, c_float, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_modulate_weights": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_void_p]),
+    "mgf_scale_channels": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
     "mgf_small_gemm": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_torgb_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]),
     "mgf_torgb_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int64, c_int, c_void_p]),

@@ -108,6 +108,25 @@ __global__ void __launch_bounds__(256) modulate_kernel(const float* base, const 
   }
 }
 
+// ---- per-(sample, channel) scaling of an NHWC 16-bit tensor: out[b,p,c] = x[b,p,c] * sc[b,c]   (activation-side modulation for
+// the low-resolution layers, where per-sample weight tensors would dwarf the activations)
+__global__ void __launch_bounds__(256) scale_channels_kernel(const __nv_bfloat16* x, const float* sc, __nv_bfloat16* out, long long HW, int C, bool f16) {
+  const int b = blockIdx.y, vecs = C / 8;
+  const long long total = HW * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vecs);
+    const long long off = (long long)b * HW * C + i * 8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off));
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + (long long)b * C + cv * 8)), s1 = __ldg(reinterpret_cast<const float4*>(sc + (long long)b * C + cv * 8 + 4));
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+    const float2 a = unpack16(w4[0], f16), bq = unpack16(w4[1], f16), c = unpack16(w4[2], f16), d = unpack16(w4[3], f16);
+    uint4 o;
+    o.x = pack16(a.x * s0.x, a.y * s0.y, f16); o.y = pack16(bq.x * s0.z, bq.y * s0.w, f16);
+    o.z = pack16(c.x * s1.x, c.y * s1.y, f16); o.w = pack16(d.x * s1.z, d.y * s1.w, f16);
+    *reinterpret_cast<uint4*>(out + off) = o;
+  }
+}
+
 // ---- tiny batched GEMM: out[b,m,n] = sum_k A[b,m,k] * Bm[n,k] (+ bias[n]); A strided (sAb, sAm), optional accumulate into out
 __global__ void __launch_bounds__(256) small_gemm_kernel(const float* A, long long sAb, long long sAm, const float* Bm, const float* bias,
                                                          float* out, long long sOb, long long sOm, int M, int N, int K, int accumulate) {
@@ -463,5 +482,15 @@ extern "C" int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, floa
   upfir2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dv,
                                                             make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C);
   MGF_CHECK_LAUNCH("upfir2_bwd");
+  return 0;
+}
+
+extern "C" int mgf_scale_channels(const void* x, const float* sc, void* out, int is_fwd, int B, int64_t HW, int C, void* stream) {
+  if (!x || !sc || !out) MGF_FAIL(MGF_E_BADARG, "scale_channels: null tensor");
+  if (C % 8) MGF_FAIL(MGF_E_SHAPE, "scale_channels: C must be a multiple of 8");
+  if (B <= 0 || HW <= 0) return 0;
+  dim3 grid(grid_for(HW * (C / 8), 256, 8), B);
+  scale_channels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, sc, (__nv_bfloat16*)out, HW, C, is_fwd && fwd_f16());
+  MGF_CHECK_LAUNCH("scale_channels");
   return 0;
 }

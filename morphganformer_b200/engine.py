@@ -155,6 +155,11 @@ class SynthesisEngine:
             L.taps_f = [(0, ty - 1, tx - 1, ty * 3 + tx) for ty in range(3) for tx in range(3)]
             L.taps_b = [(ph, 1 - ty, 1 - tx, ph * 9 + ty * 3 + tx) for ph in range(4) for ty in range(3) for tx in range(3)]
             L.phases = 4
+        # low-resolution layers: per-sample weight tensors (B x 4.7-19 MB) would dwarf the activations, so modulate the ACTIVATIONS
+        # instead (xs = x*s, epilogue *d; reference non-fused algebra, networks.py:314-324) and keep ONE shared weight tensor
+        L.shared_w = L.res <= 128 and O * I >= 256 * 256
+        L.Bb16 = L.Bb.unsqueeze(0).to(torch.bfloat16).contiguous() if L.shared_w else None     # [1, T, I, O]
+        L._Bf16 = None
         L.A = m.affine.weight.detach().float().contiguous()          # [I, 32]
         L.ab = (m.affine.bias.detach().float() * float(m.affine.b_gain)).contiguous()
         L.again = float(m.affine.w_gain)
@@ -230,17 +235,29 @@ class SynthesisEngine:
     def _layer_fwd(self, L, x_in, ws, maskbias, st, B, noise_on, add=None):
         """x_in [B,h,w,I] bf16 -> z [B,H,W,O] bf16 (post noise/bias/act)."""
         s, d = self._styles(L, ws, st, B)
-        Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape), fwd=True)
-        self._modulate(L.Bf, d, L.O, s, Wf, B, True)
         h, w = x_in.shape[1], x_in.shape[2]
         H, Wd = h * L.up, w * L.up
         st[f"xin{L.idx}"] = x_in
+        scale_n = None
+        if L.shared_w:
+            dt = _lib.forward_torch_dtype()
+            if L._Bf16 is None or L._Bf16.dtype != dt:
+                L._Bf16 = L.Bf.unsqueeze(0).to(dt).contiguous()                      # [1, T, NT, I]
+            Wf = L._Bf16
+            xs = self._buf(st, f"xs{L.idx}", tuple(x_in.shape), fwd=True)
+            _lib.check(_L().mgf_scale_channels(_p(x_in), _p(s), _p(xs), 1, B, h * w, L.I, _s(self.dev)), "mgf_scale_channels")
+            a_in = xs
+            scale_n = d if L.phases == 1 else d.repeat(1, L.phases).contiguous()      # [B, NT]
+        else:
+            Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape), fwd=True)
+            self._modulate(L.Bf, d, L.O, s, Wf, B, True)
+            a_in = x_in
         noise = L.noise if (L.has_noise and noise_on) else None
         nstr = L.nstr if noise is not None else None
         kw = dict(osy=L.up, osx=L.up, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1))
         if L.attn:
             y = self._buf(st, f"y{L.idx}", (B, H, Wd, L.O), fwd=True)
-            tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
+            tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, scale_n=scale_n, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
             VM = self._buf(st, f"VM{L.idx}", (B, 16, L.O), torch.float32)
             comps = ws[:, :-1, L.idx]                           # [B,16,32] strided
             _lib.check(_L().mgf_small_gemm(_p(comps), comps.stride(0), comps.stride(1), _p(L.WVM), _p(L.bVM), _p(VM),
@@ -250,7 +267,7 @@ class SynthesisEngine:
                                          L.gain, LRELU_ALPHA, _p(z), None, B, H * Wd, L.O, _s(self.dev)), "mgf_attn_fwd")
         else:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
-            tc.conv_tc([x_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, z, noise=noise, noise_strength=nstr, bias=L.bias,
+            tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, z, scale_n=scale_n, noise=noise, noise_strength=nstr, bias=L.bias,
                        act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, add=add, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
         return z
 
@@ -301,8 +318,13 @@ class SynthesisEngine:
     def _dgrad(self, L, dy, st, B, out, add=None, actgrad_X=None, ag_gain=1.0):
         """dy [B,H,W,O] (gradient wrt this layer's conv output) -> out [B,h,w,I] = d x_in; accumulates d(styles)."""
         d = st[f"d{L.idx}"]; s = st[f"s{L.idx}"]
-        Wb = self._buf(st, f"Wb{L.idx}", (B,) + tuple(L.Bb.shape))
-        self._modulate(L.Bb, None, 1, d, Wb, B, False)
+        if L.shared_w:       # dy*d on the (small) gradient tensor, shared transposed weights
+            dyd = self._buf(st, f"dyd{L.idx}", tuple(dy.shape))
+            _lib.check(_L().mgf_scale_channels(_p(dy), _p(d), _p(dyd), 0, B, dy.shape[1] * dy.shape[2], L.O, _s(self.dev)), "mgf_scale_channels")
+            dy, Wb = dyd, L.Bb16
+        else:
+            Wb = self._buf(st, f"Wb{L.idx}", (B,) + tuple(L.Bb.shape))
+            self._modulate(L.Bb, None, 1, d, Wb, B, False)
         x_in = st[f"xin{L.idx}"]
         h, w = x_in.shape[1], x_in.shape[2]
         ds = self._buf(st, f"ds{L.idx}", (B, L.I), torch.float32)
