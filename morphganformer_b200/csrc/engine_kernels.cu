@@ -286,32 +286,34 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, c
 // (reference Conv2dLayer.forward :245-250 -> conv2d_resample 1x1-up branch -> upfirdn2d(up=2, pad=[2,1,2,1], gain=4) -> bias_act gain).
 // fk = flipped normalised 1-D taps * 2 (gain 4 split per axis).
 __global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* v, const __nv_bfloat16* add, __nv_bfloat16* out,
-                                                         float4 fk, float g, int h, int w, int C, bool f16) {
-  const int vecs = C / 8;
-  const long long total = (long long)gridDim.y * 0 + (long long)(2 * h) * (2 * w) * vecs;
-  const int b = blockIdx.y;
+                                                         float4 fk, float g, int h, int w, int C, bool f16, int vshift) {
+  // grid: x = chunks of one output row (X, channel-vector), y = output row Y, z = sample.  vecs = C/8 = 1 << vshift.
+  const int vecs = 1 << vshift;
+  const int b = blockIdx.z, Y = blockIdx.y;
+  const int rowlen = (2 * w) << vshift;
   const float f[4] = {fk.x, fk.y, fk.z, fk.w};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % vecs); long long t = i / vecs;
-    const int X = (int)(t % (2 * w)), Y = (int)(t / (2 * w));
+  const int fy0 = Y & 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += gridDim.x * blockDim.x) {
+    const int cv = i & (vecs - 1), X = i >> vshift;
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) acc[e] = 0.f;
-    // taps with (Y + fy - 2) even: fy has the parity of Y
-    for (int fy = (Y & 1); fy < 4; fy += 2) {
-      const int iy = (Y + fy - 2) >> 1;
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      const int fy = fy0 + 2 * a, iy = (Y + fy - 2) >> 1;
       if (iy < 0 || iy >= h) continue;
-      for (int fx = (X & 1); fx < 4; fx += 2) {
-        const int ix = (X + fx - 2) >> 1;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; c2++) {
+        const int fx = (X & 1) + 2 * c2, ix = (X + fx - 2) >> 1;
         if (ix < 0 || ix >= w) continue;
         const float cf = f[fy] * f[fx];
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(v + (((long long)b * h + iy) * w + ix) * C + cv * 8));
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(v + ((((long long)b * h + iy) * w + ix) << (vshift + 3))) + cv);
         const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 4; e++) { const float2 q = unpack16(w4[e], f16); acc[e * 2] = fmaf(cf, q.x, acc[e * 2]); acc[e * 2 + 1] = fmaf(cf, q.y, acc[e * 2 + 1]); }
       }
     }
-    const long long off = (((long long)b * 2 * h + Y) * 2 * w + X) * C + cv * 8;
+    const long long off = ((((long long)b * 2 * h + Y) * 2 * w + X) << (vshift + 3)) + cv * 8;
     float av[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) av[e] = 0.f;
@@ -329,14 +331,13 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* v,
 }
 
 // adjoint of the above (without the add): dv[b,iy,ix,c] = g * sum_{fy,fx} fk[fy] fk[fx] dout[b, 2iy+2-fy, 2ix+2-fx, c]
-__global__ void __launch_bounds__(256) upfir2_bwd_kernel(const __nv_bfloat16* dout, __nv_bfloat16* dv, float4 fk, float g, int h, int w, int C) {
-  const int vecs = C / 8;
-  const long long total = (long long)h * w * vecs;
-  const int b = blockIdx.y;
+__global__ void __launch_bounds__(256) upfir2_bwd_kernel(const __nv_bfloat16* dout, __nv_bfloat16* dv, float4 fk, float g, int h, int w, int C, int vshift) {
+  const int vecs = 1 << vshift;
+  const int b = blockIdx.z, iy = blockIdx.y;
+  const int rowlen = w << vshift;
   const float f[4] = {fk.x, fk.y, fk.z, fk.w};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % vecs); long long t = i / vecs;
-    const int ix = (int)(t % w), iy = (int)(t / w);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += gridDim.x * blockDim.x) {
+    const int cv = i & (vecs - 1), ix = i >> vshift;
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) acc[e] = 0.f;
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(256) upfir2_bwd_kernel(const __nv_bfloat16* do
         const int X = 2 * ix + 2 - fx;
         if (X < 0 || X >= 2 * w) continue;
         const float cf = f[fy] * f[fx];
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dout + (((long long)b * 2 * h + Y) * 2 * w + X) * C + cv * 8));
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dout + ((((long long)b * 2 * h + Y) * 2 * w + X) << (vshift + 3))) + cv);
         const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); acc[e * 2] = fmaf(cf, q.x, acc[e * 2]); acc[e * 2 + 1] = fmaf(cf, q.y, acc[e * 2 + 1]); }
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256) upfir2_bwd_kernel(const __nv_bfloat16* do
     uint4 o;
     o.x = pack_bf16(acc[0] * g, acc[1] * g); o.y = pack_bf16(acc[2] * g, acc[3] * g);
     o.z = pack_bf16(acc[4] * g, acc[5] * g); o.w = pack_bf16(acc[6] * g, acc[7] * g);
-    *reinterpret_cast<uint4*>(dv + (((long long)b * h + iy) * w + ix) * C + cv * 8) = o;
+    *reinterpret_cast<uint4*>(dv + ((((long long)b * h + iy) * w + ix) << (vshift + 3)) + cv * 8) = o;
   }
 }
 
@@ -465,22 +466,30 @@ extern "C" int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, co
   return 0;
 }
 
+static int log2_exact(int v) { int s = 0; while ((1 << s) < v) s++; return (1 << s) == v ? s : -1; }
+
 extern "C" int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream) {
   if (!v || !out || !fk4) MGF_FAIL(MGF_E_BADARG, "upfir2_add: null tensor");
-  if (C % 8) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: C must be a multiple of 8");
-  dim3 grid(grid_for((long long)4 * h * w * (C / 8), 256, 8), B);
+  const int vs = (C % 8) ? -1 : log2_exact(C / 8);
+  if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: C/8 must be a power of two");
+  if (2 * h > 65535 || B > 65535) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: image too tall");
+  const int rowlen = (2 * w) << vs;
+  dim3 grid((rowlen + 255) / 256, 2 * h, B);
   upfir2_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)add, (__nv_bfloat16*)out,
-                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, fwd_f16());
+                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, fwd_f16(), vs);
   MGF_CHECK_LAUNCH("upfir2_add");
   return 0;
 }
 
 extern "C" int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream) {
   if (!dout || !dv || !fk4) MGF_FAIL(MGF_E_BADARG, "upfir2_bwd: null tensor");
-  if (C % 8) MGF_FAIL(MGF_E_SHAPE, "upfir2_bwd: C must be a multiple of 8");
-  dim3 grid(grid_for((long long)h * w * (C / 8), 256, 8), B);
+  const int vs = (C % 8) ? -1 : log2_exact(C / 8);
+  if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "upfir2_bwd: C/8 must be a power of two");
+  if (h > 65535 || B > 65535) MGF_FAIL(MGF_E_SHAPE, "upfir2_bwd: image too tall");
+  const int rowlen = w << vs;
+  dim3 grid((rowlen + 255) / 256, h, B);
   upfir2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dv,
-                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C);
+                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, vs);
   MGF_CHECK_LAUNCH("upfir2_bwd");
   return 0;
 }

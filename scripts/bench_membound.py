@@ -1,0 +1,41 @@
+"""Micro-benchmark of the HBM-bound engine kernels at the 1024^2 x 8 bench shapes: achieved algorithmic GB/s (CUDA events, best of 5)."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from morphganformer_b200 import _lib
+L = _lib.lib(); s = torch.cuda.current_stream().cuda_stream
+def p(t): return t.data_ptr() if t is not None else None
+def run(name, fn, nbytes):
+    ts = []
+    for i in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        if i >= 2: ts.append(e0.elapsed_time(e1))
+    print("%-34s %.3f ms  %6.0f GB/s" % (name, min(ts), nbytes / min(ts) / 1e6), flush=True)
+B = 8
+bf = lambda *sh: torch.randn(*sh, device="cuda").to(torch.bfloat16)
+for (H, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
+    f = bf(B, H, H, C).abs(); n1 = bf(B, H, H, C).abs() * 0.1; lin = torch.rand(C, device="cuda"); val = torch.zeros(B, device="cuda"); coef = torch.full((B,), 0.5, device="cuda")
+    out = torch.empty_like(f); n = f.numel() * 2
+    run("lpips_head fwd %dx%d C%d" % (H, H, C), lambda: L.mgf_lpips_head(1, p(f), p(n1), p(lin), None, None, p(val), 0, B, H * H, C, s), 2 * n)
+    dy = bf(B, H // 2, H // 2, C)
+    run("lpips_tap_pool_bwd %dx%d C%d" % (H, H, C), lambda: L.mgf_lpips_tap_pool_bwd(p(f), p(n1), p(lin), p(coef), p(dy), p(out), B, H, H, C, s), 3.25 * n)
+    y = torch.empty(B, H // 2, H // 2, C, dtype=torch.bfloat16, device="cuda")
+    run("maxpool2_fwd %dx%d C%d" % (H, H, C), lambda: L.mgf_maxpool2_fwd(p(f), p(y), B, H, H, C, s), 1.25 * n)
+for (H, C) in [(1024, 32), (512, 64), (256, 128)]:
+    z = bf(B, H, H, C); dz = bf(B, H, H, C); dy = torch.empty_like(z); R = torch.zeros(B, C, device="cuda"); noise = torch.randn(H, H, device="cuda"); ns = torch.tensor([0.1], device="cuda"); bias = torch.zeros(C, device="cuda")
+    n = z.numel() * 2
+    run("act_bwd mode0 %dx%d C%d" % (H, H, C), lambda: L.mgf_act_bwd(p(dz), p(z), p(dy), p(R), p(noise), p(ns), p(bias), 0.2, 1.0, 0, B, H * H, C, s), 3 * n)
+    run("act_bwd reduce-only %dx%d C%d" % (H, H, C), lambda: L.mgf_act_bwd(p(dz), p(z), None, p(R), p(noise), p(ns), p(bias), 0.2, 1.4, 1, B, H * H, C, s), 2 * n)
+    v = bf(B, H // 2, H // 2, C); fk = (ctypes.c_float * 4)(0.125, 0.375, 0.375, 0.125)
+    run("upfir2_add -> %dx%d C%d" % (H, H, C), lambda: L.mgf_upfir2_add(p(v), p(z), p(dy), fk, 2.8, B, H // 2, H // 2, C, s), 2.25 * n)
+    dv = torch.empty_like(v)
+    run("upfir2_bwd %dx%d C%d" % (H, H, C), lambda: L.mgf_upfir2_bwd(p(dz), p(dv), fk, 2.8, B, H // 2, H // 2, C, s), 1.25 * n)
+R_ = 1024
+img = torch.randn(B, 3, R_, R_, device="cuda"); tgt = torch.randn_like(img); col = torch.empty(B, R_, R_, 32, dtype=torch.bfloat16, device="cuda"); mse = torch.zeros(B, device="cuda"); dimg = torch.empty_like(img)
+run("lpips_prep 1024", lambda: L.mgf_lpips_prep(p(img), p(tgt), p(col), p(mse), B, R_, s), img.numel() * 8 + col.numel() * 2)
+run("lpips_prep_bwd 1024", lambda: L.mgf_lpips_prep_bwd(p(col), p(img), p(tgt), 0.1, p(dimg), B, R_, s), img.numel() * 12 + col.numel() * 2)
+y = bf(B, R_, R_, 32); wr = torch.randn(3, 32, device="cuda"); sr = torch.randn(B, 32, device="cuda"); br = torch.zeros(3, device="cuda")
+run("torgb_fwd 1024 C32", lambda: L.mgf_torgb_fwd(p(y), p(wr), p(sr), p(br), p(img), B, R_ * R_, 32, s), y.numel() * 2 + img.numel() * 4)
+dyy = torch.empty_like(y); ds = torch.zeros(B, 32, device="cuda"); RR = torch.zeros(B, 32, device="cuda")
+run("torgb_bwd 1024 C32", lambda: L.mgf_torgb_bwd(p(dimg), p(y), p(wr), p(sr), p(dyy), p(ds), p(RR), B, R_ * R_, 32, s), y.numel() * 4 + img.numel() * 4)
