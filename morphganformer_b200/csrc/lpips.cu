@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f,
 // replaces lpips_head<2> + maxpool2_bwd for those taps: x and n1 are read once, the head gradient never touches HBM
 // (7 tensor passes -> 3.25).  A group of LPP lanes owns one 2x2 window (4 pixels), channel vectors stay in registers.
 template <int VPL>
-__global__ void __launch_bounds__(256) lpips_tap_pool_bwd_kernel(const __nv_bfloat16* x, const __nv_bfloat16* n1, const float* lin, const float* coef,
+__global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kernel(const __nv_bfloat16* x, const __nv_bfloat16* n1, const float* lin, const float* coef,
                                                                  const __nv_bfloat16* dy, __nv_bfloat16* dx, int H, int W, int C, bool f16) {
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpp = (C / 8) / VPL, wpw = 32 / lpp;                // lanes per window, windows per warp
@@ -264,37 +264,40 @@ __global__ void __launch_bounds__(256) lpips_tap_pool_bwd_kernel(const __nv_bflo
     const long long wi = w0 + sub;
     const bool ok = wi < nwin;
     const int xo = (int)((ok ? wi : 0) % Wo), yo = (int)((ok ? wi : 0) / Wo);
-    float xv[4][VPL][8], gv[4][VPL][8];
+    // the 4 pixels of the window stay PACKED in registers (16-bit pairs) and are unpacked on use: 32 registers instead of 128
+    uint4 xr[4][VPL], nr[4][VPL];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const long long row = (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C;
-      float tv[VPL][8];
-      float ss = 0.f;
 #pragma unroll
       for (int q = 0; q < VPL; q++) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row) + q * lpp + ll);
-        const uint4 un = __ldg(reinterpret_cast<const uint4*>(n1 + row) + q * lpp + ll);
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w}, n4[4] = {un.x, un.y, un.z, un.w};
+        xr[k][q] = __ldg(reinterpret_cast<const uint4*>(x + row) + q * lpp + ll);
+        nr[k][q] = __ldg(reinterpret_cast<const uint4*>(n1 + row) + q * lpp + ll);
+      }
+    }
+    // one pass: |f|^2, sum lin f^2, sum lin f n1 per pixel -> one shuffle round of 3 values -> inv and k2
+    float inv[4], k2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float ss = 0.f, sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int q = 0; q < VPL; q++) {
+        const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w}, n4[4] = {nr[k][q].x, nr[k][q].y, nr[k][q].z, nr[k][q].w};
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const float2 v = unpack16(w4[e], f16), t = unpack16(n4[e], f16);
-          xv[k][q][e * 2] = v.x; xv[k][q][e * 2 + 1] = v.y; tv[q][e * 2] = t.x; tv[q][e * 2 + 1] = t.y;
           ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss);
+          sa = fmaf(lw[q][e * 2] * v.x, v.x, sa); sa = fmaf(lw[q][e * 2 + 1] * v.y, v.y, sa);
+          sb = fmaf(lw[q][e * 2] * v.x, t.x, sb); sb = fmaf(lw[q][e * 2 + 1] * v.y, t.y, sb);
         }
       }
-      for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float r = sqrtf(ss), inv = 1.f / (r + eps);
-      float dot = 0.f;
-#pragma unroll
-      for (int q = 0; q < VPL; q++)
-#pragma unroll
-        for (int e = 0; e < 8; e++) { gv[k][q][e] = 2.f * lw[q][e] * (xv[k][q][e] * inv - tv[q][e]); dot = fmaf(gv[k][q][e], xv[k][q][e], dot); }
-      for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      const float k2 = (r > 0.f) ? dot * inv * inv / r : 0.f;
-#pragma unroll
-      for (int q = 0; q < VPL; q++)
-#pragma unroll
-        for (int e = 0; e < 8; e++) gv[k][q][e] = cf * (gv[k][q][e] * inv - k2 * xv[k][q][e]);
+      for (int o = lpp >> 1; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o); sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o);
+      }
+      const float r = sqrtf(ss);
+      inv[k] = 1.f / (r + eps);
+      const float dot = 2.f * (inv[k] * sa - sb);                // g . f  with g = 2 lin (f inv - n1)
+      k2[k] = (r > 0.f) ? dot * inv[k] * inv[k] / r : 0.f;
     }
     if (!ok) continue;
 #pragma unroll
@@ -306,19 +309,33 @@ __global__ void __launch_bounds__(256) lpips_tap_pool_bwd_kernel(const __nv_bflo
 #pragma unroll
         for (int e = 0; e < 4; e++) { const float2 v = unpack_bf16(w4[e]); g[e * 2] = v.x; g[e * 2 + 1] = v.y; }
       }
+      float xv[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float2 v = unpack16(w4[e], f16); xv[k][e * 2] = v.x; xv[k][e * 2 + 1] = v.y; }
+      }
       int arg[8];
 #pragma unroll
       for (int e = 0; e < 8; e++) {
-        int a = 0; float m = xv[0][q][e];
+        int a = 0; float m = xv[0][e];
 #pragma unroll
-        for (int k = 1; k < 4; k++) if (xv[k][q][e] > m) { m = xv[k][q][e]; a = k; }
+        for (int k = 1; k < 4; k++) if (xv[k][e] > m) { m = xv[k][e]; a = k; }
         arg[e] = a;
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
+        const uint32_t n4[4] = {nr[k][q].x, nr[k][q].y, nr[k][q].z, nr[k][q].w};
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) { const float v = ((arg[e] == k) ? g[e] : 0.f) + gv[k][q][e]; o[e] = xv[k][q][e] > 0.f ? v : 0.f; }
+        for (int e = 0; e < 4; e++) {
+          const float2 t = unpack16(n4[e], f16);
+          const float h0 = cf * (2.f * lw[q][e * 2] * (xv[k][e * 2] * inv[k] - t.x) * inv[k] - k2[k] * xv[k][e * 2]);
+          const float h1 = cf * (2.f * lw[q][e * 2 + 1] * (xv[k][e * 2 + 1] * inv[k] - t.y) * inv[k] - k2[k] * xv[k][e * 2 + 1]);
+          const float v0 = ((arg[e * 2] == k) ? g[e * 2] : 0.f) + h0, v1 = ((arg[e * 2 + 1] == k) ? g[e * 2 + 1] : 0.f) + h1;
+          o[e * 2] = xv[k][e * 2] > 0.f ? v0 : 0.f; o[e * 2 + 1] = xv[k][e * 2 + 1] > 0.f ? v1 : 0.f;
+        }
         uint4 u;
         u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
         const long long row = (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C;
