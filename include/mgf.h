@@ -112,6 +112,9 @@ typedef struct {
   int32_t bn; int32_t reduce_per_sample;
   /* which tensors are FORWARD-dtype tensors (see mgf_set_forward_dtype); 0 = gradient tensor (bf16) */
   int32_t ab_fwd, out_fwd, x_fwd, add_fwd;
+  /* rows are pairs of 32-channel pixels viewed as one 64-channel super-pixel (the caller passes block-expanded weights): the
+   * noise plane is then [GH, 2*GW] and the two 32-column halves of a row get their own noise value */
+  int32_t superpix;
 } mgf_conv_tc_desc;
 int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream);
 /* debugging / A-B measurement: 0 disables the halo (shared-memory tap reuse) variant that mgf_conv_tc picks for C = 64/128 3x3 layers */

@@ -59,6 +59,7 @@ struct alignas(64) Params {
   int total_tiles;
   uint32_t idesc; int out_f16, x_f16, add_f16;
   int tiles_hw;      // halo kernel: tiles per image (tilesW * tilesH)
+  int superpix;                  // output rows are PAIRS of pixels (32+32 channels): noise differs between the two 32-column halves
   int x_tma; uint32_t x_bytes;   // X tile arrives by TMA (one 64/32-channel group per tile) instead of per-thread strided loads
 };
 
@@ -174,7 +175,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
 // Fused layer tail for one 128 x BN accumulator tile (called by all four warps of an epilogue group after the tfull wait).
 // Row `valid`/(x, y, b) identify this thread's pixel; tacc = TMEM address of the tile (lane quarter already applied).
 template <int BN, int NSTG>
-__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nz,
+__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nz, float nz1,
                                               uint8_t* stg, int group, int r, float* racc, uint64_t* xbar, uint32_t xphase, uint64_t* tempty_bar) {
       const int phase_idx = t.n0 / p.Cout, co0 = t.n0 % p.Cout;
       const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
@@ -249,8 +250,9 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           for (int j = 0; j < 8; j++) { const float4 f = __ldg(sp + j); v[4 * j] *= f.x; v[4 * j + 1] *= f.y; v[4 * j + 2] *= f.z; v[4 * j + 3] *= f.w; }
         }
         if (p.noise) {
+          const float nzc = (p.superpix && (c & 1)) ? nz1 : nz;      // super-pixel rows: odd 32-column chunk = right pixel of the pair
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] += nz;
+          for (int j = 0; j < 32; j++) v[j] += nzc;
         }
         if (p.bias) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + co0 + c * 32);
@@ -425,14 +427,19 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           tma_load_4d(&p.xmap, &xbar[as], stg, t.n0, t.x0, t.y0, t.b0);
         }
       }
-      float nz = 0.f;                         // noise value of this thread's pixel, fetched before the accumulator wait
+      float nz = 0.f, nz1 = 0.f;              // noise value(s) of this thread's pixel, fetched before the accumulator wait
       if (p.noise && valid) {
-        const int ph = t.n0 / p.Cout;
-        nz = __ldg(p.noise + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+        if (p.superpix) {                     // row = pixel pair (2x, 2x+1) of a [H, 2*GW] noise plane
+          const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)y * (2 * p.OW) + 2 * x));
+          nz = n2.x * nstr; nz1 = n2.y * nstr;
+        } else {
+          const int ph = t.n0 / p.Cout;
+          nz = __ldg(p.noise + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+        }
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, C::NSTG>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz,
+      epilogue_tile<BN, C::NSTG>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz, nz1,
                                  stg, as, r, racc, &xbar[as], aphase, &tempty[as]);
       aphase ^= 1;
     }
@@ -614,14 +621,19 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
           tma_load_4d(&p.xmap, &xbar[as], stg, t.n0, t.x0, t.y0, t.b0);
         }
       }
-      float nz = 0.f;                         // noise value of this thread's pixel, fetched before the accumulator wait
+      float nz = 0.f, nz1 = 0.f;              // noise value(s) of this thread's pixel, fetched before the accumulator wait
       if (p.noise && valid) {
-        const int ph = t.n0 / p.Cout;
-        nz = __ldg(p.noise + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+        if (p.superpix) {                     // row = pixel pair (2x, 2x+1) of a [H, 2*GW] noise plane
+          const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)y * (2 * p.OW) + 2 * x));
+          nz = n2.x * nstr; nz1 = n2.y * nstr;
+        } else {
+          const int ph = t.n0 / p.Cout;
+          nz = __ldg(p.noise + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+        }
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, C::NSTG>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz,
+      epilogue_tile<BN, C::NSTG>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz, nz1,
                                  stg, as, r, racc, &xbar[as], aphase, &tempty[as]);
       aphase ^= 1;
     }
@@ -804,7 +816,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     p.scale_n = d->scale_n; p.reduce_out = d->reduce_out; p.X = (const __nv_bfloat16*)d->X;
     p.noise = d->noise; p.noise_strength = d->noise_strength; p.bias = d->bias;
     p.act = d->act; p.alpha = d->alpha; p.gain = d->gain; p.add = (const __nv_bfloat16*)d->add;
-    p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain;
+    p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain; p.superpix = d->superpix;
     if ((p.reduce_out || p.actgrad) && !p.X) MGF_FAIL(MGF_E_BADARG, "conv_tc: reduce/actgrad need X");
     const bool f16 = fwd_f16();
     const uint32_t fmt = (f16 && d->ab_fwd) ? 0u : 1u;
@@ -865,7 +877,8 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   p.scale_n = d->scale_n; p.reduce_out = d->reduce_out; p.X = (const __nv_bfloat16*)d->X;
   p.noise = d->noise; p.noise_strength = d->noise_strength; p.bias = d->bias;
   p.act = d->act; p.alpha = d->alpha; p.gain = d->gain; p.add = (const __nv_bfloat16*)d->add;
-  p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain;
+  p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain; p.superpix = d->superpix;
+  if (p.superpix && (d->phases != 1 || d->Cout != 64)) MGF_FAIL(MGF_E_UNSUP, "conv_tc: superpix needs phases == 1 and Cout == 64 (two 32-channel pixels)");
   if ((p.reduce_out || p.actgrad) && !p.X) MGF_FAIL(MGF_E_BADARG, "conv_tc: reduce/actgrad need X");
   p.tx_bytes = (uint32_t)((p.rows * BK + BN * BK) * 2);
   {

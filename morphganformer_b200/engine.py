@@ -160,6 +160,24 @@ class SynthesisEngine:
         L.shared_w = L.res <= 128 and O * I >= 256 * 256
         L.Bb16 = L.Bb.unsqueeze(0).to(torch.bfloat16).contiguous() if L.shared_w else None     # [1, T, I, O]
         L._Bf16 = None
+        # 32 -> 32 channel 3x3 layers (the 1024^2 block): 64-byte pixel rows halve the TMA efficiency, so view two neighbouring pixels as
+        # one 64-channel super-pixel (same memory) and expand the weights to the block form [9][(po,o)][(pi,i)]
+        L.superpix = (m.up == 1 and O == 32 and I == 32 and L.res >= 64 and not L.shared_w and m.transformer is None)
+        if L.superpix:
+            Bf2 = torch.zeros(9, 64, 64, device=W.device); Bb2 = torch.zeros(9, 64, 64, device=W.device)
+            for ky in range(3):
+                for ks in range(3):            # super-pixel shift dxs = ks - 1
+                    for po in range(2):
+                        for pi in range(2):
+                            kx = 2 * (ks - 1) + pi - po + 1          # forward: x_in = x_out + kx - 1
+                            if 0 <= kx < 3:
+                                Bf2[ky * 3 + ks, po * 32:(po + 1) * 32, pi * 32:(pi + 1) * 32] = W[:, :, ky, kx]
+                            kb = po + 1 - 2 * (ks - 1) - pi          # dgrad: dy pixel x' = x + 1 - kx
+                            if 0 <= kb < 3:
+                                Bb2[ky * 3 + ks, po * 32:(po + 1) * 32, pi * 32:(pi + 1) * 32] = W[:, :, ky, kb].t()
+            L.Bf, L.Bb = Bf2.contiguous(), Bb2.contiguous()
+            L.taps_f = [(0, ky - 1, ks - 1, ky * 3 + ks) for ky in range(3) for ks in range(3)]
+            L.taps_b = [(0, 1 - ky, ks - 1, ky * 3 + ks) for ky in range(3) for ks in range(3)]
         L.A = m.affine.weight.detach().float().contiguous()          # [I, 32]
         L.ab = (m.affine.bias.detach().float() * float(m.affine.b_gain)).contiguous()
         L.again = float(m.affine.w_gain)
@@ -248,6 +266,12 @@ class SynthesisEngine:
             _lib.check(_L().mgf_scale_channels(_p(x_in), _p(s), _p(xs), 1, B, h * w, L.I, _s(self.dev)), "mgf_scale_channels")
             a_in = xs
             scale_n = d if L.phases == 1 else d.repeat(1, L.phases).contiguous()      # [B, NT]
+        elif L.superpix:
+            s2, d2 = s.repeat(1, 2).contiguous(), d.repeat(1, 2).contiguous()
+            st[f"s2_{L.idx}"], st[f"d2_{L.idx}"] = s2, d2
+            Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape), fwd=True)
+            self._modulate(L.Bf, d2, 64, s2, Wf, B, True)
+            a_in = x_in.view(B, h, w // 2, 64)
         else:
             Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape), fwd=True)
             self._modulate(L.Bf, d, L.O, s, Wf, B, True)
@@ -265,6 +289,11 @@ class SynthesisEngine:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             _lib.check(_L().mgf_attn_fwd(_p(y), _p(L.Kf), _p(L.Sc), _p(maskbias), _p(VM), _p(L.bm), _p(noise), _p(nstr), _p(L.bias),
                                          L.gain, LRELU_ALPHA, _p(z), None, B, H * Wd, L.O, _s(self.dev)), "mgf_attn_fwd")
+        elif L.superpix:
+            z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
+            bias2 = L.bias.repeat(2).contiguous() if L.bias is not None else None
+            tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w // 2), 1, 64, z.view(B, H, Wd // 2, 64), noise=noise, noise_strength=nstr, bias=bias2,
+                       act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, alg_scale=0.5, tag="g.fwd", superpix=True)
         else:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, z, scale_n=scale_n, noise=noise, noise_strength=nstr, bias=L.bias,
@@ -318,7 +347,9 @@ class SynthesisEngine:
     def _dgrad(self, L, dy, st, B, out, add=None, actgrad_X=None, ag_gain=1.0):
         """dy [B,H,W,O] (gradient wrt this layer's conv output) -> out [B,h,w,I] = d x_in; accumulates d(styles)."""
         d = st[f"d{L.idx}"]; s = st[f"s{L.idx}"]
-        if L.shared_w:       # dy*d on the (small) gradient tensor, shared transposed weights
+        if L.superpix:
+            Wb = None            # handled below with the block-expanded operands
+        elif L.shared_w:     # dy*d on the (small) gradient tensor, shared transposed weights
             dyd = self._buf(st, f"dyd{L.idx}", tuple(dy.shape))
             _lib.check(_L().mgf_scale_channels(_p(dy), _p(d), _p(dyd), 0, B, dy.shape[1] * dy.shape[2], L.O, _s(self.dev)), "mgf_scale_channels")
             dy, Wb = dyd, L.Bb16
@@ -327,6 +358,17 @@ class SynthesisEngine:
             self._modulate(L.Bb, None, 1, d, Wb, B, False)
         x_in = st[f"xin{L.idx}"]
         h, w = x_in.shape[1], x_in.shape[2]
+        if L.superpix:
+            assert add is None
+            s2, d2 = st[f"s2_{L.idx}"], st[f"d2_{L.idx}"]
+            Wb = self._buf(st, f"Wb{L.idx}", (B,) + tuple(L.Bb.shape))
+            self._modulate(L.Bb, None, 1, d2, Wb, B, False)
+            ds2 = self._buf(st, f"ds2_{L.idx}", (B, 64), torch.float32)
+            ds2.zero_()
+            tc.conv_tc([dy.view(B, h, w // 2, 64)], Wb, L.taps_b, (B, h, w // 2), 1, 64, out.view(B, h, w // 2, 64), scale_n=s2, reduce_out=ds2,
+                       X=x_in.view(B, h, w // 2, 64), actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain,
+                       reduce_per_sample=True, alg_scale=0.5, tag="g.bwd", fwd=False)
+            return ds2[:, :32] + ds2[:, 32:]
         ds = self._buf(st, f"ds{L.idx}", (B, L.I), torch.float32)
         ds.zero_()
         acts = [dy] if L.up == 1 else [tc.phase_view(dy, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
