@@ -80,6 +80,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)       # a still-exiting NVML client stalls this process's next cudaMalloc for ~0.5 s
+        except Exception:
+            self.proc.kill()
         sm, smax, reasons = [], None, set()
         for r in self.rows:
             try:
@@ -232,12 +236,14 @@ def run_native(args):
         loss_host = torch.empty(B).pin_memory()
         t0 = time.perf_counter()
         e0.record()
-        P.set_targets(target_host.to(dev, non_blocking=True))               # target upload is part of a projection job
+        P.set_targets(target_host)                                          # target upload (pinned host -> HBM) is part of a projection job
         for i in range(K):
             P.step_noise[P.i + 1].copy_(noise_host[W + K + i], non_blocking=True)   # this step's Adam kernel adds it for step i+1
             per_img = P.step()
             loss_host.copy_(per_img, non_blocking=True)
             torch.cuda.current_stream().synchronize()                       # the caller reads the loss every step (tqdm in the reference)
+            if os.environ.get("MGF_BENCH_DEBUG"):
+                print("e2e step %d done at %.1f ms" % (i, (time.perf_counter() - t0) * 1e3), file=sys.stderr)
         e1.record()
         barrier()
         ems = e0.elapsed_time(e1)

@@ -109,7 +109,9 @@ class LpipsEngine:
             self.n1 = None
         target = self.target
         B = target.shape[0]
-        h, _, _ = self._features(target, None, None, "t")
+        # the trunk runs in the generated-image branch's buffers (tag "g": overwritten by every forward anyway), so a new job
+        # allocates nothing once the first one has run -- addresses stay stable for graph replay and set_target costs ~6 ms
+        h, _, _ = self._features(target, None, None, "g")
         fresh = self.n1 is None
         if fresh:
             self.n1 = []
@@ -120,8 +122,6 @@ class LpipsEngine:
             _lib.check(_L().mgf_lpips_head(0, _p(f), None, None, None, _p(n), None, 0, B, f.shape[1] * f.shape[2], f.shape[3], s), "mgf_lpips_head")
             if fresh:
                 self.n1.append(n)
-        for key in [k for k in self._st if k.startswith("t")]:
-            del self._st[key]
 
     @torch.no_grad()
     def forward(self, img, want_mse=True):

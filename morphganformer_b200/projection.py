@@ -87,13 +87,13 @@ class Projector:
         self.i = 0
 
     def set_targets(self, target):
-        """target [B,3,R,R] fp32 in [-1,1] (device or host)."""
-        target = target.to(self.dev, torch.float32)
+        """target [B,3,R,R] fp32 in [-1,1] (device or host; a pinned host tensor is uploaded asynchronously straight into the
+        resident target buffer, no intermediate device allocation)."""
         assert target.shape[0] == self.B
         if getattr(self, "target", None) is not None and tuple(self.target.shape) == tuple(target.shape):
-            self.target.copy_(target)                   # same buffer: a captured graph keeps working for the next job
+            self.target.copy_(target, non_blocking=True)   # same buffer: a captured graph keeps working for the next job
         else:
-            self.target = target.contiguous().clone()
+            self.target = target.to(self.dev, torch.float32).contiguous().clone()
             self.graph = None
         if self.lp is not None:
             self.lp.set_target(self.target)
