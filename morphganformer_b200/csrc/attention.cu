@@ -318,7 +318,7 @@ static int attn_check(int C, const char* who) {
   return 0;
 }
 
-extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
+extern "C" int mgf_attn_fwd_simt(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                             const float* noise, const float* nstr, const float* bias, float gain, float alpha,
                             void* out, float* probs, int B, int64_t HW, int C, void* stream) {
   if (!X || !Kf || !Sc || !maskbias || !VM || !bm || !out) MGF_FAIL(MGF_E_BADARG, "attn_fwd: null tensor");
@@ -343,7 +343,7 @@ extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, con
   return 0;
 }
 
-extern "C" int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
+extern "C" int mgf_attn_bwd_simt(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                             const float* noise, const float* nstr, const float* bias, float gain, float alpha,
                             void* dX, float* dVM, float* R, int B, int64_t HW, int C, void* stream) {
   if (!X || !dz || !Kf || !Sc || !maskbias || !VM || !bm || !dX || !dVM) MGF_FAIL(MGF_E_BADARG, "attn_bwd: null tensor");

@@ -1,0 +1,68 @@
+"""Tensor-core duplex-attention kernels (mgf_attn_fwd / mgf_attn_bwd) against a plain PyTorch fp32 statement of the same folded
+layer (reference training/networks.py:748-822 + :1036-1040 with the host-side constant folding of engine.py).  Floating-point
+kernel -> torch fp32 reference; tolerances: outputs are stored in 16 bits (fp16: 2^-11, bf16: 2^-8 relative), gradients in bf16."""
+import pytest
+import torch
+
+from morphganformer_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(X, Kf, Sc, mb, VM, bm, noise, ns, bias, gain, alpha):
+    S = X @ Kf.t() + Sc[None] + mb[:, None, :]
+    A = torch.softmax(S, -1)
+    ctl = A @ VM + bm
+    xn = X * torch.rsqrt(X.square().mean(-1, keepdim=True) + 1e-8)
+    u = xn * (1 + ctl) + noise[None, :, None] * ns + bias
+    return torch.nn.functional.leaky_relu(u, alpha) * gain, A
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+@pytest.mark.parametrize("fwd", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,HW,C", [(2, 16, 32), (2, 100, 64), (3, 1032, 128), (2, 4096, 256), (1, 500, 384), (2, 1000, 512), (8, 16, 512)])
+def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd):
+    L = _lib.lib()
+    _lib.set_forward_dtype(fwd)
+    try:
+        dt = torch.float16 if fwd == "fp16" else torch.bfloat16
+        g = torch.Generator(device="cuda").manual_seed(B * 1000 + HW + C)
+        r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+        X16 = (r(B, HW, C) * 1.5).to(dt)
+        Kf, Sc, mb = r(16, C) * (2.0 / C ** 0.5), r(HW, 16), r(B, 16) * 0.3
+        VM, bm, noise, ns, bias = r(B, 16, C) * 0.3, r(C) * 0.1, r(HW), torch.tensor([0.2], device="cuda"), r(C) * 0.1
+        dz16 = r(B, HW, C).to(torch.bfloat16)
+        gain, alpha = 1.4142135, 0.2
+        s = torch.cuda.current_stream().cuda_stream
+        out = torch.empty_like(X16); probs = torch.empty(B, HW, 16, device="cuda")
+        _lib.check(L.mgf_attn_fwd(_p(X16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(out), _p(probs), B, HW, C, s), "fwd")
+        dX = torch.empty(B, HW, C, device="cuda", dtype=torch.bfloat16); dVM = torch.zeros(B, 16, C, device="cuda"); R = torch.zeros(B, C, device="cuda")
+        _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(dX), _p(dVM), _p(R), B, HW, C, s), "bwd")
+        torch.cuda.synchronize()
+        Xr = X16.float().requires_grad_(True); VMr = VM.clone().requires_grad_(True)
+        ref, A = _ref(Xr, Kf, Sc, mb, VMr, bm, noise, ns, bias, gain, alpha)
+        gX, gVM = torch.autograd.grad(ref, [Xr, VMr], grad_outputs=dz16.float())
+        Rr = (gX * Xr.detach()).sum(1)
+        eps = 2.0 ** -10 if fwd == "fp16" else 2.0 ** -7
+        scale = ref.abs().max().item()
+        assert (probs - A).abs().max().item() < (2e-3 if fwd == "fp16" else 1.5e-2)
+        # lrelu kink: an element whose pre-activation is within rounding of 0 may flip slope; compare in the large
+        eo = (out.float() - ref).abs()
+        assert eo.max().item() < 4 * eps * scale and eo.mean().item() < eps * ref.abs().mean().item()
+        rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+        assert rel(dX.float(), gX) < 1.5e-2, rel(dX.float(), gX)
+        assert rel(dVM, gVM) < 1.5e-2, rel(dVM, gVM)
+        assert rel(R, Rr) < 1.5e-2, rel(R, Rr)
+    finally:
+        _lib.set_forward_dtype("bf16")
+
+
+def test_attn_rejects_bad_shapes():
+    L = _lib.lib()
+    x = torch.zeros(1, 16, 48, device="cuda", dtype=torch.bfloat16)
+    f = torch.zeros(16, 48, device="cuda")
+    rc = L.mgf_attn_fwd(_p(x), _p(f), _p(f), _p(f), _p(f), _p(f), None, None, None, 1.0, 0.2, _p(x), None, 1, 16, 48, 0)
+    assert rc != 0 and b"C=48" in L.mgf_last_error()
