@@ -163,6 +163,13 @@ int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc
  * MSELoss (1024_example_percept_MSE.py:143), Adam + latent noise (:117, :134-135, :153). */
 int mgf_lpips_prep(const float* img, const float* target, void* col, float* mse, int B, int R, void* stream);
 int mgf_lpips_prep_bwd(const void* dcol, const float* img, const float* target, float mcoef, float* dimg, int B, int R, void* stream);
+/* LPIPS input stage fused with VGG conv1_1 (vgg_first.cu): ScalingLayer (networks_basic.py:94-101) + conv3x3(3->64) + bias + ReLU
+ * (pretrained_networks.py:97-135, slice1 layers 0-1) straight from the fp32 NCHW image, and its backward to the image.
+ * W [64][32] fp32, column (ky*3+kx)*3+c (27..31 unused); out [B,R,R,64] in the forward 16-bit type; gy [B,R,R,64] bf16. */
+int mgf_vgg_conv1_fwd(const float* img, const float* target, float* mse, const float* W, const float* bias, void* out,
+                      int B, int R, void* stream);
+int mgf_vgg_conv1_bwd(const void* gy, const float* W, const float* img, const float* target, float mcoef, float* dimg,
+                      int B, int R, void* stream);
 int mgf_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, void* stream);
 int mgf_maxpool2_bwd(const void* x, const void* dy, const void* extra, void* dx, int B, int H, int W, int C, void* stream);
 int mgf_lpips_head(int mode, const void* f, const void* n1, const float* lin, const float* coef, void* out, float* val,

@@ -6,9 +6,9 @@ channel-unit-normalisation, squared difference, 1x1 `lin` layers, spatial mean, 
 during a projection, so its normalised tap features are computed once (set_target) instead of every step as the reference does.
 Also produces the MSE term of the projection loss in the same pass over the image (1024_example_percept_MSE.py:143).
 
-Everything arithmetic is a kernel of libmgf_sm100a.so: mgf_lpips_prep (scale + im2col of the 3-channel input so conv1_1 runs as
-a K=32 GEMM), mgf_conv_tc (all convolutions and their input gradients, bias+ReLU and ReLU-mask fused in the epilogue),
-mgf_maxpool2_*, mgf_lpips_head.
+Everything arithmetic is a kernel of libmgf_sm100a.so: mgf_vgg_conv1_fwd/bwd (ScalingLayer + conv1_1 + ReLU and its backward,
+straight from / to the fp32 NCHW image), mgf_conv_tc (the other 12 convolutions and their input gradients, bias+ReLU and ReLU-mask
+fused in the epilogue), mgf_maxpool2_*, mgf_lpips_head, mgf_lpips_tap_pool_bwd.
 """
 import torch
 from . import _lib, tc
@@ -75,11 +75,12 @@ class LpipsEngine:
         """Runs the VGG trunk; returns the list of conv outputs h[i] (post-ReLU, NHWC bf16) and pooled tensors."""
         B, _, R, _ = img.shape
         s = _lib.stream_ptr(self.dev)
-        col = self._buf(tag + "col", (B, R, R, 32), fwd=True)
-        _lib.check(_L().mgf_lpips_prep(_p(img), _p(target), _p(col), _p(mse), B, R, s), "mgf_lpips_prep")
-        h, x, res, ci = [], col, R, 0
+        # ScalingLayer + conv1_1 + ReLU (+ the MSE sum) in one kernel, straight from the fp32 image (no im2col buffer)
+        y0 = self._buf(f"{tag}h0", (B, R, R, 64), fwd=True)
+        _lib.check(_L().mgf_vgg_conv1_fwd(_p(img), _p(target), _p(mse), _p(self.wf[0]), _p(self.bias[0]), _p(y0), B, R, s), "mgf_vgg_conv1_fwd")
+        h, x, res, ci = [y0], y0, R, 1
         pooled = {}
-        for item in VGG:
+        for item in VGG[1:]:
             if item == "P":
                 y = self._buf(f"{tag}p{ci}", (B, res // 2, res // 2, x.shape[3]), fwd=True)
                 _lib.check(_L().mgf_maxpool2_fwd(_p(x), _p(y), B, res, res, x.shape[3], s), "mgf_maxpool2_fwd")
@@ -88,13 +89,11 @@ class LpipsEngine:
                 continue
             cin, cout = item
             y = self._buf(f"{tag}h{ci}", (B, res, res, cout), fwd=True)
-            taps = [(0, 0, 0, 0)] if ci == 0 else tc.TAPS_3X3
-            tc.conv_tc([x], self._wfwd(ci), taps, (B, res, res), 1, cout, y, bias=self.bias[ci], act=2, gain=1.0,
-                       alg_scale=27.0 / 32.0 if ci == 0 else 1.0, tag="vgg.fwd")
+            tc.conv_tc([x], self._wfwd(ci), tc.TAPS_3X3, (B, res, res), 1, cout, y, bias=self.bias[ci], act=2, gain=1.0, tag="vgg.fwd")
             h.append(y)
             x = y
             ci += 1
-        return h, pooled, col
+        return h, pooled, None
 
     @torch.no_grad()
     def set_target(self, target):
@@ -184,10 +183,10 @@ class LpipsEngine:
                 g = g2
                 pos -= 1
             ci -= 1
-        dcol = self._buf("dcol", (B, R, R, 32))
-        tc.conv_tc([g], self.wb[0], [(0, 0, 0, 0)], (B, R, R), 1, 32, dcol, alg_scale=27.0 / 32.0, tag="vgg.bwd", fwd=False)
         dimg = torch.empty_like(self.img)
-        _lib.check(_L().mgf_lpips_prep_bwd(_p(dcol), _p(self.img), _p(self.target), float(mse_coef), _p(dimg), B, R, s), "mgf_lpips_prep_bwd")
+        # conv1_1 input gradient (64 -> 27 product + col2im in shared memory) / scale + the MSE gradient, one kernel
+        _lib.check(_L().mgf_vgg_conv1_bwd(_p(g), _p(self.wf[0]), _p(self.img), _p(self.target) if mse_coef else None, float(mse_coef), _p(dimg), B, R, s),
+                   "mgf_vgg_conv1_bwd")
         return dimg
 
 

@@ -39,3 +39,9 @@ y = bf(B, R_, R_, 32); wr = torch.randn(3, 32, device="cuda"); sr = torch.randn(
 run("torgb_fwd 1024 C32", lambda: L.mgf_torgb_fwd(p(y), p(wr), p(sr), p(br), p(img), B, R_ * R_, 32, s), y.numel() * 2 + img.numel() * 4)
 dyy = torch.empty_like(y); ds = torch.zeros(B, 32, device="cuda"); RR = torch.zeros(B, 32, device="cuda")
 run("torgb_bwd 1024 C32", lambda: L.mgf_torgb_bwd(p(dimg), p(y), p(wr), p(sr), p(dyy), p(ds), p(RR), B, R_ * R_, 32, s), y.numel() * 4 + img.numel() * 4)
+
+# fused LPIPS input stage + VGG conv1_1 (vgg_first.cu): bytes = image (+ target) + the 64-channel tensor once (+ image gradient)
+wc = torch.randn(64, 32, device="cuda") * 0.1; b64 = torch.zeros(64, device="cuda"); h0 = torch.empty(B, R_, R_, 64, dtype=torch.bfloat16, device="cuda")
+run("vgg_conv1_fwd 1024 (+mse)", lambda: L.mgf_vgg_conv1_fwd(p(img), p(tgt), p(mse), p(wc), p(b64), p(h0), B, R_, s), img.numel() * 8 + h0.numel() * 2)
+run("vgg_conv1_fwd 1024 (no mse)", lambda: L.mgf_vgg_conv1_fwd(p(img), None, None, p(wc), p(b64), p(h0), B, R_, s), img.numel() * 4 + h0.numel() * 2)
+run("vgg_conv1_bwd 1024 (+mse grad)", lambda: L.mgf_vgg_conv1_bwd(p(h0), p(wc), p(img), p(tgt), 0.1, p(dimg), B, R_, s), img.numel() * 12 + h0.numel() * 2)
