@@ -88,11 +88,11 @@ def build_generator(res, seed=0, **kw):
     return G
 
 
-def build_lpips(seed=4):
+def build_lpips(seed=4, net_type="vgg"):
     import torch
     ref = load()
     torch.manual_seed(seed)
-    net = ref.lpips_nb.PNetLin(pnet_type="vgg", pnet_rand=True, use_dropout=True, version="0.1", lpips=True).eval()
-    sd = torch.load(os.path.join(REF_ROOT, "lpips", "weights", "v0.1", "vgg.pth"), map_location="cpu")
+    net = ref.lpips_nb.PNetLin(pnet_type=net_type, pnet_rand=True, use_dropout=True, version="0.1", lpips=True).eval()
+    sd = torch.load(os.path.join(REF_ROOT, "lpips", "weights", "v0.1", net_type + ".pth"), map_location="cpu")
     net.load_state_dict(sd, strict=False)
     return net.requires_grad_(False)

@@ -61,6 +61,27 @@ def build_vgg_lpips_sd(seed=4):
     return sd
 
 
+def build_lpips_sd(net, seed=4):
+    """LPIPS alex / squeeze parameters: torchvision default random init under `seed` in the reference's naming + the shipped
+    `lin` weights (tests/golden/lpips_lin_{alex,squeeze}_v0.1.npz, written by make_golden_lpips_nets.py)."""
+    import torchvision
+    if net == "vgg":
+        return build_vgg_lpips_sd(seed)
+    torch.manual_seed(seed)
+    feats = (torchvision.models.alexnet(weights=None) if net == "alex" else torchvision.models.squeezenet1_1(weights=None)).features
+    slices = {"alex": [range(0, 2), range(2, 5), range(5, 8), range(8, 10), range(10, 12)],
+              "squeeze": [range(0, 2), range(2, 5), range(5, 8), range(8, 10), range(10, 11), range(11, 12), range(12, 13)]}[net]
+    sd = {}
+    for s, idxs in enumerate(slices, 1):
+        for i in idxs:
+            for k, v in feats[i].state_dict().items():
+                sd[f"net.slice{s}.{i}.{k}"] = v.detach().clone()
+    lin = np.load(os.path.join(GOLDEN, f"lpips_lin_{net}_v0.1.npz"))
+    for kk in range(len(slices)):
+        sd[f"lin{kk}.model.1.weight"] = torch.from_numpy(lin[f"lin{kk}"]).reshape(1, -1, 1, 1)
+    return sd
+
+
 # (name, x shape, filter taps or None, kwargs) -- the calls SURVEY 8a-7 lists plus edge cases the reference ops accept
 UPFIRDN_CASES = [
     ("skip_up2", (2, 5, 8, 8), [1, 3, 3, 1], dict(up=2, padding=[2, 1, 2, 1], gain=4)),
