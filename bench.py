@@ -275,8 +275,15 @@ def run_native(args):
         by_tag = {}
         for (tag, a, b, fa, fe, _desc) in recs:
             d = by_tag.setdefault(tag, [0.0, 0.0, 0.0, 0]); d[0] += a.elapsed_time(b); d[1] += fa; d[2] += fe; d[3] += 1
+        traffic, traffic_src = None, None
+        try:      # DRAM bytes of all conv launches of one step from the committed ncu pass (profiles/, same workload); null if absent
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01e_conv_dram_traffic.json")))
+            if (B, R, use_lpips) == (8, 1024, True):
+                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes of one step)", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " bf16_tflops_sustained",
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_src + " bf16_tflops_sustained",
                 "executed_tflops": exe / (tms / 1000.0) / 1e12, "launches_per_step": len(recs) // 2, "kernel_ms_per_step": tms / 2,
                 "share_of_step": (tms / 2) / (ms / K),
                 "by_group": {k: {"ms_per_step": v[0] / 2, "alg_tflops": v[1] / (v[0] / 1000.0) / 1e12, "launches": v[3] // 2} for k, v in by_tag.items()}}

@@ -32,8 +32,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 }
 
 template <bool F16> __device__ __forceinline__ uint32_t pk(float a, float b) {
-  if (F16) { __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f)); return *reinterpret_cast<uint32_t*>(&h); }
-  return pack_bf16(a, b);
+  return F16 ? pack_f16_sat(a, b) : pack_bf16(a, b);
 }
 template <bool F16> __device__ __forceinline__ float2 upk(uint32_t u) {
   if (F16) { __half2 h = *reinterpret_cast<__half2*>(&u); return __half22float2(h); }

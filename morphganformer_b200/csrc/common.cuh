@@ -69,12 +69,14 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 // 16-bit storage with a run-time element type: f16 = IEEE half (forward activations/operands when the library is in fp16-forward
 // mode: same tensor-core rate, 8x finer rounding than bf16), otherwise bfloat16 (always used for gradients: range).
+// fp16 packing saturates to +-65504 in the conversion itself (one F2FP.SATFINITE instead of four clamps + the conversion)
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));     // first source -> upper half
+  return r;
+}
 __device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
-  if (f16) {
-    __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-    return *reinterpret_cast<uint32_t*>(&t);
-  }
-  return pack_bf16(a, b);
+  return f16 ? pack_f16_sat(a, b) : pack_bf16(a, b);
 }
 __device__ __forceinline__ float2 unpack16(uint32_t u, bool f16) {
   if (f16) { __half2 t = *reinterpret_cast<__half2*>(&u); return __half22float2(t); }

@@ -21,7 +21,7 @@ _SCALE = (.458, .448, .450)
 
 
 def _conv_relu(x, w, b, stride=1, padding=0):
-    return bias_act.bias_act(conv2d_gradfix.conv2d(x, w, None, stride=stride, padding=padding), b, act="relu")
+    return bias_act.bias_act(conv2d_gradfix.conv2d(x, w, None, stride=stride, padding=padding), b, act="relu", gain=1)    # bias_act's default relu gain is sqrt(2) (StyleGAN convention); VGG/Alex/Squeeze use plain ReLU
 
 
 class LpipsNet(torch.nn.Module):
