@@ -159,6 +159,13 @@ int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc
                  const float* noise, const float* nstr, const float* bias, float gain, float alpha,
                  void* dX, float* dVM, float* R, int B, int64_t HW, int C, void* stream);
 
+/* ---- mapping network z -> ws and its backward wrt z (mapping.cu): training/networks.py MappingNetwork.forward :894-942 with the
+ * GANformer-default configuration (16 local + 1 global latents x 32, 4 resnet blocks, latent self-attention, positional maps).
+ * params: packed fp32 weights, mgf_mapping_param_floats() floats (layout: mapping.cu; packed by morphganformer_b200.mapping_engine). */
+int mgf_mapping_param_floats(void);
+int mgf_mapping_fwd(const float* z, const float* params, const float* maskbias, float* ws, int B, int num_ws, void* stream);
+int mgf_mapping_bwd(const float* z, const float* params, const float* maskbias, const float* dws, float* dz, int B, int num_ws, void* stream);
+
 /* ---- projection-loss and optimizer kernels (lpips.cu): lpips/networks_basic.py:64-101, lpips/__init__.py:44-46,
  * MSELoss (1024_example_percept_MSE.py:143), Adam + latent noise (:117, :134-135, :153). */
 int mgf_lpips_prep(const float* img, const float* target, void* col, float* mse, int B, int R, void* stream);

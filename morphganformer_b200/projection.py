@@ -5,7 +5,7 @@ statistics :212-216) with the gradient actually flowing through G (the reference
 section 0-4 -- the intended loop is built here, matching oracle/projection.py).  All images of a batch are independent jobs
 (per-image mean MSE, per-image LPIPS), so a batch can be sharded over GPUs with no per-step collective.
 
-One step = mapping network (eager PyTorch, ~0.1 MFLOP/img) -> tcgen05 synthesis engine forward -> LPIPS/MSE forward ->
+One step = mapping network (mgf_mapping_fwd; PyTorch module for non-default mapping configurations) -> tcgen05 synthesis engine forward -> LPIPS/MSE forward ->
 LPIPS/MSE backward -> synthesis backward -> mapping backward -> fused Adam + next-step latent noise (mgf_adam_noise_step).
 No host synchronisation inside a step: the lr / noise schedule lives in a device array indexed by a device step counter.
 """
@@ -30,7 +30,7 @@ def latent_stats(noise_sample):
 class Projector:
     def __init__(self, G, lpips_state_dict, batch, steps, lr=0.1, lamda=0.5, noise=0.05, noise_ramp=0.75, lr_rampdown=0.25,
                  lr_rampup=0.05, weight_decay=1e-4, latent_mean=None, latent_std=None, use_lpips=True, step_noise=None,
-                 noise_seed=3, forward_dtype=None):
+                 noise_seed=3, forward_dtype=None, fused_mapping=True):
         """forward_dtype: None keeps the library's current setting; 'fp16' / 'bf16' select the 16-bit type of the engine's forward
         activations and operands (gradients are always bf16).  fp16 meets the 1e-2 image / 1e-3 loss parity bars; bf16 has the
         fp32 exponent range (use it for checkpoints whose activations may exceed 6.5e4).  Same speed."""
@@ -63,6 +63,9 @@ class Projector:
             step_noise = torch.randn(steps, batch, k, zd, generator=g, device=self.dev)
         self.step_noise = step_noise.to(self.dev, torch.float32).contiguous()
         self.lp = LpipsEngine(lpips_state_dict, self.dev) if use_lpips else None
+        # the mapping network and its backward as two kernels when G has the GANformer-default mapping (else the PyTorch module + autograd)
+        from . import mapping_engine
+        self.mapper = mapping_engine.MappingEngine(G) if (fused_mapping and mapping_engine.supported(G)) else None
         self.mask = torch.ones(batch, k - 1, device=self.dev)
         self.reset()
 
@@ -149,14 +152,20 @@ class Projector:
 
     def _step_eager(self):
         G = self.G
-        z = self.latent_n.detach().requires_grad_(True)
-        with torch.enable_grad():
-            ws = G.mapping(z, None, pos=G.pos, mask=self.mask)
         eng = self._engine()
+        if self.mapper is not None:
+            ws = self.mapper.forward(self.latent_n, self.mask)
+        else:
+            z = self.latent_n.detach().requires_grad_(True)
+            with torch.enable_grad():
+                ws = G.mapping(z, None, pos=G.pos, mask=self.mask)
         img = eng.forward_raw(ws, mask=self.mask, noise_mode="const")
         per_img, dimg = self._loss_and_grad(img)
         dws = eng.backward_raw(dimg)
-        (gz,) = torch.autograd.grad(ws, [z], grad_outputs=[dws])
+        if self.mapper is not None:
+            gz = self.mapper.backward(dws)
+        else:
+            (gz,) = torch.autograd.grad(ws, [z], grad_outputs=[dws])
         # best-so-far bookkeeping (reference: keep latent_n of the lowest-loss step, :155-158)
         better = per_img < self.best_loss
         self.best_loss.copy_(torch.where(better, per_img, self.best_loss))
