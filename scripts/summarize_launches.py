@@ -12,7 +12,8 @@ def ms(r):
     return v / 1e6 if u.startswith('ns') else (v / 1e3 if u.startswith('us') else v)
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows[s:e]:
-    n = re.sub(r'\(.*', '', r['Kernel Name'])
+    n = r['Kernel Name'].replace('<unnamed>::', '').replace('(anonymous namespace)::', '')
+    n = re.sub(r'\(.*', '', n)
     n = re.sub(r'^void ', '', n)
     if 'conv_tc_kernel' in n or 'conv_halo' in n: n = re.sub(r'^.*tc::', '', n)
     else: n = re.sub(r'<.*', '', n); n = n.split('::')[-1] if 'mgf::' in n else 'torch: ' + n[-40:]
@@ -24,4 +25,4 @@ tt = [0, 0.0]
 for n, (c, m) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     if n.startswith('torch:'): tt[0] += c; tt[1] += m; continue
     print("| `%s` | %d | %.3f | %.1f%% |" % (n, c, m, 100 * m / tot))
-print("| PyTorch kernels (mapping network fwd/bwd, bookkeeping) | %d | %.3f | %.1f%% |" % (tt[0], tt[1], 100 * tt[1] / tot))
+print("| PyTorch kernels (buffer fills / copies, loss bookkeeping) | %d | %.3f | %.1f%% |" % (tt[0], tt[1], 100 * tt[1] / tot))
