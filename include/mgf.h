@@ -115,6 +115,9 @@ typedef struct {
   /* rows are pairs of 32-channel pixels viewed as one 64-channel super-pixel (the caller passes block-expanded weights): the
    * noise plane is then [GH, 2*GW] and the two 32-column halves of a row get their own noise value */
   int32_t superpix;
+  /* elements between the noise planes of consecutive samples: 0 = one [OH, OW] plane shared by all samples (noise_mode 'const'),
+   * OH*OW = per-sample planes [NB, OH, OW] (noise_mode 'random', reference networks.py:1015-1017) */
+  int64_t noise_bstride;
 } mgf_conv_tc_desc;
 int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream);
 /* debugging / A-B measurement: 0 disables the halo (shared-memory tap reuse) variant that mgf_conv_tc picks for C = 64/128 3x3 layers */
@@ -145,7 +148,7 @@ int mgf_torgb_fwd(const void* y, const float* wrgb, const float* s, const float*
 int mgf_torgb_bwd(const float* dimg, const void* y, const float* wrgb, const float* s, void* dy, float* ds, float* R,
                   int B, int64_t HW, int C, void* stream);
 int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, const float* noise, const float* nstr, const float* bias,
-                float alpha, float gain, int mode, int B, int64_t HW, int C, void* stream);
+                float alpha, float gain, int mode, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
 int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
 int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
 
@@ -154,10 +157,10 @@ int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int
  * bm [C] are the host-folded constants described in attention.cu.  bwd writes dX, accumulates dVM [B,16,C] and R [B,C]. */
 int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                  const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                 void* out, float* probs, int B, int64_t HW, int C, void* stream);
+                 void* out, float* probs, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
 int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                  const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                 void* dX, float* dVM, float* R, int B, int64_t HW, int C, void* stream);
+                 void* dX, float* dVM, float* R, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
 
 /* ---- mapping network z -> ws and its backward wrt z (mapping.cu): training/networks.py MappingNetwork.forward :894-942 with the
  * GANformer-default configuration (16 local + 1 global latents x 32, 4 resnet blocks, latent self-attention, positional maps).

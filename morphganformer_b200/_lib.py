@@ -36,11 +36,11 @@ SIGNATURES = {
     "mgf_small_gemm": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_torgb_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]),
     "mgf_torgb_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int64, c_int, c_void_p]),
-    "mgf_act_bwd": (c_int, [c_void_p] * 7 + [c_float, c_float, c_int, c_int, c_int64, c_int, c_void_p]),
+    "mgf_act_bwd": (c_int, [c_void_p] * 7 + [c_float, c_float, c_int, c_int, c_int64, c_int, c_int64, c_void_p]),
     "mgf_upfir2_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_upfir2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
-    "mgf_attn_fwd": (c_int, [c_void_p] * 9 + [c_float, c_float, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
-    "mgf_attn_bwd": (c_int, [c_void_p] * 10 + [c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "mgf_attn_fwd": (c_int, [c_void_p] * 9 + [c_float, c_float, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
+    "mgf_attn_bwd": (c_int, [c_void_p] * 10 + [c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
     "mgf_lpips_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mgf_mapping_param_floats": (c_int, []),
     "mgf_mapping_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

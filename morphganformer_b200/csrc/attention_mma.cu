@@ -54,7 +54,7 @@ struct AttnMP {
   const float* noise; const float* nstr; const float* bias; float gain, alpha;
   void* out; float* probs;
   const __nv_bfloat16* dz; __nv_bfloat16* dX; float* dVM; float* R;
-  long long HW; int C; int pix_per_cta;
+  long long HW; int C; int pix_per_cta; long long nbs;      // nbs: elements between per-sample noise planes (0 = shared plane)
 };
 
 // Row-major 16-bit coefficient table [16][C] with a padded row (2C + 64 bytes): the 16-byte reads of a quarter-warp (two rows g,
@@ -64,25 +64,33 @@ __host__ __device__ inline int krow(int C) { return C + 32; }
 // for channel chan(j, m, g) = (j*4 + g/2)*8 + 2m + g%2 (so that output column 2t+e of n-tile m is channel (j*4+t)*8 + 2m + e).
 __device__ __forceinline__ int perm_chan(int nt, int g) { return ((nt >> 2) * 4 + (g >> 1)) * 8 + 2 * (nt & 3) + (g & 1); }
 
+// Table fills are the whole cost of the low-resolution layers (a 4x4 .. 32x32 grid is a handful of warp tiles per CTA): float4 loads,
+// 8-byte shared stores and 4-way unrolling keep many loads in flight instead of one dependent load per iteration.
 template <bool F16>
-__device__ __forceinline__ void fill_rowtable(uint16_t* hi, uint16_t* lo, const float* src, int C) {
-  const int KS = krow(C);
-  for (int i = threadIdx.x; i < NT * C; i += blockDim.x) {
-    const int r = i / C, c = i - r * C;
-    const float v = src[i];
-    const uint16_t h = cv16<F16>(v);
-    hi[r * KS + c] = h;
-    if (lo) lo[r * KS + c] = cv16<F16>(v - cvf<F16>(h));
+__device__ __forceinline__ void fill_rowtable(uint16_t* hi, uint16_t* lo, const float* __restrict__ src, int C) {
+  const int KS = krow(C), C4 = C >> 2;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < NT * C4; i += blockDim.x) {
+    const int r = i / C4, c = (i - r * C4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    const uint16_t h0 = cv16<F16>(v.x), h1 = cv16<F16>(v.y), h2 = cv16<F16>(v.z), h3 = cv16<F16>(v.w);
+    *reinterpret_cast<uint2*>(hi + r * KS + c) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+    if (lo) {
+      const uint16_t l0 = cv16<F16>(v.x - cvf<F16>(h0)), l1 = cv16<F16>(v.y - cvf<F16>(h1)), l2 = cv16<F16>(v.z - cvf<F16>(h2)), l3 = cv16<F16>(v.w - cvf<F16>(h3));
+      *reinterpret_cast<uint2*>(lo + r * KS + c) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+    }
   }
 }
 template <bool F16>
-__device__ __forceinline__ void fill_permtable(uint2* dst, const float* src, int C) {      // src [16][C] fp32
+__device__ __forceinline__ void fill_permtable(uint2* dst, const float* __restrict__ src, int C) {      // src [16][C] fp32
+#pragma unroll 4
   for (int i = threadIdx.x; i < (C / 8) * 32; i += blockDim.x) {
     const int nt = i >> 5, ln = i & 31, g = ln >> 2, t = ln & 3;
     const int ch = perm_chan(nt, g);
+    const float a = __ldg(src + (2 * t) * C + ch), b = __ldg(src + (2 * t + 1) * C + ch), c = __ldg(src + (2 * t + 8) * C + ch), d = __ldg(src + (2 * t + 9) * C + ch);
     uint2 u;
-    u.x = pk<F16>(src[(2 * t) * C + ch], src[(2 * t + 1) * C + ch]);
-    u.y = pk<F16>(src[(2 * t + 8) * C + ch], src[(2 * t + 9) * C + ch]);
+    u.x = pk<F16>(a, b);
+    u.y = pk<F16>(c, d);
     dst[i] = u;
   }
 }
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(AttnMP p) {
       if (v1) { *reinterpret_cast<float2*>(pr1 + 2 * t) = make_float2(P[2], P[3]); *reinterpret_cast<float2*>(pr1 + 8 + 2 * t) = make_float2(P[6], P[7]); }
     }
     const uint32_t pa0 = pk<true>(P[0], P[1]), pa1 = pk<true>(P[2], P[3]), pa2 = pk<true>(P[4], P[5]), pa3 = pk<true>(P[6], P[7]);
-    const float nz0 = p.noise ? p.noise[q0] * ns : 0.f, nz1 = p.noise ? p.noise[q1] * ns : 0.f;
+    const float nz0 = p.noise ? p.noise[b * p.nbs + q0] * ns : 0.f, nz1 = p.noise ? p.noise[b * p.nbs + q1] * ns : 0.f;
     uint4* o0 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + ((long long)b * p.HW + q0) * C);
     uint4* o1 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + ((long long)b * p.HW + q1) * C);
 #pragma unroll
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
     if (active) {
       tile_probs<F16, C32>(x0, x1, sKhi, sKlo, C, g, t, p.Sc + q0 * NT, p.Sc + q1 * NT, mbr, P, rn0, rn1);
       pa0 = pk<true>(P[0], P[1]); pa1 = pk<true>(P[2], P[3]); pa2 = pk<true>(P[4], P[5]); pa3 = pk<true>(P[6], P[7]);
-      if (p.noise) { nz0 = p.noise[q0] * ns; nz1 = p.noise[q1] * ns; }
+      if (p.noise) { nz0 = p.noise[b * p.nbs + q0] * ns; nz1 = p.noise[b * p.nbs + q1] * ns; }
       // probabilities of the tile (bf16) for the dVM phase
       *reinterpret_cast<uint32_t*>(myP + g * SPS + 2 * t) = pack_bf16(P[0], P[1]); *reinterpret_cast<uint32_t*>(myP + g * SPS + 8 + 2 * t) = pack_bf16(P[4], P[5]);
       *reinterpret_cast<uint32_t*>(myP + (g + 8) * SPS + 2 * t) = pack_bf16(P[2], P[3]); *reinterpret_cast<uint32_t*>(myP + (g + 8) * SPS + 8 + 2 * t) = pack_bf16(P[6], P[7]);
@@ -476,12 +484,12 @@ using namespace mgf;
 
 extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                             const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                            void* out, float* probs, int B, int64_t HW, int C, void* stream) {
+                            void* out, float* probs, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
   if (!X || !Kf || !Sc || !maskbias || !VM || !bm || !out) MGF_FAIL(MGF_E_BADARG, "attn_fwd: null tensor");
   if (B <= 0 || HW <= 0) MGF_FAIL(MGF_E_SHAPE, "attn_fwd: empty batch or grid");
   if (int e = check_c(C, "attn_fwd")) return e;
   AttnMP p{}; p.X = X; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm; p.noise = noise; p.nstr = nstr; p.bias = bias;
-  p.gain = gain; p.alpha = alpha; p.out = out; p.probs = probs; p.HW = HW; p.C = C;
+  p.gain = gain; p.alpha = alpha; p.out = out; p.probs = probs; p.HW = HW; p.C = C; p.nbs = noise_bstride;
   p.pix_per_cta = pix_per_cta(HW, B, 2);      // one wave of 2 CTAs per SM
   dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
   const int rc = fwd_f16() ? launch_fwd<true>(p, grid, fwd_smem(C), (cudaStream_t)stream) : launch_fwd<false>(p, grid, fwd_smem(C), (cudaStream_t)stream);
@@ -492,12 +500,12 @@ extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, con
 
 extern "C" int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                             const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                            void* dX, float* dVM, float* R, int B, int64_t HW, int C, void* stream) {
+                            void* dX, float* dVM, float* R, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
   if (!X || !dz || !Kf || !Sc || !maskbias || !VM || !bm || !dX || !dVM) MGF_FAIL(MGF_E_BADARG, "attn_bwd: null tensor");
   if (B <= 0 || HW <= 0) MGF_FAIL(MGF_E_SHAPE, "attn_bwd: empty batch or grid");
   if (int e = check_c(C, "attn_bwd")) return e;
   AttnMP p{}; p.X = X; p.dz = (const __nv_bfloat16*)dz; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm;
-  p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.HW = HW; p.C = C;
+  p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.HW = HW; p.C = C; p.nbs = noise_bstride;
   p.pix_per_cta = pix_per_cta(HW, B, 1);      // one wave of 1 CTA per SM
   dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
   const int rc = fwd_f16() ? launch_bwd<true>(p, grid, bwd_smem(C), (cudaStream_t)stream) : launch_bwd<false>(p, grid, bwd_smem(C), (cudaStream_t)stream);

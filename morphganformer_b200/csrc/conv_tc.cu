@@ -59,6 +59,7 @@ struct alignas(64) Params {
   int total_tiles;
   uint32_t idesc; int out_f16, x_f16, add_f16;
   int tiles_hw;      // halo kernel: tiles per image (tilesW * tilesH)
+  long long noise_bstride;       // elements between per-sample noise planes (0: one plane for all samples)
   int superpix;                  // output rows are PAIRS of pixels (32+32 channels): noise differs between the two 32-column halves
   int x_tma; uint32_t x_bytes;   // X tile arrives by TMA (one 64/32-channel group per tile) instead of per-thread strided loads
 };
@@ -430,11 +431,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       float nz = 0.f, nz1 = 0.f;              // noise value(s) of this thread's pixel, fetched before the accumulator wait
       if (p.noise && valid) {
         if (p.superpix) {                     // row = pixel pair (2x, 2x+1) of a [H, 2*GW] noise plane
-          const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)y * (2 * p.OW) + 2 * x));
+          const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)b * p.noise_bstride + (long long)y * (2 * p.OW) + 2 * x));
           nz = n2.x * nstr; nz1 = n2.y * nstr;
         } else {
           const int ph = t.n0 / p.Cout;
-          nz = __ldg(p.noise + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+          nz = __ldg(p.noise + (long long)b * p.noise_bstride + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
         }
       }
       mbar_wait(&tfull[as], aphase);
@@ -624,11 +625,11 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       float nz = 0.f, nz1 = 0.f;              // noise value(s) of this thread's pixel, fetched before the accumulator wait
       if (p.noise && valid) {
         if (p.superpix) {                     // row = pixel pair (2x, 2x+1) of a [H, 2*GW] noise plane
-          const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)y * (2 * p.OW) + 2 * x));
+          const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)b * p.noise_bstride + (long long)y * (2 * p.OW) + 2 * x));
           nz = n2.x * nstr; nz1 = n2.y * nstr;
         } else {
           const int ph = t.n0 / p.Cout;
-          nz = __ldg(p.noise + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+          nz = __ldg(p.noise + (long long)b * p.noise_bstride + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
         }
       }
       mbar_wait(&tfull[as], aphase);
@@ -816,7 +817,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     p.scale_n = d->scale_n; p.reduce_out = d->reduce_out; p.X = (const __nv_bfloat16*)d->X;
     p.noise = d->noise; p.noise_strength = d->noise_strength; p.bias = d->bias;
     p.act = d->act; p.alpha = d->alpha; p.gain = d->gain; p.add = (const __nv_bfloat16*)d->add;
-    p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain; p.superpix = d->superpix;
+    p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain; p.superpix = d->superpix; p.noise_bstride = d->noise_bstride;
     if ((p.reduce_out || p.actgrad) && !p.X) MGF_FAIL(MGF_E_BADARG, "conv_tc: reduce/actgrad need X");
     const bool f16 = fwd_f16();
     const uint32_t fmt = (f16 && d->ab_fwd) ? 0u : 1u;
@@ -877,7 +878,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   p.scale_n = d->scale_n; p.reduce_out = d->reduce_out; p.X = (const __nv_bfloat16*)d->X;
   p.noise = d->noise; p.noise_strength = d->noise_strength; p.bias = d->bias;
   p.act = d->act; p.alpha = d->alpha; p.gain = d->gain; p.add = (const __nv_bfloat16*)d->add;
-  p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain; p.superpix = d->superpix;
+  p.actgrad = d->actgrad; p.ag_alpha = d->ag_alpha; p.ag_gain = d->ag_gain; p.superpix = d->superpix; p.noise_bstride = d->noise_bstride;
   if (p.superpix && (d->phases != 1 || d->Cout != 64)) MGF_FAIL(MGF_E_UNSUP, "conv_tc: superpix needs phases == 1 and Cout == 64 (two 32-channel pixels)");
   if ((p.reduce_out || p.actgrad) && !p.X) MGF_FAIL(MGF_E_BADARG, "conv_tc: reduce/actgrad need X");
   p.tx_bytes = (uint32_t)((p.rows * BK + BN * BK) * 2);

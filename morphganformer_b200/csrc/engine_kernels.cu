@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* dimg, const
 // R[b,o] += sum_p dy * y with y = lrelu^-1(z/gain) - noise*ns - bias.   One CTA per (pixel chunk, sample); C <= 512.
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, const __nv_bfloat16* z, __nv_bfloat16* dy, float* R,
                                                       const float* noise, const float* nstr, const float* bias,
-                                                      float alpha, float gain, int mode, long long HW, int C, int pix_per_cta, bool zf16) {
+                                                      float alpha, float gain, int mode, long long HW, int C, int pix_per_cta, bool zf16, long long nbs) {
   extern __shared__ float racc[];   // [C]
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < C; i += blockDim.x) racc[i] = 0.f;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, c
       const long long off = ((long long)b * HW + p) * C + cv * 8;
       const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + off));
       const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dz + off));
-      const float nz = noise ? noise[p] * ns : 0.f;
+      const float nz = noise ? noise[b * nbs + p] * ns : 0.f;
       const uint32_t z4[4] = {uz.x, uz.y, uz.z, uz.w}, d4[4] = {ud.x, ud.y, ud.z, ud.w};
       uint32_t o4[4];
 #pragma unroll
@@ -451,7 +451,7 @@ extern "C" int mgf_torgb_bwd(const float* dimg, const void* y, const float* wrgb
 }
 
 extern "C" int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, const float* noise, const float* nstr, const float* bias,
-                           float alpha, float gain, int mode, int B, int64_t HW, int C, void* stream) {
+                           float alpha, float gain, int mode, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
   if (!dz || !z || !R) MGF_FAIL(MGF_E_BADARG, "act_bwd: null tensor");
   if (C % 8 || C > 4096) MGF_FAIL(MGF_E_SHAPE, "act_bwd: C must be a multiple of 8");
   if ((C / 8) < 256 && 256 % (C / 8)) MGF_FAIL(MGF_E_SHAPE, "act_bwd: C/8 must divide 256");
@@ -461,7 +461,7 @@ extern "C" int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, co
   if (ppc < 16) ppc = 16;
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
   act_bwd_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)z, (__nv_bfloat16*)dy, R,
-                                                                        noise, nstr, bias, alpha, gain, mode, HW, C, (int)ppc, fwd_f16());
+                                                                        noise, nstr, bias, alpha, gain, mode, HW, C, (int)ppc, fwd_f16(), (long long)noise_bstride);
   MGF_CHECK_LAUNCH("act_bwd");
   return 0;
 }

@@ -276,7 +276,7 @@ class SynthesisEngine:
             Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape), fwd=True)
             self._modulate(L.Bf, d, L.O, s, Wf, B, True)
             a_in = x_in
-        noise = L.noise if (L.has_noise and noise_on) else None
+        noise, nbs = self._noise_of(L, st, B, H, Wd, draw=True)
         nstr = L.nstr if noise is not None else None
         kw = dict(osy=L.up, osx=L.up, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1))
         if L.attn:
@@ -288,23 +288,37 @@ class SynthesisEngine:
                                            16 * L.O, L.O, B, 16, L.O, comps.shape[2], 0, _s(self.dev)), "mgf_small_gemm")
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             _lib.check(_L().mgf_attn_fwd(_p(y), _p(L.Kf), _p(L.Sc), _p(maskbias), _p(VM), _p(L.bm), _p(noise), _p(nstr), _p(L.bias),
-                                         L.gain, LRELU_ALPHA, _p(z), None, B, H * Wd, L.O, _s(self.dev)), "mgf_attn_fwd")
+                                         L.gain, LRELU_ALPHA, _p(z), None, B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_fwd")
         elif L.superpix:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             bias2 = L.bias.repeat(2).contiguous() if L.bias is not None else None
             tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w // 2), 1, 64, z.view(B, H, Wd // 2, 64), noise=noise, noise_strength=nstr, bias=bias2,
-                       act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, alg_scale=0.5, tag="g.fwd", superpix=True)
+                       act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, alg_scale=0.5, tag="g.fwd", superpix=True, noise_bstride=nbs)
         else:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, z, scale_n=scale_n, noise=noise, noise_strength=nstr, bias=L.bias,
-                       act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, add=add, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
+                       act=1 if L.has_bias else 0, alpha=LRELU_ALPHA, gain=L.gain, add=add, alg_scale=1.0 / L.phases, tag="g.fwd", noise_bstride=nbs, **kw)
         return z
 
     # -------------------------------------------------------------------------------------------- forward
     @torch.no_grad()
+    def _noise_of(self, L, st, B, H, Wd, draw=False):
+        """(noise tensor or None, elements between per-sample planes).  'const': the layer's [H,W] buffer shared by all samples;
+        'random': a fresh randn([B,1,H,W]) per layer and call, drawn in layer order like the reference (networks.py:1015-1017, so the
+        same torch seed gives the same noise as the ops engine), kept in the state for the backward pass."""
+        mode = st["noise_mode"]
+        if not L.has_noise or mode == "none":
+            return None, 0
+        if mode == "const":
+            return L.noise, 0
+        key = f"rnoise{L.idx}"
+        if draw:
+            st[key] = torch.randn([B, 1, H, Wd], device=self.dev)
+        return st[key], H * Wd
+
     def forward_raw(self, ws, mask=None, noise_mode="const"):
-        if noise_mode not in ("const", "none"):
-            raise NotImplementedError("tc engine: noise_mode='random' (per-sample noise planes) is not built; use 'const' or 'none'")
+        if noise_mode not in ("const", "none", "random"):
+            raise ValueError("noise_mode must be 'random', 'const' or 'none'")
         B = ws.shape[0]
         st = self._state(B)
         ws = ws.detach().to(torch.float32).contiguous()
@@ -313,7 +327,8 @@ class SynthesisEngine:
             mask = torch.ones(B, self.k - 1, device=self.dev)
         maskbias = ((1.0 - mask.to(torch.float32)) * -10000.0).contiguous()
         st["maskbias"] = maskbias
-        st["noise_on"] = noise_on = noise_mode == "const"
+        st["noise_mode"] = noise_mode
+        st["noise_on"] = noise_on = noise_mode != "none"
         x = None
         for e in self.blocks:
             r = e["res"]
@@ -387,14 +402,13 @@ class SynthesisEngine:
         """dz: gradient wrt the layer output z.  Returns (dy, R): gradient wrt the conv output and sum_p dy*y."""
         y = st[f"y{L.idx}"]
         H, Wd = y.shape[1], y.shape[2]
-        noise_on = st["noise_on"]
-        noise = L.noise if (L.has_noise and noise_on) else None
+        noise, nbs = self._noise_of(L, st, B, H, Wd)
         nstr = L.nstr if noise is not None else None
         dy = self._buf(st, f"dy{L.idx}", tuple(y.shape))
         dVM = self._buf(st, f"dVM{L.idx}", (B, 16, L.O), torch.float32); dVM.zero_()
         R = self._buf(st, f"R{L.idx}", (B, L.O), torch.float32); R.zero_()
         _lib.check(_L().mgf_attn_bwd(_p(y), _p(dz), _p(L.Kf), _p(L.Sc), _p(st["maskbias"]), _p(st[f"VM{L.idx}"]), _p(L.bm), _p(noise), _p(nstr),
-                                     _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), B, H * Wd, L.O, _s(self.dev)), "mgf_attn_bwd")
+                                     _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_bwd")
         dcomp = dws[:, :-1, L.idx]                                 # [B,16,32] strided, accumulate
         _lib.check(_L().mgf_small_gemm(_p(dVM), 16 * L.O, L.O, _p(L.WVMt), None, _p(dcomp), dcomp.stride(0), dcomp.stride(1),
                                        B, 16, dcomp.shape[2], L.O, 1, _s(self.dev)), "mgf_small_gemm")
@@ -402,13 +416,12 @@ class SynthesisEngine:
 
     def _act_bwd(self, L, dz, z, st, B, mode, want_dy=True):
         H, Wd = z.shape[1], z.shape[2]
-        noise_on = st["noise_on"]
-        noise = L.noise if (L.has_noise and noise_on) else None
+        noise, nbs = self._noise_of(L, st, B, H, Wd)
         nstr = L.nstr if noise is not None else None
         dy = self._buf(st, f"dy{L.idx}", tuple(z.shape)) if want_dy else None
         R = self._buf(st, f"R{L.idx}", (B, L.O), torch.float32); R.zero_()
         _lib.check(_L().mgf_act_bwd(_p(dz), _p(z), _p(dy), _p(R), _p(noise), _p(nstr), _p(L.bias), LRELU_ALPHA, L.gain, mode,
-                                    B, H * Wd, L.O, _s(self.dev)), "mgf_act_bwd")
+                                    B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_act_bwd")
         return dy, R
 
     @torch.no_grad()

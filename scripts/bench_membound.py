@@ -25,8 +25,8 @@ for (H, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
 for (H, C) in [(1024, 32), (512, 64), (256, 128)]:
     z = bf(B, H, H, C); dz = bf(B, H, H, C); dy = torch.empty_like(z); R = torch.zeros(B, C, device="cuda"); noise = torch.randn(H, H, device="cuda"); ns = torch.tensor([0.1], device="cuda"); bias = torch.zeros(C, device="cuda")
     n = z.numel() * 2
-    run("act_bwd mode0 %dx%d C%d" % (H, H, C), lambda: L.mgf_act_bwd(p(dz), p(z), p(dy), p(R), p(noise), p(ns), p(bias), 0.2, 1.0, 0, B, H * H, C, s), 3 * n)
-    run("act_bwd reduce-only %dx%d C%d" % (H, H, C), lambda: L.mgf_act_bwd(p(dz), p(z), None, p(R), p(noise), p(ns), p(bias), 0.2, 1.4, 1, B, H * H, C, s), 2 * n)
+    run("act_bwd mode0 %dx%d C%d" % (H, H, C), lambda: L.mgf_act_bwd(p(dz), p(z), p(dy), p(R), p(noise), p(ns), p(bias), 0.2, 1.0, 0, B, H * H, C, 0, s), 3 * n)
+    run("act_bwd reduce-only %dx%d C%d" % (H, H, C), lambda: L.mgf_act_bwd(p(dz), p(z), None, p(R), p(noise), p(ns), p(bias), 0.2, 1.4, 1, B, H * H, C, 0, s), 2 * n)
     v = bf(B, H // 2, H // 2, C); fk = (ctypes.c_float * 4)(0.125, 0.375, 0.375, 0.125)
     run("upfir2_add -> %dx%d C%d" % (H, H, C), lambda: L.mgf_upfir2_add(p(v), p(z), p(dy), fk, 2.8, B, H // 2, H // 2, C, s), 2.25 * n)
     dv = torch.empty_like(v)

@@ -38,9 +38,9 @@ def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd):
         gain, alpha = 1.4142135, 0.2
         s = torch.cuda.current_stream().cuda_stream
         out = torch.empty_like(X16); probs = torch.empty(B, HW, 16, device="cuda")
-        _lib.check(L.mgf_attn_fwd(_p(X16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(out), _p(probs), B, HW, C, s), "fwd")
+        _lib.check(L.mgf_attn_fwd(_p(X16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(out), _p(probs), B, HW, C, 0, s), "fwd")
         dX = torch.empty(B, HW, C, device="cuda", dtype=torch.bfloat16); dVM = torch.zeros(B, 16, C, device="cuda"); R = torch.zeros(B, C, device="cuda")
-        _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(dX), _p(dVM), _p(R), B, HW, C, s), "bwd")
+        _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(dX), _p(dVM), _p(R), B, HW, C, 0, s), "bwd")
         torch.cuda.synchronize()
         Xr = X16.float().requires_grad_(True); VMr = VM.clone().requires_grad_(True)
         ref, A = _ref(Xr, Kf, Sc, mb, VMr, bm, noise, ns, bias, gain, alpha)
@@ -64,5 +64,5 @@ def test_attn_rejects_bad_shapes():
     L = _lib.lib()
     x = torch.zeros(1, 16, 48, device="cuda", dtype=torch.bfloat16)
     f = torch.zeros(16, 48, device="cuda")
-    rc = L.mgf_attn_fwd(_p(x), _p(f), _p(f), _p(f), _p(f), _p(f), None, None, None, 1.0, 0.2, _p(x), None, 1, 16, 48, 0)
+    rc = L.mgf_attn_fwd(_p(x), _p(f), _p(f), _p(f), _p(f), _p(f), None, None, None, 1.0, 0.2, _p(x), None, 1, 16, 48, 0, 0)
     assert rc != 0 and b"C=48" in L.mgf_last_error()

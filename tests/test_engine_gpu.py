@@ -76,8 +76,38 @@ def test_tc_engine_noise_none_and_mask():
     Gc = G.cuda(); Gc.synthesis.engine = "tc"
     img, _ = Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=mask.cuda(), noise_mode="none")
     assert (img.cpu() - ref).abs().max().item() < TOL["bf16"][0] * max(1.0, ref.abs().max().item())
-    with pytest.raises(NotImplementedError):
-        Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=mask.cuda(), noise_mode="random")
+
+
+def test_tc_engine_noise_random_matches_ops_engine_under_same_seed():
+    """noise_mode='random' (the reference default, networks.py:1010-1017): per-sample randn planes drawn in layer order, so the same
+    torch seed gives the ops engine and the tc engine identical noise; forward within the fp16-forward tolerance, d(ws) direction too."""
+    from morphganformer_b200 import _lib
+    res = 64
+    G = util.build_G(res, 0, 2048, 64).cuda()
+    ws = util.case_tensor((3, 17, G.num_ws, 32), 23).cuda()
+    mask = torch.ones(3, 16, device="cuda")
+    tgt = torch.tanh(util.case_tensor((3, 3, res, res), 24)).cuda()
+    out = {}
+    _lib.set_forward_dtype("fp16")
+    try:
+        for eng in ("ops", "tc"):
+            G.synthesis.engine = eng
+            w = ws.clone().requires_grad_(True)
+            torch.manual_seed(77)
+            img, _ = G.synthesis(w, pos=G.pos, mask=mask, noise_mode="random")
+            g, = torch.autograd.grad((img - tgt).square().mean(), [w])
+            out[eng] = (img.detach(), g)
+        torch.manual_seed(78)
+        G.synthesis.engine = "tc"
+        other, _ = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="random")
+    finally:
+        _lib.set_forward_dtype("bf16")
+    ref, gref = out["ops"]; img, g = out["tc"]
+    rng = max(1.0, ref.abs().max().item())
+    assert (img - ref).abs().max().item() < 1e-2 * rng
+    assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.999
+    assert (other - img).abs().max().item() > 1e-3 * rng          # a different seed really gives different noise
+    assert (img[0] - img[1]).abs().max().item() > 0               # and the planes differ per sample
 
 
 def test_full_size_1024_tc_engine_vs_exact_fp32_ops_engine():
