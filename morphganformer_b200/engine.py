@@ -287,8 +287,12 @@ class SynthesisEngine:
             _lib.check(_L().mgf_small_gemm(_p(comps), comps.stride(0), comps.stride(1), _p(L.WVM), _p(L.bVM), _p(VM),
                                            16 * L.O, L.O, B, 16, L.O, comps.shape[2], 0, _s(self.dev)), "mgf_small_gemm")
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
+            probs = None
+            if st.get("want_probs"):                            # attention maps requested: [B, HW, 16] fp32 per attention layer, in layer order
+                probs = torch.empty(B, H * Wd, 16, device=self.dev)
+                st["probs"].append(probs)
             _lib.check(_L().mgf_attn_fwd(_p(y), _p(L.Kf), _p(L.Sc), _p(maskbias), _p(VM), _p(L.bm), _p(noise), _p(nstr), _p(L.bias),
-                                         L.gain, LRELU_ALPHA, _p(z), None, B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_fwd")
+                                         L.gain, LRELU_ALPHA, _p(z), _p(probs), B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_fwd")
         elif L.superpix:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             bias2 = L.bias.repeat(2).contiguous() if L.bias is not None else None
@@ -316,11 +320,14 @@ class SynthesisEngine:
             st[key] = torch.randn([B, 1, H, Wd], device=self.dev)
         return st[key], H * Wd
 
-    def forward_raw(self, ws, mask=None, noise_mode="const"):
+    def forward_raw(self, ws, mask=None, noise_mode="const", want_probs=False):
+        """want_probs: also keep every attention layer's probabilities [B, HW, 16] (fp32) in self.last_probs (attention maps)."""
         if noise_mode not in ("const", "none", "random"):
             raise ValueError("noise_mode must be 'random', 'const' or 'none'")
         B = ws.shape[0]
         st = self._state(B)
+        st["want_probs"], st["probs"] = bool(want_probs), []
+        self.last_probs = st["probs"]
         ws = ws.detach().to(torch.float32).contiguous()
         st["ws"] = ws
         if mask is None:
@@ -485,20 +492,20 @@ class SynthesisEngine:
         return dws
 
     # -------------------------------------------------------------------------------------------- autograd entry
-    def __call__(self, ws, pos=None, mask=None, noise_mode="const", fused_modconv=None, **_ignored):
-        return _SynthesisFn.apply(ws, self, mask, noise_mode)
+    def __call__(self, ws, pos=None, mask=None, noise_mode="const", fused_modconv=None, want_probs=False, **_ignored):
+        return _SynthesisFn.apply(ws, self, mask, noise_mode, want_probs)
 
 
 class _SynthesisFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ws, eng, mask, noise_mode):
+    def forward(ctx, ws, eng, mask, noise_mode, want_probs):
         ctx.eng = eng
         ctx.B = ws.shape[0]
-        return eng.forward_raw(ws, mask=mask, noise_mode=noise_mode)
+        return eng.forward_raw(ws, mask=mask, noise_mode=noise_mode, want_probs=want_probs)
 
     @staticmethod
     def backward(ctx, dimg):
-        return ctx.eng.backward_raw(dimg), None, None, None
+        return ctx.eng.backward_raw(dimg), None, None, None, None
 
 
 def smoke():

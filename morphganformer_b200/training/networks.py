@@ -512,13 +512,22 @@ class SynthesisNetwork(torch.nn.Module):
             maps.append(a.reshape(-1, heads, self.k - 1, self.img_res, self.img_res))
         return torch.stack(maps, dim=1).permute(0, 3, 1, 2, 4, 5)
 
-    def forward(self, ws, return_att_maps=True, **block_kwargs):
+    def forward(self, ws, return_att_maps=None, **block_kwargs):
+        """return_att_maps: the reference default is True (networks.py:1244).  Left unset (None) it means True on the ops engine and
+        False on the tc engine, where the maps are 738 MB per image at 1024^2 (SURVEY.md 8a-1) -- pass True to get them there too;
+        `torch.zeros([1])` is the reference's own "no maps" value (:1224-1225)."""
         torch_misc.assert_shape(ws, [None, self.k, self.num_ws, self.w_dim])
         if self.engine == "tc":
             from .. import engine as _engine
             if self._tc is None:
                 self._tc = _engine.SynthesisEngine(self)
-            return self._tc(ws, **block_kwargs), torch.zeros([1], device=ws.device)
+            img = self._tc(ws, want_probs=bool(return_att_maps), **block_kwargs)
+            if not return_att_maps:
+                return img, torch.zeros([1], device=ws.device)
+            probs = [p.reshape(p.shape[0], 1, p.shape[1], p.shape[2]) for p in self._tc.last_probs]
+            return img, self.list2tensor(probs, ws.device)
+        if return_att_maps is None:
+            return_att_maps = True
         ws = ws.to(torch.float32)
         block_ws, w_idx = [], 0
         for res in self.block_resolutions:

@@ -138,3 +138,28 @@ def test_full_size_1024_tc_engine_vs_exact_fp32_ops_engine():
     print("1024^2: max-abs %.4g of range %.3g, rel rms %.3g, dws cosine %.6f" % (e.abs().max().item(), rng, (e.square().mean().sqrt() / ref.square().mean().sqrt()).item(), cos))
     assert e.abs().max().item() < 1e-2 * rng
     assert cos > 0.999
+
+
+def test_tc_engine_attention_maps_match_ops_engine():
+    """`G.synthesis(ws, return_att_maps=True)` on the tc engine returns the same [B, 16, layers, 1, R, R] tensor as
+    the ops engine (list2tensor :1222-1242 on the kernel's fp32 probabilities); unset, the tc engine keeps the cheap zeros([1])."""
+    from morphganformer_b200 import _lib
+    res = 64
+    G = util.build_G(res, 0, 2048, 64).cuda()
+    ws = util.case_tensor((2, 17, G.num_ws, 32), 25).cuda()
+    mask = torch.ones(2, 16, device="cuda")
+    G.synthesis.engine = "ops"
+    with torch.no_grad():
+        _, att_ref = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const")
+    _lib.set_forward_dtype("fp16")
+    try:
+        G.synthesis.engine = "tc"
+        with torch.no_grad():
+            _, att = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const", return_att_maps=True)
+            _, none = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const")
+    finally:
+        _lib.set_forward_dtype("bf16")
+    assert tuple(none.shape) == (1,)
+    assert tuple(att.shape) == tuple(att_ref.shape) and att.shape[1] == 16 and att.shape[-1] == res
+    assert (att - att_ref).abs().max().item() < 5e-3
+    assert torch.allclose(att.sum(1), torch.ones_like(att.sum(1)), atol=1e-4)       # probabilities over the 16 latents
