@@ -149,7 +149,7 @@ def run_reference(args):
     value = len(times) / total
     sample = "1 image x 1 Adam step per timed step at %dx%d (same loss, same generator); torch %s CPU fp32" % (res, res, __import__("torch").__version__)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": workload_name(args), "sample_res": res, "sample_batch": 1},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
