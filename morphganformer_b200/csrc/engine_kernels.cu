@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const __nv_bfloat16* y, 
 
 // backward: dy[b,p,o] = sum_c dimg[b,c,p] wrgb[c,o] s[b,o];  ds[b,o] += sum_{p,c} dimg wrgb[c,o] y[b,p,o];  R[b,o] += sum_p dy*y
 // thread = (pixel lane, 8-channel vector); per-CTA shared accumulators, then one global atomic per channel per CTA.
-__global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* dimg, const __nv_bfloat16* y, const float* wrgb, const float* s,
-                                                        __nv_bfloat16* dy, float* ds, float* R, long long HW, int C, int pix_per_cta, bool yf16) {
+template <bool yf16>
+__global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict__ dimg, const __nv_bfloat16* __restrict__ y, const float* __restrict__ wrgb,
+                                                        const float* __restrict__ s, __nv_bfloat16* __restrict__ dy, float* ds, float* R, long long HW, int C, int pix_per_cta) {
   extern __shared__ float sm[];
   float* acc_ds = sm;        // [C]
   float* acc_R = sm + C;     // [C]
@@ -237,9 +238,10 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* dimg, const
 // ---- leaky-ReLU backward with demod-gradient reduction.  z = lrelu(y + noise*ns + bias) * gain (what the conv epilogue stored).
 // dy = dz * gain * (z > 0 ? 1 : alpha)  (mode 0) or dy = dz (mode 1: dz is already the pre-activation gradient);
 // R[b,o] += sum_p dy * y with y = lrelu^-1(z/gain) - noise*ns - bias.   One CTA per (pixel chunk, sample); C <= 512.
-__global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, const __nv_bfloat16* z, __nv_bfloat16* dy, float* R,
-                                                      const float* noise, const float* nstr, const float* bias,
-                                                      float alpha, float gain, int mode, long long HW, int C, int pix_per_cta, bool zf16, long long nbs) {
+template <bool zf16>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ dy, float* R,
+                                                      const float* __restrict__ noise, const float* __restrict__ nstr, const float* __restrict__ bias,
+                                                      float alpha, float gain, int mode, long long HW, int C, int pix_per_cta, long long nbs) {
   extern __shared__ float racc[];   // [C]
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < C; i += blockDim.x) racc[i] = 0.f;
@@ -285,8 +287,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* dz, c
 // out[b,Y,X,c] = add[b,Y,X,c] + g * sum_{fy,fx} fk[fy]*fk[fx] * v[b,(Y+fy-2)/2,(X+fx-2)/2,c]   over taps where the index is even
 // (reference Conv2dLayer.forward :245-250 -> conv2d_resample 1x1-up branch -> upfirdn2d(up=2, pad=[2,1,2,1], gain=4) -> bias_act gain).
 // fk = flipped normalised 1-D taps * 2 (gain 4 split per axis).
-__global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* v, const __nv_bfloat16* add, __nv_bfloat16* out,
-                                                         float4 fk, float g, int h, int w, int C, bool f16, int vshift) {
+template <bool f16>
+__global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ out,
+                                                         float4 fk, float g, int h, int w, int C, int vshift) {
   // grid: x = chunks of one output row (X, channel-vector), y = output row Y, z = sample.  vecs = C/8 = 1 << vshift.
   const int vecs = 1 << vshift;
   const int b = blockIdx.z, Y = blockIdx.y;
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* v,
 }
 
 // adjoint of the above (without the add): dv[b,iy,ix,c] = g * sum_{fy,fx} fk[fy] fk[fx] dout[b, 2iy+2-fy, 2ix+2-fx, c]
-__global__ void __launch_bounds__(256) upfir2_bwd_kernel(const __nv_bfloat16* dout, __nv_bfloat16* dv, float4 fk, float g, int h, int w, int C, int vshift) {
+__global__ void __launch_bounds__(256) upfir2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dv, float4 fk, float g, int h, int w, int C, int vshift) {
   const int vecs = 1 << vshift;
   const int b = blockIdx.z, iy = blockIdx.y;
   const int rowlen = w << vshift;
@@ -445,7 +448,8 @@ extern "C" int mgf_torgb_bwd(const float* dimg, const void* y, const float* wrgb
   long long ppc = (HW * B + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8);
   if (ppc < 16) ppc = 16;
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
-  torgb_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dimg, (const __nv_bfloat16*)y, wrgb, s, (__nv_bfloat16*)dy, ds, R, HW, C, (int)ppc, fwd_f16());
+  if (fwd_f16()) torgb_bwd_kernel<true><<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dimg, (const __nv_bfloat16*)y, wrgb, s, (__nv_bfloat16*)dy, ds, R, HW, C, (int)ppc);
+  else torgb_bwd_kernel<false><<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dimg, (const __nv_bfloat16*)y, wrgb, s, (__nv_bfloat16*)dy, ds, R, HW, C, (int)ppc);
   MGF_CHECK_LAUNCH("torgb_bwd");
   return 0;
 }
@@ -460,8 +464,10 @@ extern "C" int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, co
   long long ppc = (HW * B + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8);
   if (ppc < 16) ppc = 16;
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), B);
-  act_bwd_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)z, (__nv_bfloat16*)dy, R,
-                                                                        noise, nstr, bias, alpha, gain, mode, HW, C, (int)ppc, fwd_f16(), (long long)noise_bstride);
+  if (fwd_f16()) act_bwd_kernel<true><<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)z, (__nv_bfloat16*)dy, R,
+                                                                        noise, nstr, bias, alpha, gain, mode, HW, C, (int)ppc, (long long)noise_bstride);
+  else act_bwd_kernel<false><<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)z, (__nv_bfloat16*)dy, R,
+                                                                        noise, nstr, bias, alpha, gain, mode, HW, C, (int)ppc, (long long)noise_bstride);
   MGF_CHECK_LAUNCH("act_bwd");
   return 0;
 }
@@ -475,8 +481,10 @@ extern "C" int mgf_upfir2_add(const void* v, const void* add, void* out, const f
   if (2 * h > 65535 || B > 65535) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: image too tall");
   const int rowlen = (2 * w) << vs;
   dim3 grid((rowlen + 255) / 256, 2 * h, B);
-  upfir2_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)add, (__nv_bfloat16*)out,
-                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, fwd_f16(), vs);
+  if (fwd_f16()) upfir2_add_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)add, (__nv_bfloat16*)out,
+                                                                                  make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, vs);
+  else upfir2_add_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)add, (__nv_bfloat16*)out,
+                                                                         make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, vs);
   MGF_CHECK_LAUNCH("upfir2_add");
   return 0;
 }

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256) lpips_prep_bwd_kernel(const __nv_bfloat16
   }
 }
 
-__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, int H, int W, int C, bool f16) {
+template <bool f16>
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int H, int W, int C) {
   const int b = blockIdx.y, vecs = C / 8, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)Ho * Wo * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -159,9 +160,9 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* 
 // mode 2: backward, df = coef[b]/HW * (g/(r+eps) - (g.f) f / (r (r+eps)^2)), g = 2 lin (n0 - n1); optional relu mask (df *= f > 0).
 // A group of LPP = min(32, C/8) lanes owns one pixel (VPL = C/(8*LPP) 16-byte vectors per lane, kept in registers), so a warp
 // covers 32/LPP pixels and every lane is busy for all VGG widths (64..512); reductions are xor-shuffles inside the group.
-template <int MODE, int VPL>
-__global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f, const __nv_bfloat16* n1, const float* lin, const float* coef,
-                                                         __nv_bfloat16* outp, float* val, long long HW, int C, int relu_mask, bool f16) {
+template <int MODE, int VPL, bool f16>
+__global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* __restrict__ f, const __nv_bfloat16* __restrict__ n1, const float* __restrict__ lin,
+                                                         const float* __restrict__ coef, __nv_bfloat16* __restrict__ outp, float* val, long long HW, int C, int relu_mask) {
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpp = (C / 8) / VPL;            // lanes per pixel: 8, 16 or 32
   const int ppw = 32 / lpp;                 // pixels per warp
@@ -246,9 +247,10 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* f,
 //   dx = ( route(dy through the 2x2 max-pool) + d(head)/dx ) * (x > 0)
 // replaces lpips_head<2> + maxpool2_bwd for those taps: x and n1 are read once, the head gradient never touches HBM
 // (7 tensor passes -> 3.25).  A group of LPP lanes owns one 2x2 window (4 pixels), channel vectors stay in registers.
-template <int VPL>
-__global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kernel(const __nv_bfloat16* x, const __nv_bfloat16* n1, const float* lin, const float* coef,
-                                                                 const __nv_bfloat16* dy, __nv_bfloat16* dx, int H, int W, int C, bool f16) {
+template <int VPL, bool f16>      // f16: compile-time forward dtype (the run-time flag cost a select per unpacked pair in an issue-bound kernel)
+__global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1,
+                                                                 const float* __restrict__ lin, const float* __restrict__ coef,
+                                                                 const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int H, int W, int C) {
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpp = (C / 8) / VPL, wpw = 32 / lpp;                // lanes per window, windows per warp
   const int sub = lane / lpp, ll = lane % lpp;
@@ -395,7 +397,8 @@ extern "C" int mgf_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int
   if (!x || !y) MGF_FAIL(MGF_E_BADARG, "maxpool2_fwd: null tensor");
   if (C % 8 || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "maxpool2_fwd: C%%8, H%%2, W%%2 must be 0");
   dim3 grid(gridp((long long)(H / 2) * (W / 2) * (C / 8)), B);
-  maxpool2_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C, fwd_f16());
+  if (fwd_f16()) maxpool2_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C);
+  else maxpool2_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, H, W, C);
   MGF_CHECK_LAUNCH("maxpool2_fwd");
   return 0;
 }
@@ -418,7 +421,8 @@ extern "C" int mgf_lpips_head(int mode, const void* f, const void* n1, const flo
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *fp = (const __nv_bfloat16*)f, *np = (const __nv_bfloat16*)n1;
   __nv_bfloat16* op = (__nv_bfloat16*)out;
-#define MGF_HEAD(M, V) lpips_head_kernel<M, V><<<grid, 256, 0, st>>>(fp, np, lin, coef, op, val, HW, C, relu_mask, fwd_f16())
+#define MGF_HEAD(M, V) do { if (fwd_f16()) lpips_head_kernel<M, V, true><<<grid, 256, 0, st>>>(fp, np, lin, coef, op, val, HW, C, relu_mask); \
+                            else lpips_head_kernel<M, V, false><<<grid, 256, 0, st>>>(fp, np, lin, coef, op, val, HW, C, relu_mask); } while (0)
   if (vpl == 1) { if (mode == 0) MGF_HEAD(0, 1); else if (mode == 1) MGF_HEAD(1, 1); else MGF_HEAD(2, 1); }
   else { if (mode == 0) MGF_HEAD(0, 2); else if (mode == 1) MGF_HEAD(1, 2); else MGF_HEAD(2, 2); }
 #undef MGF_HEAD
@@ -434,8 +438,10 @@ extern "C" int mgf_lpips_tap_pool_bwd(const void* x, const void* n1, const float
   long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (vpl == 1) lpips_tap_pool_bwd_kernel<1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, H, W, C, fwd_f16());
-  else lpips_tap_pool_bwd_kernel<2><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, H, W, C, fwd_f16());
+#define MGF_TPB(V, F) lpips_tap_pool_bwd_kernel<V, F><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, H, W, C)
+  if (fwd_f16()) { if (vpl == 1) MGF_TPB(1, true); else MGF_TPB(2, true); }
+  else { if (vpl == 1) MGF_TPB(1, false); else MGF_TPB(2, false); }
+#undef MGF_TPB
   MGF_CHECK_LAUNCH("lpips_tap_pool_bwd");
   return 0;
 }

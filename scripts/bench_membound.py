@@ -3,6 +3,7 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from morphganformer_b200 import _lib
+_lib.set_forward_dtype("fp16")      # the bench mode (16-bit payloads: only the timing matters here)
 L = _lib.lib(); s = torch.cuda.current_stream().cuda_stream
 def p(t): return t.data_ptr() if t is not None else None
 def run(name, fn, nbytes):
