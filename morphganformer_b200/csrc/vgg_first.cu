@@ -56,8 +56,11 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_fwd_kernel(const float* __re
   for (int s = 0; s < 2; s++)
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-      const float* wr = W + perm_chan(nt, g) * 32 + 16 * s + 2 * t;
-      bw[s][nt][0] = pack16(wr[0], wr[1], F16); bw[s][nt][1] = pack16(wr[8], wr[9], F16);
+      // patch columns 27..31 do not exist: their weights are forced to zero here, so the A fragment may hold any finite value there
+      const float* wr = W + perm_chan(nt, g) * 32;
+      const int k0 = 16 * s + 2 * t;
+      bw[s][nt][0] = pack16(k0 < 27 ? wr[k0] : 0.f, k0 + 1 < 27 ? wr[k0 + 1] : 0.f, F16);
+      bw[s][nt][1] = pack16(k0 + 8 < 27 ? wr[k0 + 8] : 0.f, k0 + 9 < 27 ? wr[k0 + 9] : 0.f, F16);
     }
   float bv[2][8];
 #pragma unroll
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_fwd_kernel(const float* __re
   for (int i = 0; i < 8; i++) {
     const int k = 16 * (i >> 2) + 2 * t + 8 * ((i >> 1) & 1) + (i & 1);
     const int tap = k / 3, c = k - tap * 3;
-    koff[i] = (k < 27) ? c * FPL + (tap / 3) * FSW + (tap % 3) : -1;
+    koff[i] = (k < 27) ? c * FPL + (tap / 3) * FSW + (tap % 3) : 0;      // k >= 27: any finite tile value (its weight is zero)
   }
   float mse_local = 0.f;
   int mse_b = -1;
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_fwd_kernel(const float* __re
     const float* p1 = sx + warp * FSW + xl1;
     float v0[8], v1[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { v0[i] = koff[i] >= 0 ? p0[koff[i]] : 0.f; v1[i] = koff[i] >= 0 ? p1[koff[i]] : 0.f; }
+    for (int i = 0; i < 8; i++) { v0[i] = p0[koff[i]]; v1[i] = p1[koff[i]]; }
     uint32_t a[2][4];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
