@@ -243,6 +243,94 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* __
   }
 }
 
+// Fused forward of an LPIPS tap that is followed by a max-pool: val[b] += (1/HW) sum_p sum_c lin_c (f_c/(|f|+eps) - n1_c)^2 over the four
+// pixels of every 2x2 window AND y = max over the window, in one pass over f (the separate head + pool kernels read f twice).
+// Same lane-group-per-window layout as the backward kernel below.
+template <int VPL, bool f16>
+__global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1, const float* __restrict__ lin,
+                                                                 __nv_bfloat16* __restrict__ y, float* val, int H, int W, int C) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lpp = (C / 8) / VPL, wpw = 32 / lpp;
+  const int sub = lane / lpp, ll = lane % lpp;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long nwin = (long long)Ho * Wo, HW = (long long)H * W;
+  const float eps = 1e-10f;
+  float lw[VPL][8];
+#pragma unroll
+  for (int q = 0; q < VPL; q++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) lw[q][e] = lin[(q * lpp + ll) * 8 + e];
+  float vsum = 0.f;
+  for (long long w0 = ((long long)blockIdx.x * 8 + warp) * wpw; w0 < nwin; w0 += (long long)gridDim.x * 8 * wpw) {
+    const long long wi = w0 + sub;
+    const bool ok = wi < nwin;
+    const int xo = (int)((ok ? wi : 0) % Wo), yo = (int)((ok ? wi : 0) / Wo);
+    uint4 xr[4][VPL], nr[4][VPL];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const long long row = (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C;
+#pragma unroll
+      for (int q = 0; q < VPL; q++) {
+        xr[k][q] = __ldg(reinterpret_cast<const uint4*>(x + row) + q * lpp + ll);
+        nr[k][q] = __ldg(reinterpret_cast<const uint4*>(n1 + row) + q * lpp + ll);
+      }
+    }
+    float mx[VPL][8];
+#pragma unroll
+    for (int q = 0; q < VPL; q++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) mx[q][e] = -3.0e38f;
+    float wsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      // pass 1 over the packed registers: |f|^2 and the running max; pass 2: the distance in its direct form (f inv - n1)^2, which
+      // stays accurate when the projection converges and the two terms nearly cancel
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < VPL; q++) {
+        const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 v = unpack16(w4[e], f16);
+          mx[q][e * 2] = fmaxf(mx[q][e * 2], v.x); mx[q][e * 2 + 1] = fmaxf(mx[q][e * 2 + 1], v.y);
+          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss);
+        }
+      }
+      for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = 1.f / (sqrtf(ss) + eps);
+#pragma unroll
+      for (int q = 0; q < VPL; q++) {
+        const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w}, n4[4] = {nr[k][q].x, nr[k][q].y, nr[k][q].z, nr[k][q].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 v = unpack16(w4[e], f16), t = unpack16(n4[e], f16);
+          const float d0 = fmaf(v.x, inv, -t.x), d1 = fmaf(v.y, inv, -t.y);
+          wsum = fmaf(lw[q][e * 2] * d0, d0, wsum); wsum = fmaf(lw[q][e * 2 + 1] * d1, d1, wsum);
+        }
+      }
+    }
+    if (ok) {
+      vsum += wsum;
+#pragma unroll
+      for (int q = 0; q < VPL; q++) {
+        uint4 o;
+        o.x = pack16(mx[q][0], mx[q][1], f16); o.y = pack16(mx[q][2], mx[q][3], f16); o.z = pack16(mx[q][4], mx[q][5], f16); o.w = pack16(mx[q][6], mx[q][7], f16);
+        reinterpret_cast<uint4*>(y + (((long long)b * Ho + yo) * Wo + xo) * C)[q * lpp + ll] = o;
+      }
+    }
+  }
+  vsum = warp_sum(vsum);
+  __shared__ float red[8];
+  if (lane == 0) red[warp] = vsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i];
+    if (t != 0.f) atomicAdd(&val[b], t / (float)HW);
+  }
+}
+
 // Fused backward of an LPIPS tap that is followed by a max-pool (relu1_2, relu2_2, relu3_3, relu4_3):
 //   dx = ( route(dy through the 2x2 max-pool) + d(head)/dx ) * (x > 0)
 // replaces lpips_head<2> + maxpool2_bwd for those taps: x and n1 are read once, the head gradient never touches HBM
@@ -427,6 +515,21 @@ extern "C" int mgf_lpips_head(int mode, const void* f, const void* n1, const flo
   else { if (mode == 0) MGF_HEAD(0, 2); else if (mode == 1) MGF_HEAD(1, 2); else MGF_HEAD(2, 2); }
 #undef MGF_HEAD
   MGF_CHECK_LAUNCH("lpips_head");
+  return 0;
+}
+extern "C" int mgf_lpips_tap_pool_fwd(const void* x, const void* n1, const float* lin, void* y, float* val, int B, int H, int W, int C, void* stream) {
+  if (!x || !n1 || !lin || !y || !val) MGF_FAIL(MGF_E_BADARG, "lpips_tap_pool_fwd: null tensor");
+  if (!(C == 64 || C == 128 || C == 256 || C == 512) || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "lpips_tap_pool_fwd: C in {64,128,256,512}, even H/W");
+  const int vpl = C == 512 ? 2 : 1, lpp = (C / 8) / vpl, wpw = 32 / lpp;
+  const long long nwin = (long long)(H / 2) * (W / 2);
+  long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define MGF_TPF(V, F) lpips_tap_pool_fwd_kernel<V, F><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, (__nv_bfloat16*)y, val, H, W, C)
+  if (fwd_f16()) { if (vpl == 1) MGF_TPF(1, true); else MGF_TPF(2, true); }
+  else { if (vpl == 1) MGF_TPF(1, false); else MGF_TPF(2, false); }
+#undef MGF_TPF
+  MGF_CHECK_LAUNCH("lpips_tap_pool_fwd");
   return 0;
 }
 extern "C" int mgf_lpips_tap_pool_bwd(const void* x, const void* n1, const float* lin, const float* coef, const void* dy, void* dx,

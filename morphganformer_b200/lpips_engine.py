@@ -71,8 +71,10 @@ class LpipsEngine:
             self._st[name] = t
         return t
 
-    def _features(self, img, target, mse, tag):
-        """Runs the VGG trunk; returns the list of conv outputs h[i] (post-ReLU, NHWC bf16) and pooled tensors."""
+    def _features(self, img, target, mse, tag, head_val=None):
+        """Runs the VGG trunk; returns the list of conv outputs h[i] (post-ReLU, NHWC bf16) and pooled tensors.
+        head_val: if given ([B] fp32, zeroed), the LPIPS head of every tap that is followed by a pool (relu1_2 .. relu4_3) is accumulated
+        into it by the fused tap+pool kernel (one pass over the feature map instead of two); the caller adds the last tap."""
         B, _, R, _ = img.shape
         s = _lib.stream_ptr(self.dev)
         # ScalingLayer + conv1_1 + ReLU (+ the MSE sum) in one kernel, straight from the fp32 image (no im2col buffer)
@@ -83,7 +85,12 @@ class LpipsEngine:
         for item in VGG[1:]:
             if item == "P":
                 y = self._buf(f"{tag}p{ci}", (B, res // 2, res // 2, x.shape[3]), fwd=True)
-                _lib.check(_L().mgf_maxpool2_fwd(_p(x), _p(y), B, res, res, x.shape[3], s), "mgf_maxpool2_fwd")
+                if head_val is not None and (ci - 1) in TAP_AFTER:
+                    k = TAP_AFTER[ci - 1]
+                    _lib.check(_L().mgf_lpips_tap_pool_fwd(_p(x), _p(self.n1[k]), _p(self.lin[k]), _p(y), _p(head_val), B, res, res, x.shape[3], s),
+                               "mgf_lpips_tap_pool_fwd")
+                else:
+                    _lib.check(_L().mgf_maxpool2_fwd(_p(x), _p(y), B, res, res, x.shape[3], s), "mgf_maxpool2_fwd")
                 pooled[ci] = y
                 x, res = y, res // 2
                 continue
@@ -131,9 +138,11 @@ class LpipsEngine:
         s = _lib.stream_ptr(self.dev)
         val = self._buf("val", (B,), torch.float32); val.zero_()
         mse = self._buf("mse", (B,), torch.float32); mse.zero_()
-        h, pooled, col = self._features(img, self.target if want_mse else None, mse if want_mse else None, "g")
+        h, pooled, col = self._features(img, self.target if want_mse else None, mse if want_mse else None, "g", head_val=val)
         self.h, self.pooled, self.img = h, pooled, img
         for ci, k in TAP_AFTER.items():
+            if ci != 12:                      # taps followed by a pool were accumulated by the fused tap+pool kernel
+                continue
             f = h[ci]
             _lib.check(_L().mgf_lpips_head(1, _p(f), _p(self.n1[k]), _p(self.lin[k]), None, None, _p(val), 0, B, f.shape[1] * f.shape[2], f.shape[3], s), "mgf_lpips_head")
         return val, mse
