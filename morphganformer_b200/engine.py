@@ -99,6 +99,7 @@ class SynthesisEngine:
         self.Cm = torch.from_numpy(up_phase_matrix()).float()
         self.blocks = []
         self._states = {}
+        self._side = None          # side stream for the per-layer operand preparation (forward_raw)
         self.refresh()
 
     # -------------------------------------------------------------------------------------------- weight folding
@@ -250,31 +251,50 @@ class SynthesisEngine:
             w = e["skip_f"] = e["skip_f32"].to(dt).contiguous()
         return w
 
-    def _layer_fwd(self, L, x_in, ws, maskbias, st, B, noise_on, add=None):
-        """x_in [B,h,w,I] bf16 -> z [B,H,W,O] bf16 (post noise/bias/act)."""
+    def _prep_layer(self, L, ws, st, B):
+        """Everything of a layer that depends only on ws: styles s / demod d, the per-sample modulated forward weights and (attention
+        layers) VM = (Y Wv^T + bv) Wm^T.  forward_raw runs this for ALL layers on a side stream, so these ~60 small latency-bound
+        launches overlap the convolutions instead of sitting between them; the main stream waits on the layer's event."""
         s, d = self._styles(L, ws, st, B)
-        h, w = x_in.shape[1], x_in.shape[2]
-        H, Wd = h * L.up, w * L.up
-        st[f"xin{L.idx}"] = x_in
-        scale_n = None
+        Wf, VM = None, None
         if L.shared_w:
             dt = _lib.forward_torch_dtype()
             if L._Bf16 is None or L._Bf16.dtype != dt:
                 L._Bf16 = L.Bf.unsqueeze(0).to(dt).contiguous()                      # [1, T, NT, I]
             Wf = L._Bf16
-            xs = self._buf(st, f"xs{L.idx}", tuple(x_in.shape), fwd=True)
-            _lib.check(_L().mgf_scale_channels(_p(x_in), _p(s), _p(xs), 1, B, h * w, L.I, _s(self.dev)), "mgf_scale_channels")
-            a_in = xs
-            scale_n = d if L.phases == 1 else d.repeat(1, L.phases).contiguous()      # [B, NT]
         elif L.superpix:
             s2, d2 = s.repeat(1, 2).contiguous(), d.repeat(1, 2).contiguous()
             st[f"s2_{L.idx}"], st[f"d2_{L.idx}"] = s2, d2
             Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape), fwd=True)
             self._modulate(L.Bf, d2, 64, s2, Wf, B, True)
-            a_in = x_in.view(B, h, w // 2, 64)
         else:
             Wf = self._buf(st, f"Wf{L.idx}", (B,) + tuple(L.Bf.shape), fwd=True)
             self._modulate(L.Bf, d, L.O, s, Wf, B, True)
+        if L.attn:
+            VM = self._buf(st, f"VM{L.idx}", (B, 16, L.O), torch.float32)
+            comps = ws[:, :-1, L.idx]                           # [B,16,32] strided
+            _lib.check(_L().mgf_small_gemm(_p(comps), comps.stride(0), comps.stride(1), _p(L.WVM), _p(L.bVM), _p(VM),
+                                           16 * L.O, L.O, B, 16, L.O, comps.shape[2], 0, _s(self.dev)), "mgf_small_gemm")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        st[f"prep{L.idx}"] = (s, d, Wf, VM, ev)
+
+    def _layer_fwd(self, L, x_in, ws, maskbias, st, B, noise_on, add=None):
+        """x_in [B,h,w,I] bf16 -> z [B,H,W,O] bf16 (post noise/bias/act)."""
+        s, d, Wf, VM, ev = st[f"prep{L.idx}"]
+        torch.cuda.current_stream(self.dev).wait_event(ev)
+        h, w = x_in.shape[1], x_in.shape[2]
+        H, Wd = h * L.up, w * L.up
+        st[f"xin{L.idx}"] = x_in
+        scale_n = None
+        if L.shared_w:
+            xs = self._buf(st, f"xs{L.idx}", tuple(x_in.shape), fwd=True)
+            _lib.check(_L().mgf_scale_channels(_p(x_in), _p(s), _p(xs), 1, B, h * w, L.I, _s(self.dev)), "mgf_scale_channels")
+            a_in = xs
+            scale_n = d if L.phases == 1 else d.repeat(1, L.phases).contiguous()      # [B, NT]
+        elif L.superpix:
+            a_in = x_in.view(B, h, w // 2, 64)
+        else:
             a_in = x_in
         noise, nbs = self._noise_of(L, st, B, H, Wd, draw=True)
         nstr = L.nstr if noise is not None else None
@@ -282,10 +302,6 @@ class SynthesisEngine:
         if L.attn:
             y = self._buf(st, f"y{L.idx}", (B, H, Wd, L.O), fwd=True)
             tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, scale_n=scale_n, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
-            VM = self._buf(st, f"VM{L.idx}", (B, 16, L.O), torch.float32)
-            comps = ws[:, :-1, L.idx]                           # [B,16,32] strided
-            _lib.check(_L().mgf_small_gemm(_p(comps), comps.stride(0), comps.stride(1), _p(L.WVM), _p(L.bVM), _p(VM),
-                                           16 * L.O, L.O, B, 16, L.O, comps.shape[2], 0, _s(self.dev)), "mgf_small_gemm")
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             probs = None
             if st.get("want_probs"):                            # attention maps requested: [B, HW, 16] fp32 per attention layer, in layer order
@@ -336,6 +352,16 @@ class SynthesisEngine:
         st["maskbias"] = maskbias
         st["noise_mode"] = noise_mode
         st["noise_on"] = noise_on = noise_mode != "none"
+        # per-layer operands that depend only on ws, for all layers, on the side stream (fork here, per-layer events, join at the end)
+        main = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            for e in self.blocks:
+                for key in ("conv0", "conv1", "conv_last"):
+                    if e.get(key) is not None:
+                        self._prep_layer(e[key], ws, st, B)
         x = None
         for e in self.blocks:
             r = e["res"]
@@ -363,6 +389,7 @@ class SynthesisEngine:
                 img = torch.empty(B, 3, r, r, dtype=torch.float32, device=self.dev)
                 _lib.check(_L().mgf_torgb_fwd(_p(yl), _p(rgb["w"]), _p(srgb), _p(rgb["bias"]), _p(img), B, r * r, rgb["C"], _s(self.dev)), "mgf_torgb_fwd")
                 st["yl"] = yl
+        main.wait_stream(self._side)
         return img
 
     # -------------------------------------------------------------------------------------------- backward
