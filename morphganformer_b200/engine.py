@@ -25,6 +25,8 @@ from . import _lib, tc
 
 SQRT2 = math.sqrt(2.0)
 SQRT_HALF = math.sqrt(0.5)
+import os as _os
+BWD_SIDE_REDUCTIONS = _os.environ.get("MGF_BWD_SIDE", "1") != "0"      # A/B switch: d(style) reductions on the side stream
 LRELU_ALPHA = 0.2
 
 
@@ -403,21 +405,23 @@ class SynthesisEngine:
             _lib.check(_L().mgf_scale_channels(_p(dy), _p(d), _p(dyd), 0, B, dy.shape[1] * dy.shape[2], L.O, _s(self.dev)), "mgf_scale_channels")
             dy, Wb = dyd, L.Bb16
         else:
-            Wb = self._buf(st, f"Wb{L.idx}", (B,) + tuple(L.Bb.shape))
-            self._modulate(L.Bb, None, 1, d, Wb, B, False)
+            Wb, ev = st[f"bprep{L.idx}"]                       # modulated on the side stream at the start of backward_raw
+            torch.cuda.current_stream(self.dev).wait_event(ev)
         x_in = st[f"xin{L.idx}"]
         h, w = x_in.shape[1], x_in.shape[2]
         if L.superpix:
             assert add is None
             s2, d2 = st[f"s2_{L.idx}"], st[f"d2_{L.idx}"]
-            Wb = self._buf(st, f"Wb{L.idx}", (B,) + tuple(L.Bb.shape))
-            self._modulate(L.Bb, None, 1, d2, Wb, B, False)
+            Wb, ev = st[f"bprep{L.idx}"]
+            torch.cuda.current_stream(self.dev).wait_event(ev)
             ds2 = self._buf(st, f"ds2_{L.idx}", (B, 64), torch.float32)
             ds2.zero_()
             tc.conv_tc([dy.view(B, h, w // 2, 64)], Wb, L.taps_b, (B, h, w // 2), 1, 64, out.view(B, h, w // 2, 64), scale_n=s2, reduce_out=ds2,
                        X=x_in.view(B, h, w // 2, 64), actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain,
                        reduce_per_sample=True, alg_scale=0.5, tag="g.bwd", fwd=False)
-            return ds2[:, :32] + ds2[:, 32:]
+            dsum = self._buf(st, f"ds{L.idx}", (B, 32), torch.float32)          # persistent: consumed later on the side stream
+            torch.add(ds2[:, :32], ds2[:, 32:], out=dsum)
+            return dsum
         ds = self._buf(st, f"ds{L.idx}", (B, L.I), torch.float32)
         ds.zero_()
         acts = [dy] if L.up == 1 else [tc.phase_view(dy, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
@@ -426,11 +430,36 @@ class SynthesisEngine:
                    alg_scale=1.0 / L.phases, tag="g.bwd", fwd=False)
         return ds
 
+    def _on_side(self, fn):
+        """Runs fn() on the side stream after everything queued so far on the current stream (small reductions into dws that nothing on
+        the critical path waits for; backward_raw joins the side stream before it returns)."""
+        if not BWD_SIDE_REDUCTIONS:
+            return fn()
+        main = torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            fn()
+
+    def _prep_bwd(self, st, B):
+        """Backward operands that depend only on the forward's demodulation factors: Wb[b] = W * d[b] for every non-shared layer."""
+        for e in self.blocks:
+            for key in ("conv0", "conv1", "conv_last"):
+                L = e.get(key)
+                if L is None or L.shared_w:
+                    continue
+                Wb = self._buf(st, f"Wb{L.idx}", (B,) + tuple(L.Bb.shape))
+                self._modulate(L.Bb, None, 1, st[f"d2_{L.idx}"] if L.superpix else st[f"d{L.idx}"], Wb, B, False)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.dev))
+                st[f"bprep{L.idx}"] = (Wb, ev)
+
     def _style_bwd(self, L, ds, R, st, dws, B):
         d = st[f"d{L.idx}"]; s = st[f"s{L.idx}"]
         dwg = dws[:, -1, L.idx]
-        _lib.check(_L().mgf_style_bwd(_p(ds), _p(R), _p(s), _p(d), _p(L.Wsq), _p(L.A), L.again, 1.0, _p(dwg), dwg.stride(0),
-                                      B, L.I, L.O, dwg.shape[1], _s(self.dev)), "mgf_style_bwd")
+        self._on_side(lambda: _lib.check(_L().mgf_style_bwd(_p(ds), _p(R), _p(s), _p(d), _p(L.Wsq), _p(L.A), L.again, 1.0, _p(dwg), dwg.stride(0),
+                                                            B, L.I, L.O, dwg.shape[1], _s(self.dev)), "mgf_style_bwd"))
 
     def _attn_bwd(self, L, dz, st, dws, B):
         """dz: gradient wrt the layer output z.  Returns (dy, R): gradient wrt the conv output and sum_p dy*y."""
@@ -444,8 +473,8 @@ class SynthesisEngine:
         _lib.check(_L().mgf_attn_bwd(_p(y), _p(dz), _p(L.Kf), _p(L.Sc), _p(st["maskbias"]), _p(st[f"VM{L.idx}"]), _p(L.bm), _p(noise), _p(nstr),
                                      _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_bwd")
         dcomp = dws[:, :-1, L.idx]                                 # [B,16,32] strided, accumulate
-        _lib.check(_L().mgf_small_gemm(_p(dVM), 16 * L.O, L.O, _p(L.WVMt), None, _p(dcomp), dcomp.stride(0), dcomp.stride(1),
-                                       B, 16, dcomp.shape[2], L.O, 1, _s(self.dev)), "mgf_small_gemm")
+        self._on_side(lambda: _lib.check(_L().mgf_small_gemm(_p(dVM), 16 * L.O, L.O, _p(L.WVMt), None, _p(dcomp), dcomp.stride(0), dcomp.stride(1),
+                                                             B, 16, dcomp.shape[2], L.O, 1, _s(self.dev)), "mgf_small_gemm"))
         return dy, R
 
     def _act_bwd(self, L, dz, z, st, B, mode, want_dy=True):
@@ -466,6 +495,12 @@ class SynthesisEngine:
         ws = st["ws"]
         dws = torch.zeros_like(ws)
         dimg = dimg.to(torch.float32).contiguous()
+        main = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self._prep_bwd(st, B)
         g = None
         for e in reversed(self.blocks):
             r = e["res"]
@@ -478,8 +513,8 @@ class SynthesisEngine:
                 _lib.check(_L().mgf_torgb_bwd(_p(dimg), _p(yl), _p(rgb["w"]), _p(st["s_rgb"]), _p(dyl), _p(ds_rgb), _p(R_last),
                                               B, r * r, rgb["C"], _s(self.dev)), "mgf_torgb_bwd")
                 dwg = dws[:, -1, rgb["idx"]]
-                _lib.check(_L().mgf_style_bwd(_p(ds_rgb), None, None, None, None, _p(rgb["A"]), rgb["again"], rgb["sgain"], _p(dwg), dwg.stride(0),
-                                              B, rgb["C"], 0, dwg.shape[1], _s(self.dev)), "mgf_style_bwd")
+                self._on_side(lambda: _lib.check(_L().mgf_style_bwd(_p(ds_rgb), None, None, None, None, _p(rgb["A"]), rgb["again"], rgb["sgain"], _p(dwg),
+                                                                    dwg.stride(0), B, rgb["C"], 0, dwg.shape[1], _s(self.dev)), "mgf_style_bwd"))
                 g = self._buf(st, f"g{r}", tuple(st[f"xin{Ll.idx}"].shape))
                 ds = self._dgrad(Ll, dyl, st, B, g)
                 self._style_bwd(Ll, ds, R_last, st, dws, B)
@@ -516,6 +551,7 @@ class SynthesisEngine:
             ds0 = self._dgrad(L0, dy0, st, B, gprev, add=gs)
             self._style_bwd(L0, ds0, R0, st, dws, B)
             g = gprev
+        main.wait_stream(self._side)
         return dws
 
     # -------------------------------------------------------------------------------------------- autograd entry
