@@ -482,9 +482,16 @@ class SynthesisEngine:
         noise, nbs = self._noise_of(L, st, B, H, Wd)
         nstr = L.nstr if noise is not None else None
         dy = self._buf(st, f"dy{L.idx}", tuple(z.shape)) if want_dy else None
-        R = self._buf(st, f"R{L.idx}", (B, L.O), torch.float32); R.zero_()
-        _lib.check(_L().mgf_act_bwd(_p(dz), _p(z), _p(dy), _p(R), _p(noise), _p(nstr), _p(L.bias), LRELU_ALPHA, L.gain, mode,
-                                    B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_act_bwd")
+        R = self._buf(st, f"R{L.idx}", (B, L.O), torch.float32)
+
+        def run():
+            R.zero_()
+            _lib.check(_L().mgf_act_bwd(_p(dz), _p(z), _p(dy), _p(R), _p(noise), _p(nstr), _p(L.bias), LRELU_ALPHA, L.gain, mode,
+                                        B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_act_bwd")
+        if want_dy:
+            run()
+        else:             # reduce-only pass (R feeds only the d(style) reduction, which already lives on the side stream): off the critical path
+            self._on_side(run)
         return dy, R
 
     @torch.no_grad()
@@ -530,9 +537,10 @@ class SynthesisEngine:
             h = x_in.shape[1]
             # skip branch: d v = FIR^T(g) ; d x_in (skip part) = conv1x1^T
             dv = self._buf(st, f"dv{r}", (B, h, h, L0.O))
-            _lib.check(_L().mgf_upfir2_bwd(_p(g), _p(dv), e["fk4"], e["skip_gain"], B, h, h, L0.O, _s(self.dev)), "mgf_upfir2_bwd")
+            g_blk, fk4, sg = g, e["fk4"], e["skip_gain"]
+            self._on_side(lambda: _lib.check(_L().mgf_upfir2_bwd(_p(g_blk), _p(dv), fk4, sg, B, h, h, L0.O, _s(self.dev)), "mgf_upfir2_bwd"))
+            ev_dv = torch.cuda.Event(); ev_dv.record(self._side if BWD_SIDE_REDUCTIONS else main)
             gs = self._buf(st, f"gs{r}", tuple(x_in.shape))
-            tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd", fwd=False)
             # conv1
             z0 = st[f"z{L0.idx}"]
             dy1, R1 = self._attn_bwd(L1, g, st, dws, B) if L1.attn else self._act_bwd(L1, g, st[f"z{L1.idx}"], st, B, 0)
@@ -548,6 +556,8 @@ class SynthesisEngine:
             self._style_bwd(L1, ds1, R1, st, dws, B)
             # conv0 (up) dgrad, adding the skip-branch gradient in the epilogue -> gradient wrt the previous block's output
             gprev = self._buf(st, f"g{r // 2}", tuple(x_in.shape))
+            main.wait_event(ev_dv)                             # the FIR adjoint of the skip branch ran beside conv1's backward
+            tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd", fwd=False)
             ds0 = self._dgrad(L0, dy0, st, B, gprev, add=gs)
             self._style_bwd(L0, ds0, R0, st, dws, B)
             g = gprev
