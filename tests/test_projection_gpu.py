@@ -97,3 +97,24 @@ def test_cuda_graph_replay_equals_eager():
     np.testing.assert_allclose(out[1][0].numpy(), out[0][0].numpy(), rtol=2e-3)     # float atomics reorder between runs
     assert (out[1][1] - out[0][1]).abs().max() < 2e-2
     np.testing.assert_allclose(out[1][2].numpy(), out[0][2].numpy(), rtol=2e-3)
+
+
+def test_fused_mapping_equals_pytorch_mapping_path():
+    """The projection step with the mapping network on mgf_mapping_fwd/bwd equals the step that keeps the PyTorch module + autograd."""
+    from morphganformer_b200.projection import Projector, latent_stats
+    res, cb, cm, B, steps = 64, 2048, 64, 2, 4
+    lsd = util.build_vgg_lpips_sd(4)
+    mean, std = latent_stats(util.case_tensor((2000, 17, 32), 70))
+    noise = util.case_tensor((20, B, 17, 32), 71)
+    tgt = torch.tanh(util.case_tensor((B, 3, res, res), 73))
+    out = []
+    for fused in (True, False):
+        G = util.build_G(res, 0, cb, cm).cuda()
+        P = Projector(G, lsd, B, 20, latent_mean=mean, latent_std=std, step_noise=noise, fused_mapping=fused)
+        assert (P.mapper is not None) == fused
+        P.set_targets(tgt)
+        P.run(steps)
+        torch.cuda.synchronize()
+        out.append((P.losses[:steps].cpu(), P.latent.cpu()))
+    np.testing.assert_allclose(out[0][0].numpy(), out[1][0].numpy(), rtol=2e-3)
+    assert (out[0][1] - out[1][1]).abs().max() < 2e-2
