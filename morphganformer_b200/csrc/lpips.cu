@@ -418,11 +418,14 @@ __global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kern
       for (int k = 0; k < 4; k++) {
         const uint32_t n4[4] = {nr[k][q].x, nr[k][q].y, nr[k][q].z, nr[k][q].w};
         float o[8];
+        // head gradient h = cf (2 lin (x inv - t) inv - k2 x) = x * (ca lin - ck) - t * (cb lin): two FMAs per element
+        const float ca = 2.f * cf * inv[k] * inv[k], cb = 2.f * cf * inv[k], ck = cf * k2[k];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const float2 t = unpack16(n4[e], f16);
-          const float h0 = cf * (2.f * lw[q][e * 2] * (xv[k][e * 2] * inv[k] - t.x) * inv[k] - k2[k] * xv[k][e * 2]);
-          const float h1 = cf * (2.f * lw[q][e * 2 + 1] * (xv[k][e * 2 + 1] * inv[k] - t.y) * inv[k] - k2[k] * xv[k][e * 2 + 1]);
+          const float l0 = lw[q][e * 2], l1 = lw[q][e * 2 + 1];
+          const float h0 = fmaf(xv[k][e * 2], fmaf(ca, l0, -ck), -(cb * l0) * t.x);
+          const float h1 = fmaf(xv[k][e * 2 + 1], fmaf(ca, l1, -ck), -(cb * l1) * t.y);
           const float v0 = ((arg[e * 2] == k) ? g[e * 2] : 0.f) + h0, v1 = ((arg[e * 2 + 1] == k) ? g[e * 2 + 1] : 0.f) + h1;
           o[e * 2] = xv[k][e * 2] > 0.f ? v0 : 0.f; o[e * 2 + 1] = xv[k][e * 2 + 1] > 0.f ? v1 : 0.f;
         }
