@@ -436,7 +436,9 @@ extern "C" int mgf_torgb_fwd(const void* y, const float* wrgb, const float* s, c
   if (C == 32) torgb_fwd_kernel<32><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, fwd_f16());
   else if (C == 64) torgb_fwd_kernel<64><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, fwd_f16());
   else if (C == 128) torgb_fwd_kernel<128><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, fwd_f16());
-  else MGF_FAIL(MGF_E_UNSUP, "torgb_fwd: C=%d not in {32,64,128}", C);
+  else if (C == 256) torgb_fwd_kernel<256><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, fwd_f16());   // 64^2 .. 128^2 generators
+  else if (C == 512) torgb_fwd_kernel<512><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, wrgb, s, bias, img, HW, fwd_f16());
+  else MGF_FAIL(MGF_E_UNSUP, "torgb_fwd: C=%d not in {32,64,128,256,512}", C);
   MGF_CHECK_LAUNCH("torgb_fwd");
   return 0;
 }

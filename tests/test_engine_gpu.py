@@ -163,3 +163,29 @@ def test_tc_engine_attention_maps_match_ops_engine():
     assert tuple(att.shape) == tuple(att_ref.shape) and att.shape[1] == 16 and att.shape[-1] == res
     assert (att - att_ref).abs().max().item() < 5e-3
     assert torch.allclose(att.sum(1), torch.ones_like(att.sum(1)), atol=1e-4)       # probabilities over the 16 latents
+
+
+@pytest.mark.parametrize("res,B,cb,cm", [(128, 3, 32768, 512), (64, 2, 32768, 512), (512, 1, 32768, 512), (256, 5, 8192, 128), (32, 1, 1024, 32)])
+def test_tc_engine_other_resolutions_and_batches(res, B, cb, cm):
+    """Shapes besides the bench's (odd batches, every block count, the GANformer-default and narrower channel tables): tc engine
+    (fp16-forward) vs the exact-fp32 ops engine on the same GPU, image within 1e-2 of the range and d(ws) direction."""
+    from morphganformer_b200 import _lib
+    G = util.build_G(res, 0, cb, cm).cuda()
+    ws = util.case_tensor((B, 17, G.num_ws, 32), 30 + res).cuda()
+    mask = torch.ones(B, 16, device="cuda")
+    tgt = torch.tanh(util.case_tensor((B, 3, res, res), 31 + res)).cuda()
+    out = {}
+    _lib.set_forward_dtype("fp16")
+    try:
+        for eng in ("ops", "tc"):
+            G.synthesis.engine = eng
+            w = ws.clone().requires_grad_(True)
+            img, _ = G.synthesis(w, pos=G.pos, mask=mask, noise_mode="const", return_att_maps=False)
+            g, = torch.autograd.grad((img - tgt).square().mean(), [w])
+            out[eng] = (img.detach(), g)
+    finally:
+        _lib.set_forward_dtype("bf16")
+    ref, gref = out["ops"]; img, g = out["tc"]
+    rng = max(1.0, ref.abs().max().item())
+    assert (img - ref).abs().max().item() < 1e-2 * rng
+    assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.998
