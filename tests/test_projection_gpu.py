@@ -118,3 +118,28 @@ def test_fused_mapping_equals_pytorch_mapping_path():
         out.append((P.losses[:steps].cpu(), P.latent.cpu()))
     np.testing.assert_allclose(out[0][0].numpy(), out[1][0].numpy(), rtol=2e-3)
     assert (out[0][1] - out[1][1]).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("res,B,cb,cm", [(32, 1, 1024, 32), (128, 3, 32768, 512)])
+def test_projection_first_steps_other_resolutions(res, B, cb, cm):
+    """Projection (MSE + LPIPS-VGG) at the smallest supported resolution and at a default-channel 128^2 generator with an odd batch:
+    the first two per-step losses against the oracle loop (fp16-forward engine)."""
+    from morphganformer_b200.projection import Projector, latent_stats
+    from morphganformer_b200 import _lib
+    steps = 2
+    G = util.build_G(res, 0, cb, cm)
+    gsd, lsd = util.state_dict_cpu(G), util.build_vgg_lpips_sd(4)
+    mean, std = latent_stats(util.case_tensor((2000, 17, 32), 70))
+    noise = util.case_tensor((steps, B, 17, 32), 71)
+    with torch.no_grad():
+        tgt = torch.tanh(ganformer.generator(gsd, util.case_tensor((B, 17, 32), 72), res)[0])
+    ref = oproj.project(gsd, lsd, tgt, mean, std, noise, res, steps, total_steps=50)
+    try:
+        P = Projector(G.cuda(), lsd, B, 50, latent_mean=mean, latent_std=std, forward_dtype="fp16",
+                      step_noise=torch.cat([noise, torch.zeros(48, B, 17, 32)]))
+        P.set_targets(tgt)
+        P.run(steps)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_forward_dtype("bf16")
+    np.testing.assert_allclose(P.losses[:steps].cpu().numpy(), ref["losses"].numpy(), rtol=3e-3)
