@@ -1,4 +1,4 @@
-"""LPIPS with the AlexNet and SqueezeNet-1.1 backbones on the exact-fp32 ops path.
+"""LPIPS with the AlexNet and SqueezeNet-1.1 backbones, and VGG16 in exact fp32, on the ops path.
 
 Mirrors lpips.PerceptualLoss(model='net-lin', net='alex' | 'squeeze') of the reference (lpips/__init__.py:13-41 ->
 networks_basic.py:27-92; backbones pretrained_networks.py:6-95; linear heads weights/v0.1/{alex,squeeze}.pth) and the optional
@@ -15,7 +15,9 @@ import torch.nn.functional as F
 
 from .torch_utils.ops import bias_act, conv2d_gradfix
 
-CHNS = {"alex": [64, 192, 384, 256, 256], "squeeze": [64, 128, 256, 384, 384, 512, 512]}
+CHNS = {"alex": [64, 192, 384, 256, 256], "squeeze": [64, 128, 256, 384, 384, 512, 512], "vgg": [64, 128, 256, 512, 512]}
+# VGG16 conv indices per slice (torchvision features numbering, reference pretrained_networks.py:108-117); a 2x2 max-pool opens slices 2..5
+_VGG_SLICES = [(1, (0, 2)), (2, (5, 7)), (3, (10, 12, 14)), (4, (17, 19, 21)), (5, (24, 26, 28))]
 _SHIFT = (-.030, -.088, -.188)
 _SCALE = (.458, .448, .450)
 
@@ -30,7 +32,7 @@ class LpipsNet(torch.nn.Module):
         downsample_to: if set (e.g. 256), inputs larger than that are box-averaged by the integer factor first."""
         super().__init__()
         if net not in CHNS:
-            raise NotImplementedError("net must be 'alex' or 'squeeze' (VGG16 is lpips_engine.PerceptualLoss)")
+            raise NotImplementedError("net must be 'alex', 'squeeze' or 'vgg'")
         self.net_type, self.downsample_to = net, downsample_to
         for k, v in state_dict.items():
             if k.startswith("net.") or k.startswith("lin"):
@@ -52,6 +54,15 @@ class LpipsNet(torch.nn.Module):
         return torch.cat([a, b], 1)
 
     def features(self, x):
+        if self.net_type == "vgg":                        # exact-fp32 VGG16 trunk (the tuned 16-bit tcgen05 path is lpips_engine.LpipsEngine)
+            feats, h = [], x
+            for s, idxs in _VGG_SLICES:
+                if s > 1:
+                    h = F.max_pool2d(h, 2, 2)
+                for i in idxs:
+                    h = self._cv(h, s, i, padding=1)
+                feats.append(h)
+            return feats
         if self.net_type == "alex":                       # torchvision alexnet.features[0:12]
             f1 = self._cv(x, 1, 0, stride=4, padding=2)
             f2 = self._cv(F.max_pool2d(f1, 3, 2), 2, 3, padding=2)
@@ -92,7 +103,7 @@ def PerceptualLoss(state_dict, model="net-lin", net="vgg", **kw):
     """Factory with the reference's call shape (lpips/__init__.py:13-24): VGG16 -> the tcgen05 engine, alex / squeeze -> LpipsNet."""
     if model != "net-lin":
         raise NotImplementedError("only model='net-lin' (the LPIPS linear-head variant) is built")
-    if net in ("vgg", "vgg16"):
+    if net in ("vgg", "vgg16") and not kw.get("exact_fp32"):
         from .lpips_engine import PerceptualLoss as _Vgg
         return _Vgg(state_dict, model=model, net=net)
-    return LpipsNet(state_dict, net=net, downsample_to=kw.get("downsample_to"))
+    return LpipsNet(state_dict, net="vgg" if net == "vgg16" else net, downsample_to=kw.get("downsample_to"))

@@ -30,17 +30,20 @@ def latent_stats(noise_sample):
 class Projector:
     def __init__(self, G, lpips_state_dict, batch, steps, lr=0.1, lamda=0.5, noise=0.05, noise_ramp=0.75, lr_rampdown=0.25,
                  lr_rampup=0.05, weight_decay=1e-4, latent_mean=None, latent_std=None, use_lpips=True, step_noise=None,
-                 noise_seed=3, forward_dtype=None, fused_mapping=True):
+                 noise_seed=3, forward_dtype=None, fused_mapping=True, engine="tc"):
         """forward_dtype: None keeps the library's current setting; 'fp16' / 'bf16' select the 16-bit type of the engine's forward
         activations and operands (gradients are always bf16).  fp16 meets the 1e-2 image / 1e-3 loss parity bars; bf16 has the
         fp32 exponent range (use it for checkpoints whose activations may exceed 6.5e4).  Same speed."""
         if forward_dtype is not None:
             _lib.set_forward_dtype(forward_dtype)
+        if engine not in ("tc", "ops"):
+            raise ValueError("engine must be 'tc' (16-bit tcgen05 engine, the throughput path) or 'ops' (exact fp32 kernels + autograd)")
+        self.engine = engine
         self.G = G
         self.dev = next(G.parameters()).device
         if self.dev.type != "cuda":
             raise _lib.MgfError("Projector needs the generator on a CUDA device (no CPU fallback)")
-        G.synthesis.engine = "tc"
+        G.synthesis.engine = engine
         G.eval().requires_grad_(False)
         self.B, self.steps, self.lamda, self.use_lpips = batch, steps, float(lamda), use_lpips
         self.wd = float(weight_decay)
@@ -62,10 +65,14 @@ class Projector:
             g = torch.Generator(device=self.dev).manual_seed(noise_seed)
             step_noise = torch.randn(steps, batch, k, zd, generator=g, device=self.dev)
         self.step_noise = step_noise.to(self.dev, torch.float32).contiguous()
-        self.lp = LpipsEngine(lpips_state_dict, self.dev) if use_lpips else None
+        self.lp = LpipsEngine(lpips_state_dict, self.dev) if (use_lpips and engine == "tc") else None
+        self.lp32 = None
+        if use_lpips and engine == "ops":          # exact-fp32 LPIPS-VGG16 on the ops kernels (autograd)
+            from .lpips_nets import LpipsNet
+            self.lp32 = LpipsNet(lpips_state_dict, "vgg").to(self.dev)
         # the mapping network and its backward as two kernels when G has the GANformer-default mapping (else the PyTorch module + autograd)
         from . import mapping_engine
-        self.mapper = mapping_engine.MappingEngine(G) if (fused_mapping and mapping_engine.supported(G)) else None
+        self.mapper = mapping_engine.MappingEngine(G) if (fused_mapping and engine == "tc" and mapping_engine.supported(G)) else None
         self.mask = torch.ones(batch, k - 1, device=self.dev)
         self.reset()
 
@@ -150,7 +157,23 @@ class Projector:
         self.graph = g
         return g
 
+    def _step_ops(self):
+        """The same step on the exact-fp32 path: ops-engine synthesis + fp32 LPIPS, gradients by autograd (parity reference on the GPU:
+        slow, bit-for-bit the oracle's arithmetic up to summation order)."""
+        G = self.G
+        z = self.latent_n.detach().requires_grad_(True)
+        with torch.enable_grad():
+            img = G(z, noise_mode="const")[0]
+            per_img = (img - self.target).square().mean(dim=[1, 2, 3])
+            if self.use_lpips:
+                per_img = self.lamda * self.lp32(img, self.target).reshape(-1) + (1 - self.lamda) * per_img
+            (gz,) = torch.autograd.grad(per_img.sum(), [z])
+        return per_img.detach(), gz, img.detach()
+
     def _step_eager(self):
+        if self.engine == "ops":
+            per_img, gz, img = self._step_ops()
+            return self._finish_step(per_img, gz, img)
         G = self.G
         eng = self._engine()
         if self.mapper is not None:
@@ -166,6 +189,9 @@ class Projector:
             gz = self.mapper.backward(dws)
         else:
             (gz,) = torch.autograd.grad(ws, [z], grad_outputs=[dws])
+        return self._finish_step(per_img, gz, img)
+
+    def _finish_step(self, per_img, gz, img):
         # best-so-far bookkeeping (reference: keep latent_n of the lowest-loss step, :155-158)
         better = per_img < self.best_loss
         self.best_loss.copy_(torch.where(better, per_img, self.best_loss))
