@@ -292,6 +292,27 @@ def run_native(args):
                 "share_of_step": (tms / 2) / (ms / K),
                 "by_group": {k: {"ms_per_step": v[0] / 2, "alg_tflops": v[1] / (v[0] / 1000.0) / 1e12, "launches": v[3] // 2} for k, v in by_tag.items()}}
 
+    # ---- second half of BASELINE.json's metric: generator images/sec (synthesis forward, and forward + backward wrt ws), same engine / batch
+    aux = None
+    if rank == 0:
+        eng = P._engine()
+        with torch.no_grad():
+            ws_b = P.mapper.forward(P.latent_n, P.mask) if P.mapper is not None else G.mapping(P.latent_n, None, pos=G.pos, mask=P.mask)
+        dimg_b = torch.randn(B, 3, R, R, device=dev) * 1e-3
+        def timed(fn, n=10):
+            for _ in range(3):
+                fn()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record()
+            for _ in range(n):
+                fn()
+            b_.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b_) / n
+        t_f = timed(lambda: eng.forward_raw(ws_b, mask=P.mask, noise_mode="const"))
+        t_fb = timed(lambda: (eng.forward_raw(ws_b, mask=P.mask, noise_mode="const"), eng.backward_raw(dimg_b)))
+        aux = {"generator_forward_images_per_sec": B / (t_f / 1000.0), "generator_forward_backward_images_per_sec": B / (t_fb / 1000.0),
+               "batch": B, "resolution": R, "note": "G.synthesis on the tcgen05 engine, eager launches (no graph), CUDA events, 10 iterations"}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
@@ -310,7 +331,7 @@ def run_native(args):
                        "loss": "0.5*LPIPS_vgg16 + 0.5*MSE" if use_lpips else "MSE", "optimizer": "Adam(lr 0.1 schedule, wd 1e-4) on z [B,17,32]",
                        "parallelism": "image-sharded x%d, no per-step collective" % world, "cuda_graph": P.graph is not None,
                        "l2": "inputs_exceed_l2 (per-layer activations at 1024^2 x 8 images are 0.27-1.07 GB)", "weights": "random-init seed 0"},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "loss_mean_last_step": loss_now,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "loss_mean_last_step": loss_now, "aux": aux,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
