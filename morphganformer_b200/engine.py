@@ -226,6 +226,25 @@ class SynthesisEngine:
             st[name] = t
         return t
 
+    def _zbuf(self, st, name, shape):
+        """fp32 reduction target (d(style), R, dVM, ...) carved out of one per-state arena that backward_raw clears with a single fill
+        at its start, instead of ~50 separate fill launches per step.  Offsets are assigned on first use and never change."""
+        key = "z:" + name
+        t = st.get(key)
+        if t is None:
+            n = 1
+            for s in shape:
+                n *= int(s)
+            off = st.get("zpool_used", 0)
+            pool = st.get("zpool")
+            if pool is None:
+                pool = st["zpool"] = torch.zeros(1 << 20, dtype=torch.float32, device=self.dev)      # 4 MB: ~20x what a 1024^2 generator needs at B = 8
+            if off + n > pool.numel():
+                raise _lib.MgfError("engine: reduction arena exhausted (%d + %d floats)" % (off, n))
+            t = st[key] = pool[off:off + n].view(*shape)
+            st["zpool_used"] = off + ((n + 63) // 64) * 64
+        return t
+
     def _state(self, B):
         st = self._states.get(B)
         if st is None:
@@ -414,16 +433,14 @@ class SynthesisEngine:
             s2, d2 = st[f"s2_{L.idx}"], st[f"d2_{L.idx}"]
             Wb, ev = st[f"bprep{L.idx}"]
             torch.cuda.current_stream(self.dev).wait_event(ev)
-            ds2 = self._buf(st, f"ds2_{L.idx}", (B, 64), torch.float32)
-            ds2.zero_()
+            ds2 = self._zbuf(st, f"ds2_{L.idx}", (B, 64))
             tc.conv_tc([dy.view(B, h, w // 2, 64)], Wb, L.taps_b, (B, h, w // 2), 1, 64, out.view(B, h, w // 2, 64), scale_n=s2, reduce_out=ds2,
                        X=x_in.view(B, h, w // 2, 64), actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain,
                        reduce_per_sample=True, alg_scale=0.5, tag="g.bwd", fwd=False)
             dsum = self._buf(st, f"ds{L.idx}", (B, 32), torch.float32)          # persistent: consumed later on the side stream
             torch.add(ds2[:, :32], ds2[:, 32:], out=dsum)
             return dsum
-        ds = self._buf(st, f"ds{L.idx}", (B, L.I), torch.float32)
-        ds.zero_()
+        ds = self._zbuf(st, f"ds{L.idx}", (B, L.I))
         acts = [dy] if L.up == 1 else [tc.phase_view(dy, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
         tc.conv_tc(acts, Wb, L.taps_b, (B, h, w), 1, L.I, out, scale_n=s, reduce_out=ds, X=x_in, add=add,
                    actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain, reduce_per_sample=True,
@@ -468,8 +485,8 @@ class SynthesisEngine:
         noise, nbs = self._noise_of(L, st, B, H, Wd)
         nstr = L.nstr if noise is not None else None
         dy = self._buf(st, f"dy{L.idx}", tuple(y.shape))
-        dVM = self._buf(st, f"dVM{L.idx}", (B, 16, L.O), torch.float32); dVM.zero_()
-        R = self._buf(st, f"R{L.idx}", (B, L.O), torch.float32); R.zero_()
+        dVM = self._zbuf(st, f"dVM{L.idx}", (B, 16, L.O))
+        R = self._zbuf(st, f"R{L.idx}", (B, L.O))
         _lib.check(_L().mgf_attn_bwd(_p(y), _p(dz), _p(L.Kf), _p(L.Sc), _p(st["maskbias"]), _p(st[f"VM{L.idx}"]), _p(L.bm), _p(noise), _p(nstr),
                                      _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_bwd")
         dcomp = dws[:, :-1, L.idx]                                 # [B,16,32] strided, accumulate
@@ -482,10 +499,9 @@ class SynthesisEngine:
         noise, nbs = self._noise_of(L, st, B, H, Wd)
         nstr = L.nstr if noise is not None else None
         dy = self._buf(st, f"dy{L.idx}", tuple(z.shape)) if want_dy else None
-        R = self._buf(st, f"R{L.idx}", (B, L.O), torch.float32)
+        R = self._zbuf(st, f"R{L.idx}", (B, L.O))
 
         def run():
-            R.zero_()
             _lib.check(_L().mgf_act_bwd(_p(dz), _p(z), _p(dy), _p(R), _p(noise), _p(nstr), _p(L.bias), LRELU_ALPHA, L.gain, mode,
                                         B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_act_bwd")
         if want_dy:
@@ -501,6 +517,8 @@ class SynthesisEngine:
         st = self._state(B)
         ws = st["ws"]
         dws = torch.zeros_like(ws)
+        if st.get("zpool") is not None:
+            st["zpool"][:max(st.get("zpool_used", 0), 1)].zero_()       # every reduction target of this backward pass, one fill
         dimg = dimg.to(torch.float32).contiguous()
         main = torch.cuda.current_stream(self.dev)
         if self._side is None:
@@ -515,8 +533,8 @@ class SynthesisEngine:
                 rgb = e["rgb"]; Ll = e["conv_last"]
                 yl = st["yl"]
                 dyl = self._buf(st, "dyl", tuple(yl.shape))
-                ds_rgb = self._buf(st, "ds_rgb", (B, rgb["C"]), torch.float32); ds_rgb.zero_()
-                R_last = self._buf(st, f"R{Ll.idx}", (B, Ll.O), torch.float32); R_last.zero_()
+                ds_rgb = self._zbuf(st, "ds_rgb", (B, rgb["C"]))
+                R_last = self._zbuf(st, f"R{Ll.idx}", (B, Ll.O))
                 _lib.check(_L().mgf_torgb_bwd(_p(dimg), _p(yl), _p(rgb["w"]), _p(st["s_rgb"]), _p(dyl), _p(ds_rgb), _p(R_last),
                                               B, r * r, rgb["C"], _s(self.dev)), "mgf_torgb_bwd")
                 dwg = dws[:, -1, rgb["idx"]]
