@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib, tc
+from .torch_utils.ops import upfirdn2d as _upfirdn2d
 
 SQRT2 = math.sqrt(2.0)
 SQRT_HALF = math.sqrt(0.5)
@@ -93,8 +94,8 @@ class SynthesisEngine:
         self.dev = next(synthesis.parameters()).device
         if self.dev.type != "cuda":
             raise _lib.MgfError("SynthesisEngine needs the module on a CUDA device (no CPU fallback)")
-        if synthesis.architecture != "resnet":
-            raise NotImplementedError("tc engine: only the resnet architecture of the GANformer-default generator is built")
+        if synthesis.architecture not in ("resnet", "skip", "orig"):
+            raise NotImplementedError("tc engine: unknown synthesis architecture %r" % (synthesis.architecture,))
         self.res = synthesis.img_res
         self.k = synthesis.k
         self.num_ws = synthesis.num_ws
@@ -111,6 +112,7 @@ class SynthesisEngine:
         dev = self.dev
         self.blocks = []
         w_idx = 0
+        self.arch = arch = self.net.architecture            # "resnet" (GANformer default) | "skip" | "orig" (reference networks.py:1070-1174)
         for r in self.net.block_resolutions:
             blk = getattr(self.net, f"b{r}")
             e = {"res": r, "stem": blk.stem, "last": blk.is_last}
@@ -119,20 +121,23 @@ class SynthesisEngine:
                 e["conv1"] = self._fold_layer(blk.conv1, w_idx, gain=1.0); w_idx += 1
             else:
                 e["conv0"] = self._fold_layer(blk.conv0, w_idx, gain=1.0); w_idx += 1
-                e["conv1"] = self._fold_layer(blk.conv1, w_idx, gain=SQRT_HALF); w_idx += 1
-                wsk = (blk.skip.weight.detach().float() * float(blk.skip.w_gain))[:, :, 0, 0]                 # [O, I]
-                e["skip_f32"] = wsk.reshape(1, 1, *wsk.shape).contiguous()                                      # [1,1,O,I] fp32 master
-                e["skip_b"] = wsk.t().reshape(1, 1, wsk.shape[1], wsk.shape[0]).to(torch.bfloat16).contiguous()  # [1,1,I,O]
-                f1 = np.array([1, 3, 3, 1], dtype=np.float64); f1 = f1 / f1.sum()
-                e["fk4"] = (ctypes.c_float * 4)(*[float(v) for v in f1[::-1]])
-                e["skip_gain"] = 4.0 * SQRT_HALF
+                e["conv1"] = self._fold_layer(blk.conv1, w_idx, gain=SQRT_HALF if arch == "resnet" else 1.0); w_idx += 1
+                if arch == "resnet":
+                    wsk = (blk.skip.weight.detach().float() * float(blk.skip.w_gain))[:, :, 0, 0]                 # [O, I]
+                    e["skip_f32"] = wsk.reshape(1, 1, *wsk.shape).contiguous()                                      # [1,1,O,I] fp32 master
+                    e["skip_b"] = wsk.t().reshape(1, 1, wsk.shape[1], wsk.shape[0]).to(torch.bfloat16).contiguous()  # [1,1,I,O]
+                    f1 = np.array([1, 3, 3, 1], dtype=np.float64); f1 = f1 / f1.sum()
+                    e["fk4"] = (ctypes.c_float * 4)(*[float(v) for v in f1[::-1]])
+                    e["skip_gain"] = 4.0 * SQRT_HALF
             if blk.is_last:
                 e["conv_last"] = self._fold_layer(blk.conv_last, w_idx, gain=1.0); w_idx += 1
+            if blk.is_last or arch == "skip":      # ToRGB reads the ws slot after this block's convs (shared with the next block's conv0, :1134-1174)
                 tr = blk.torgb
                 C = tr.weight.shape[1]
                 e["rgb"] = dict(idx=w_idx, C=C, w=tr.weight.detach().float().reshape(3, C).contiguous(),
                                 A=tr.affine.weight.detach().float().contiguous(), ab=(tr.affine.bias.detach().float() * float(tr.affine.b_gain)).contiguous(),
                                 again=float(tr.affine.w_gain), sgain=float(tr.w_gain), bias=tr.biasAct.bias.detach().float().contiguous())
+                e["fir"] = blk.resample_kernel.detach().float()            # image up-sampling filter of the 'skip' architecture
             self.blocks.append(e)
         self.pos = None
 
@@ -383,7 +388,7 @@ class SynthesisEngine:
                 for key in ("conv0", "conv1", "conv_last"):
                     if e.get(key) is not None:
                         self._prep_layer(e[key], ws, st, B)
-        x = None
+        x, img = None, None
         for e in self.blocks:
             r = e["res"]
             if e["stem"]:
@@ -394,22 +399,31 @@ class SynthesisEngine:
                 x_in = x
                 z0 = self._layer_fwd(e["conv0"], x_in, ws, maskbias, st, B, noise_on)
                 z1 = self._layer_fwd(e["conv1"], z0, ws, maskbias, st, B, noise_on)
-                O, I = e["conv0"].O, e["conv0"].I
-                h = x_in.shape[1]
-                v = self._buf(st, f"v{r}", (B, h, h, O), fwd=True)
-                tc.conv_tc([x_in], self._skip_f(e), [(0, 0, 0, 0)], (B, h, h), 1, O, v, tag="g.fwd")
-                x = self._buf(st, f"xout{r}", (B, r, r, O), fwd=True)
-                _lib.check(_L().mgf_upfir2_add(_p(v), _p(z1), _p(x), e["fk4"], e["skip_gain"], B, h, h, O, _s(self.dev)), "mgf_upfir2_add")
+                if self.arch == "resnet":
+                    O, I = e["conv0"].O, e["conv0"].I
+                    h = x_in.shape[1]
+                    v = self._buf(st, f"v{r}", (B, h, h, O), fwd=True)
+                    tc.conv_tc([x_in], self._skip_f(e), [(0, 0, 0, 0)], (B, h, h), 1, O, v, tag="g.fwd")
+                    x = self._buf(st, f"xout{r}", (B, r, r, O), fwd=True)
+                    _lib.check(_L().mgf_upfir2_add(_p(v), _p(z1), _p(x), e["fk4"], e["skip_gain"], B, h, h, O, _s(self.dev)), "mgf_upfir2_add")
+                else:
+                    x = z1
+            if img is not None and self.arch == "skip":               # running image of the 'skip' architecture (:1166-1167), fp32 NCHW ops kernel
+                img = _upfirdn2d.upsample2d(img, e["fir"])
             if e["last"]:
                 yl = self._layer_fwd(e["conv_last"], x, ws, maskbias, st, B, noise_on)
+                st["yl"] = yl
+            if "rgb" in e:
                 rgb = e["rgb"]
-                srgb = self._buf(st, "s_rgb", (B, rgb["C"]), torch.float32)
+                xr = yl if e["last"] else x
+                st[f"xrgb{r}"] = xr
+                srgb = self._buf(st, f"s_rgb{r}", (B, rgb["C"]), torch.float32)
                 wg = ws[:, -1, rgb["idx"]]
                 _lib.check(_L().mgf_style_fwd(_p(wg), wg.stride(0), _p(rgb["A"]), _p(rgb["ab"]), rgb["again"], rgb["sgain"], None, _p(srgb), None,
                                               B, rgb["C"], 0, wg.shape[1], _s(self.dev)), "mgf_style_fwd")
-                img = torch.empty(B, 3, r, r, dtype=torch.float32, device=self.dev)
-                _lib.check(_L().mgf_torgb_fwd(_p(yl), _p(rgb["w"]), _p(srgb), _p(rgb["bias"]), _p(img), B, r * r, rgb["C"], _s(self.dev)), "mgf_torgb_fwd")
-                st["yl"] = yl
+                y_rgb = torch.empty(B, 3, r, r, dtype=torch.float32, device=self.dev)
+                _lib.check(_L().mgf_torgb_fwd(_p(xr), _p(rgb["w"]), _p(srgb), _p(rgb["bias"]), _p(y_rgb), B, r * r, rgb["C"], _s(self.dev)), "mgf_torgb_fwd")
+                img = y_rgb if img is None else img.add_(y_rgb)
         main.wait_stream(self._side)
         return img
 
@@ -529,20 +543,33 @@ class SynthesisEngine:
         g = None
         for e in reversed(self.blocks):
             r = e["res"]
-            if e["last"]:
-                rgb = e["rgb"]; Ll = e["conv_last"]
-                yl = st["yl"]
-                dyl = self._buf(st, "dyl", tuple(yl.shape))
-                ds_rgb = self._zbuf(st, "ds_rgb", (B, rgb["C"]))
-                R_last = self._zbuf(st, f"R{Ll.idx}", (B, Ll.O))
-                _lib.check(_L().mgf_torgb_bwd(_p(dimg), _p(yl), _p(rgb["w"]), _p(st["s_rgb"]), _p(dyl), _p(ds_rgb), _p(R_last),
+            if "rgb" in e:
+                # ToRGB backward of this block: gradient wrt its input (conv_last's output in the last block, the block output otherwise)
+                rgb = e["rgb"]
+                xr = st[f"xrgb{r}"]
+                dxr = self._buf(st, f"dxrgb{r}", tuple(xr.shape))
+                ds_rgb = self._zbuf(st, f"ds_rgb{r}", (B, rgb["C"]))
+                Ll = e.get("conv_last")
+                R_rgb = self._zbuf(st, f"R{Ll.idx}" if e["last"] else f"Rrgb{r}", (B, rgb["C"]))       # sum_p dy*y: only conv_last's demodulation needs it
+                _lib.check(_L().mgf_torgb_bwd(_p(dimg), _p(xr), _p(rgb["w"]), _p(st[f"s_rgb{r}"]), _p(dxr), _p(ds_rgb), _p(R_rgb),
                                               B, r * r, rgb["C"], _s(self.dev)), "mgf_torgb_bwd")
                 dwg = dws[:, -1, rgb["idx"]]
-                self._on_side(lambda: _lib.check(_L().mgf_style_bwd(_p(ds_rgb), None, None, None, None, _p(rgb["A"]), rgb["again"], rgb["sgain"], _p(dwg),
-                                                                    dwg.stride(0), B, rgb["C"], 0, dwg.shape[1], _s(self.dev)), "mgf_style_bwd"))
-                g = self._buf(st, f"g{r}", tuple(st[f"xin{Ll.idx}"].shape))
-                ds = self._dgrad(Ll, dyl, st, B, g)
-                self._style_bwd(Ll, ds, R_last, st, dws, B)
+                self._on_side(lambda ds_rgb=ds_rgb, rgb=rgb, dwg=dwg: _lib.check(_L().mgf_style_bwd(
+                    _p(ds_rgb), None, None, None, None, _p(rgb["A"]), rgb["again"], rgb["sgain"], _p(dwg), dwg.stride(0), B, rgb["C"], 0, dwg.shape[1],
+                    _s(self.dev)), "mgf_style_bwd"))
+                if e["last"]:
+                    g_last = self._buf(st, f"g{r}", tuple(st[f"xin{Ll.idx}"].shape))
+                    ds = self._dgrad(Ll, dxr, st, B, g_last)
+                    self._style_bwd(Ll, ds, R_rgb, st, dws, B)
+                    g = g_last
+                else:
+                    g.add_(dxr)                                    # 'skip' architecture: the block output also feeds its own ToRGB
+                if self.arch == "skip" and not e["stem"]:
+                    # gradient of the running image at the previous resolution: adjoint of upsample2d through the ops kernel's autograd
+                    with torch.enable_grad():
+                        a = torch.zeros(B, 3, r // 2, r // 2, device=self.dev, requires_grad=True)
+                        up = _upfirdn2d.upsample2d(a, e["fir"])
+                    (dimg,) = torch.autograd.grad(up, [a], grad_outputs=[dimg])
             if e["stem"]:
                 L1 = e["conv1"]
                 dy1, R1 = self._attn_bwd(L1, g, st, dws, B) if L1.attn else self._act_bwd(L1, g, st[f"z{L1.idx}"], st, B, 0)
@@ -553,12 +580,15 @@ class SynthesisEngine:
             L0, L1 = e["conv0"], e["conv1"]
             x_in = st[f"xin{L0.idx}"]
             h = x_in.shape[1]
-            # skip branch: d v = FIR^T(g) ; d x_in (skip part) = conv1x1^T
-            dv = self._buf(st, f"dv{r}", (B, h, h, L0.O))
-            g_blk, fk4, sg = g, e["fk4"], e["skip_gain"]
-            self._on_side(lambda: _lib.check(_L().mgf_upfir2_bwd(_p(g_blk), _p(dv), fk4, sg, B, h, h, L0.O, _s(self.dev)), "mgf_upfir2_bwd"))
-            ev_dv = torch.cuda.Event(); ev_dv.record(self._side if BWD_SIDE_REDUCTIONS else main)
-            gs = self._buf(st, f"gs{r}", tuple(x_in.shape))
+            resnet = self.arch == "resnet"
+            gs = None
+            if resnet:
+                # skip branch: d v = FIR^T(g) ; d x_in (skip part) = conv1x1^T
+                dv = self._buf(st, f"dv{r}", (B, h, h, L0.O))
+                g_blk, fk4, sg = g, e["fk4"], e["skip_gain"]
+                self._on_side(lambda: _lib.check(_L().mgf_upfir2_bwd(_p(g_blk), _p(dv), fk4, sg, B, h, h, L0.O, _s(self.dev)), "mgf_upfir2_bwd"))
+                ev_dv = torch.cuda.Event(); ev_dv.record(self._side if BWD_SIDE_REDUCTIONS else main)
+                gs = self._buf(st, f"gs{r}", tuple(x_in.shape))
             # conv1
             z0 = st[f"z{L0.idx}"]
             dy1, R1 = self._attn_bwd(L1, g, st, dws, B) if L1.attn else self._act_bwd(L1, g, st[f"z{L1.idx}"], st, B, 0)
@@ -574,8 +604,9 @@ class SynthesisEngine:
             self._style_bwd(L1, ds1, R1, st, dws, B)
             # conv0 (up) dgrad, adding the skip-branch gradient in the epilogue -> gradient wrt the previous block's output
             gprev = self._buf(st, f"g{r // 2}", tuple(x_in.shape))
-            main.wait_event(ev_dv)                             # the FIR adjoint of the skip branch ran beside conv1's backward
-            tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd", fwd=False)
+            if resnet:
+                main.wait_event(ev_dv)                         # the FIR adjoint of the skip branch ran beside conv1's backward
+                tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd", fwd=False)
             ds0 = self._dgrad(L0, dy0, st, B, gprev, add=gs)
             self._style_bwd(L0, ds0, R0, st, dws, B)
             g = gprev

@@ -189,3 +189,32 @@ def test_tc_engine_other_resolutions_and_batches(res, B, cb, cm):
     rng = max(1.0, ref.abs().max().item())
     assert (img - ref).abs().max().item() < 1e-2 * rng
     assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.998
+
+
+@pytest.mark.parametrize("arch", ["skip", "orig"])
+def test_tc_engine_skip_and_orig_architectures(arch):
+    """The other two synthesis architectures of the reference (networks.py:1070-1174: 'skip' = per-block ToRGB summed over an up-sampled
+    running image, 'orig' = plain stack) on the tc engine vs the exact-fp32 ops engine: image and d(ws)."""
+    from morphganformer_b200 import _lib
+    from morphganformer_b200.training import networks as N
+    res, B = 64, 2
+    torch.manual_seed(0)
+    G = util.randomize(N.Generator(**N.ganformer_default_kwargs(res, 2048, 64, architecture=arch)).eval().requires_grad_(False), 1).cuda()
+    ws = util.case_tensor((B, 17, G.num_ws, 32), 26).cuda()
+    mask = torch.ones(B, 16, device="cuda")
+    tgt = torch.tanh(util.case_tensor((B, 3, res, res), 27)).cuda()
+    out = {}
+    _lib.set_forward_dtype("fp16")
+    try:
+        for eng in ("ops", "tc"):
+            G.synthesis.engine = eng
+            w = ws.clone().requires_grad_(True)
+            img, _ = G.synthesis(w, pos=G.pos, mask=mask, noise_mode="const", return_att_maps=False)
+            g, = torch.autograd.grad((img - tgt).square().mean(), [w])
+            out[eng] = (img.detach(), g)
+    finally:
+        _lib.set_forward_dtype("bf16")
+    ref, gref = out["ops"]; img, g = out["tc"]
+    rng = max(1.0, ref.abs().max().item())
+    assert (img - ref).abs().max().item() < 1e-2 * rng
+    assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.998
