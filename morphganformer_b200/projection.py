@@ -30,7 +30,7 @@ def latent_stats(noise_sample):
 class Projector:
     def __init__(self, G, lpips_state_dict, batch, steps, lr=0.1, lamda=0.5, noise=0.05, noise_ramp=0.75, lr_rampdown=0.25,
                  lr_rampup=0.05, weight_decay=1e-4, latent_mean=None, latent_std=None, use_lpips=True, step_noise=None,
-                 noise_seed=3, forward_dtype=None, fused_mapping=True, engine="tc"):
+                 noise_seed=3, forward_dtype=None, fused_mapping=True, engine="tc", noise_mode="const"):
         """forward_dtype: None keeps the library's current setting; 'fp16' / 'bf16' select the 16-bit type of the engine's forward
         activations and operands (gradients are always bf16).  fp16 meets the 1e-2 image / 1e-3 loss parity bars; bf16 has the
         fp32 exponent range (use it for checkpoints whose activations may exceed 6.5e4).  Same speed."""
@@ -38,7 +38,9 @@ class Projector:
             _lib.set_forward_dtype(forward_dtype)
         if engine not in ("tc", "ops"):
             raise ValueError("engine must be 'tc' (16-bit tcgen05 engine, the throughput path) or 'ops' (exact fp32 kernels + autograd)")
-        self.engine = engine
+        if noise_mode not in ("const", "random", "none"):
+            raise ValueError("noise_mode must be 'const', 'random' or 'none'")
+        self.engine, self.noise_mode = engine, noise_mode      # 'random' is what the reference scripts get by default (networks.py:1010); 'const' is reproducible
         self.G = G
         self.dev = next(G.parameters()).device
         if self.dev.type != "cuda":
@@ -163,7 +165,7 @@ class Projector:
         G = self.G
         z = self.latent_n.detach().requires_grad_(True)
         with torch.enable_grad():
-            img = G(z, noise_mode="const")[0]
+            img = G(z, noise_mode=self.noise_mode)[0]
             per_img = (img - self.target).square().mean(dim=[1, 2, 3])
             if self.use_lpips:
                 per_img = self.lamda * self.lp32(img, self.target).reshape(-1) + (1 - self.lamda) * per_img
@@ -182,7 +184,7 @@ class Projector:
             z = self.latent_n.detach().requires_grad_(True)
             with torch.enable_grad():
                 ws = G.mapping(z, None, pos=G.pos, mask=self.mask)
-        img = eng.forward_raw(ws, mask=self.mask, noise_mode="const")
+        img = eng.forward_raw(ws, mask=self.mask, noise_mode=self.noise_mode)
         per_img, dimg = self._loss_and_grad(img)
         dws = eng.backward_raw(dimg)
         if self.mapper is not None:

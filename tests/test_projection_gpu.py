@@ -172,3 +172,24 @@ def test_1000_step_projected_latents_exact_fp32_path_vs_oracle():
     assert drift < 2e-2
     assert rel[999].max().item() < 1e-3
     assert want_l[-1].mean() < want_l[0].mean()
+
+
+def test_projection_with_random_synthesis_noise_runs_and_is_captured_in_a_graph():
+    """noise_mode='random' (the reference scripts' default synthesis noise): per-step fresh noise planes, eager and under CUDA-graph replay."""
+    from morphganformer_b200.projection import Projector, latent_stats
+    res, B = 64, 2
+    lsd = util.build_vgg_lpips_sd(4)
+    mean, std = latent_stats(util.case_tensor((2000, 17, 32), 70))
+    tgt = torch.tanh(util.case_tensor((B, 3, res, res), 73))
+    G = util.build_G(res, 0, 2048, 64).cuda()
+    P = Projector(G, lsd, B, 20, latent_mean=mean, latent_std=std, step_noise=util.case_tensor((20, B, 17, 32), 71), noise_mode="random")
+    P.set_targets(tgt)
+    torch.manual_seed(5)
+    P.step(); P.step()
+    P.capture()
+    for _ in range(4):
+        P.step()
+    torch.cuda.synchronize()
+    l = P.losses[:6].cpu()
+    assert torch.isfinite(l).all() and (l > 0).all()
+    assert len({round(float(v), 6) for v in l[:, 0]}) == 6          # every step saw different noise (replays advance the RNG too)
