@@ -149,6 +149,9 @@ int mgf_torgb_bwd(const float* dimg, const void* y, const float* wrgb, const flo
                   int B, int64_t HW, int C, void* stream);
 int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, const float* noise, const float* nstr, const float* bias,
                 float alpha, float gain, int mode, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
+/* g [B,H+2,W+2,C] bf16 = 4-tap separable FIR (taps fk4, zero padding 2, * gain) of dy [B,H,W,C] bf16: first stage of the up-convolution's
+ * input gradient (adjoint of upfirdn2d(pad 1, gain 4) after conv_transpose2d, conv2d_resample.py:117-134) */
+int mgf_fir4_pad(const void* dy, void* g, const float* fk4, float gain, int B, int H, int W, int C, void* stream);
 int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
 int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
 

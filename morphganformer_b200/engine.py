@@ -29,6 +29,8 @@ SQRT_HALF = math.sqrt(0.5)
 import os as _os
 BWD_SIDE_REDUCTIONS = _os.environ.get("MGF_BWD_SIDE", "1") != "0"      # A/B switch: d(style) reductions on the side stream
 LRELU_ALPHA = 0.2
+TWO_STAGE_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_MAX_RES", "128"))   # A/B switch: up-conv dgrad as FIR + 9-tap strided conv up to this output size
+FIR4_TAPS = (ctypes.c_float * 4)(0.125, 0.375, 0.375, 0.125)      # [1,3,3,1] / 8 (symmetric: flipping is a no-op); gain 4 = up^2 passed separately
 
 
 def _L():
@@ -159,15 +161,27 @@ class SynthesisEngine:
         else:
             Weff = torch.einsum("ptk,oik->ptoi", self.Cm.to(dev), Wk)                  # [4, 9, O, I]
             L.Bf = Weff.permute(1, 0, 2, 3).reshape(9, 4 * O, I).contiguous()           # [9, 4*O, I]
-            L.Bb = Weff.permute(0, 1, 3, 2).reshape(36, I, O).contiguous()              # [36, I, O]
             L.taps_f = [(0, ty - 1, tx - 1, ty * 3 + tx) for ty in range(3) for tx in range(3)]
-            L.taps_b = [(ph, 1 - ty, 1 - tx, ph * 9 + ty * 3 + tx) for ph in range(4) for ty in range(3) for tx in range(3)]
             L.phases = 4
+            # input gradient in the reference's own two-stage form (adjoint of conv_transpose2d(stride 2) -> FIR): g = FIR4(dy) on the
+            # (2h+1) x (2w+1) grid (mgf_fir4_pad), then dx[i,j] = sum_k W_k^T g[2i+ky, 2j+kx]: a stride-2 3x3 conv = 9 taps over the four
+            # phase views of g (view (ky%2, kx%2), shift (ky//2, kx//2)) instead of 36 taps of the folded four-phase kernels
+            # Measured (8 images): the 9-tap form halves the dgrad time at every resolution, but the FIR pass costs 0.08-0.54 ms at
+            # 128^2 .. 1024^2 (instruction-bound at 1.9 TB/s), so it only wins up to 128^2 outputs; above that the folded 36-tap form stays.
+            L.two_stage = L.res <= TWO_STAGE_MAX_RES
+            if L.two_stage:
+                L.Bb = Wk.permute(2, 1, 0).contiguous()                                   # [9, I, O]
+                L.taps_b = [((ky % 2) * 2 + (kx % 2), ky // 2, kx // 2, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+            else:
+                L.Bb = Weff.permute(0, 1, 3, 2).reshape(36, I, O).contiguous()            # [36, I, O]
+                L.taps_b = [(ph, 1 - ty, 1 - tx, ph * 9 + ty * 3 + tx) for ph in range(4) for ty in range(3) for tx in range(3)]
         # low-resolution layers: per-sample weight tensors (B x 4.7-19 MB) would dwarf the activations, so modulate the ACTIVATIONS
         # instead (xs = x*s, epilogue *d; reference non-fused algebra, networks.py:314-324) and keep ONE shared weight tensor
         L.shared_w = L.res <= 128 and O * I >= 256 * 256
         L.Bb16 = L.Bb.unsqueeze(0).to(torch.bfloat16).contiguous() if L.shared_w else None     # [1, T, I, O]
         L._Bf16 = None
+        if m.up == 1:
+            L.two_stage = False
         # 32 -> 32 channel 3x3 layers (the 1024^2 block): 64-byte pixel rows halve the TMA efficiency, so view two neighbouring pixels as
         # one 64-channel super-pixel (same memory) and expand the weights to the block form [9][(po,o)][(pi,i)]
         L.superpix = (m.up == 1 and O == 32 and I == 32 and L.res >= 64 and not L.shared_w and m.transformer is None)
@@ -455,10 +469,17 @@ class SynthesisEngine:
             torch.add(ds2[:, :32], ds2[:, 32:], out=dsum)
             return dsum
         ds = self._zbuf(st, f"ds{L.idx}", (B, L.I))
-        acts = [dy] if L.up == 1 else [tc.phase_view(dy, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
+        if L.up == 1:
+            acts = [dy]
+        elif not L.two_stage:
+            acts = [tc.phase_view(dy, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
+        else:
+            gq = self._buf(st, f"gfir{L.idx}", (B, 2 * h + 2, 2 * w + 2, L.O))
+            _lib.check(_L().mgf_fir4_pad(_p(dy), _p(gq), FIR4_TAPS, 4.0, B, 2 * h, 2 * w, L.O, _s(self.dev)), "mgf_fir4_pad")
+            acts = [tc.phase_view(gq, py, px) for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1))]
         tc.conv_tc(acts, Wb, L.taps_b, (B, h, w), 1, L.I, out, scale_n=s, reduce_out=ds, X=x_in, add=add,
                    actgrad=actgrad_X is not None, ag_alpha=LRELU_ALPHA, ag_gain=ag_gain, reduce_per_sample=True,
-                   alg_scale=1.0 / L.phases, tag="g.bwd", fwd=False)
+                   alg_scale=1.0 if (L.up == 1 or L.two_stage) else 0.25, tag="g.bwd", fwd=False)
         return ds
 
     def _on_side(self, fn):
