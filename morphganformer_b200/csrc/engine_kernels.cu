@@ -337,57 +337,59 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* __
 // u in [0, H], v in [0, W] (dy is [B,H,W,C]; g is [B,H+2,W+2,C], the last row / column are written as zeros).
 // First stage of the up-convolution's input gradient: the reference's up path is conv_transpose2d(stride 2) -> upfirdn2d(pad 1, gain 4)
 // (conv2d_resample.py:117-134), so its adjoint is this FIR (H -> H+1) followed by a stride-2 3x3 convolution: 9 taps on the tensor
-// cores instead of the 36 of the folded four-phase form.  Thread = 4 consecutive output columns x one 8-channel vector: column sums
-// (vertical taps) are formed once per input column and scattered into the up-to-four outputs they feed (7 loads per output, not 16).
+// cores instead of the 36 of the folded four-phase form (7 loads per output instead of 16: see the kernel).
 __global__ void __launch_bounds__(256) fir4_pad_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ g, float4 fk, float gain,
                                                        int H, int W, int C, int vshift) {
+  // thread = one output column v x one 8-channel vector x FOUR consecutive output rows u0 .. u0+3: consecutive threads walk along the row, so
+  // every load / store instruction of a warp covers 512 contiguous bytes (the first version ran four columns per thread: 256-byte strides
+  // between lanes, twice the L1 wavefronts).  Row sums (horizontal taps) of the 7 input rows are scattered into the four outputs they feed.
   const int vecs = 1 << vshift;
-  const int b = blockIdx.z, u = blockIdx.y;                      // output row 0 .. H+1
-  const int runs = (W + 2 + 3) >> 2;
-  const float f[4] = {fk.x, fk.y, fk.z, fk.w};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (runs << vshift); i += gridDim.x * blockDim.x) {
-    const int cv = i & (vecs - 1), v0 = (i >> vshift) * 4;       // outputs v0 .. v0+3
+  const int b = blockIdx.z, u0 = blockIdx.y * 4;
+  const float f[4] = {fk.x * gain, fk.y * gain, fk.z * gain, fk.w * gain};     // gain folded into the horizontal taps
+  const float fv[4] = {fk.x, fk.y, fk.z, fk.w};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((W + 2) << vshift); i += gridDim.x * blockDim.x) {
+    const int cv = i & (vecs - 1), v = i >> vshift;
     float acc[4][8];
 #pragma unroll
     for (int j = 0; j < 4; j++)
 #pragma unroll
       for (int e = 0; e < 8; e++) acc[j][e] = 0.f;
-    if (u <= H) {
+    if (v <= W) {
 #pragma unroll
-      for (int cc = 0; cc < 7; cc++) {                           // input columns v0-2 .. v0+4
-        const int x = v0 - 2 + cc;
-        if (x < 0 || x >= W) continue;
-        float cs[8];
+      for (int rr = 0; rr < 7; rr++) {                           // input rows u0-2 .. u0+4
+        const int y = u0 - 2 + rr;
+        if (y < 0 || y >= H) continue;
+        float rs[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) cs[e] = 0.f;
+        for (int e = 0; e < 8; e++) rs[e] = 0.f;
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-          const int y = u - a + 1;
-          if (y < 0 || y >= H) continue;
+        for (int bb = 0; bb < 4; bb++) {
+          const int x = v - bb + 1;
+          if (x < 0 || x >= W) continue;
           const uint4 q = __ldg(reinterpret_cast<const uint4*>(dy + ((((long long)b * H + y) * W + x) << (vshift + 3))) + cv);
           const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-          for (int e = 0; e < 4; e++) { const float2 t = unpack_bf16(w4[e]); cs[e * 2] = fmaf(f[a], t.x, cs[e * 2]); cs[e * 2 + 1] = fmaf(f[a], t.y, cs[e * 2 + 1]); }
+          for (int e = 0; e < 4; e++) { const float2 t = unpack_bf16(w4[e]); rs[e * 2] = fmaf(f[bb], t.x, rs[e * 2]); rs[e * 2 + 1] = fmaf(f[bb], t.y, rs[e * 2 + 1]); }
         }
-        // column x feeds output v = x + b' - 1, b' = 0..3  ->  j = v - v0 = cc - 3 + b'
+        // input row y feeds output row u = y + a - 1, a = 0..3  ->  j = u - u0 = rr - 3 + a
 #pragma unroll
-        for (int bb = 0; bb < 4; bb++) {
-          const int j = cc - 3 + bb;
+        for (int a = 0; a < 4; a++) {
+          const int j = rr - 3 + a;
           if (j >= 0 && j < 4) {
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[j][e] = fmaf(f[bb], cs[e], acc[j][e]);
+            for (int e = 0; e < 8; e++) acc[j][e] = fmaf(fv[a], rs[e], acc[j][e]);
           }
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const int v = v0 + j;
-      if (v < W + 2) {
+      const int u = u0 + j;
+      if (u < H + 2) {
         const bool live = (u <= H) && (v <= W);
         uint4 o;
-        o.x = live ? pack_bf16(acc[j][0] * gain, acc[j][1] * gain) : 0u; o.y = live ? pack_bf16(acc[j][2] * gain, acc[j][3] * gain) : 0u;
-        o.z = live ? pack_bf16(acc[j][4] * gain, acc[j][5] * gain) : 0u; o.w = live ? pack_bf16(acc[j][6] * gain, acc[j][7] * gain) : 0u;
+        o.x = live ? pack_bf16(acc[j][0], acc[j][1]) : 0u; o.y = live ? pack_bf16(acc[j][2], acc[j][3]) : 0u;
+        o.z = live ? pack_bf16(acc[j][4], acc[j][5]) : 0u; o.w = live ? pack_bf16(acc[j][6], acc[j][7]) : 0u;
         *(reinterpret_cast<uint4*>(g + ((((long long)b * (H + 2) + u) * (W + 2) + v) << (vshift + 3))) + cv) = o;
       }
     }
@@ -557,8 +559,8 @@ extern "C" int mgf_fir4_pad(const void* dy, void* g, const float* fk4, float gai
   const int vs = (C % 8) ? -1 : log2_exact(C / 8);
   if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "fir4_pad: C/8 must be a power of two");
   if (H + 2 > 65535 || B > 65535 || B <= 0 || H <= 0 || W <= 0) MGF_FAIL(MGF_E_SHAPE, "fir4_pad: bad image size");
-  const int items = ((W + 2 + 3) >> 2) << vs;
-  dim3 grid((items + 255) / 256, H + 2, B);
+  const int items = (W + 2) << vs;
+  dim3 grid((items + 255) / 256, (H + 2 + 3) / 4, B);
   fir4_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)g, make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, H, W, C, vs);
   MGF_CHECK_LAUNCH("fir4_pad");
   return 0;
