@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* __
 // First stage of the up-convolution's input gradient: the reference's up path is conv_transpose2d(stride 2) -> upfirdn2d(pad 1, gain 4)
 // (conv2d_resample.py:117-134), so its adjoint is this FIR (H -> H+1) followed by a stride-2 3x3 convolution: 9 taps on the tensor
 // cores instead of the 36 of the folded four-phase form (7 loads per output instead of 16: see the kernel).
-__global__ void __launch_bounds__(256) fir4_pad_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ g, float4 fk, float gain,
+__global__ void __launch_bounds__(256, 2) fir4_pad_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ g, float4 fk, float gain,
                                                        int H, int W, int C, int vshift) {
   // thread = one output column v x one 8-channel vector x FOUR consecutive output rows u0 .. u0+3: consecutive threads walk along the row, so
   // every load / store instruction of a warp covers 512 contiguous bytes (the first version ran four columns per thread: 256-byte strides
@@ -355,29 +355,53 @@ __global__ void __launch_bounds__(256) fir4_pad_kernel(const __nv_bfloat16* __re
 #pragma unroll
       for (int e = 0; e < 8; e++) acc[j][e] = 0.f;
     if (v <= W) {
+      // branch-free: out-of-range taps read a clamped (valid) address with a zero weight, so all loads of a batch of rows are issued
+      // before the first use (the branchy version serialised 7 dependent row round trips per thread: latency-bound at 2 TB/s)
+      float wx[4]; int xc[4];
 #pragma unroll
-      for (int rr = 0; rr < 7; rr++) {                           // input rows u0-2 .. u0+4
-        const int y = u0 - 2 + rr;
-        if (y < 0 || y >= H) continue;
-        float rs[8];
+      for (int bb = 0; bb < 4; bb++) {
+        const int x = v - bb + 1;
+        const bool ok = x >= 0 && x < W;
+        wx[bb] = ok ? f[bb] : 0.f; xc[bb] = ok ? x : 0;
+      }
 #pragma unroll
-        for (int e = 0; e < 8; e++) rs[e] = 0.f;
+      for (int r0 = 0; r0 < 7; r0 += 4) {                        // two batches: input rows u0-2 .. u0+1, then u0+2 .. u0+4
+        uint4 q[4][4];
+        float wy[4];
 #pragma unroll
-        for (int bb = 0; bb < 4; bb++) {
-          const int x = v - bb + 1;
-          if (x < 0 || x >= W) continue;
-          const uint4 q = __ldg(reinterpret_cast<const uint4*>(dy + ((((long long)b * H + y) * W + x) << (vshift + 3))) + cv);
-          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+        for (int k = 0; k < 4; k++) {
+          const int rr = r0 + k;
+          const int y = u0 - 2 + rr;
+          const bool ok = rr < 7 && y >= 0 && y < H;
+          wy[k] = ok ? 1.f : 0.f;
+          const long long rowbase = ((long long)b * H + (ok ? y : 0)) * W;
 #pragma unroll
-          for (int e = 0; e < 4; e++) { const float2 t = unpack_bf16(w4[e]); rs[e * 2] = fmaf(f[bb], t.x, rs[e * 2]); rs[e * 2 + 1] = fmaf(f[bb], t.y, rs[e * 2 + 1]); }
+          for (int bb = 0; bb < 4; bb++)
+            if (rr < 7) q[k][bb] = __ldg(reinterpret_cast<const uint4*>(dy + ((rowbase + xc[bb]) << (vshift + 3))) + cv);
         }
-        // input row y feeds output row u = y + a - 1, a = 0..3  ->  j = u - u0 = rr - 3 + a
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-          const int j = rr - 3 + a;
-          if (j >= 0 && j < 4) {
+        for (int k = 0; k < 4; k++) {
+          const int rr = r0 + k;
+          if (rr < 7) {
+            float rs[8];
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[j][e] = fmaf(fv[a], rs[e], acc[j][e]);
+            for (int e = 0; e < 8; e++) rs[e] = 0.f;
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++) {
+              const float wgt = wx[bb] * wy[k];
+              const uint32_t w4[4] = {q[k][bb].x, q[k][bb].y, q[k][bb].z, q[k][bb].w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) { const float2 t = unpack_bf16(w4[e]); rs[e * 2] = fmaf(wgt, t.x, rs[e * 2]); rs[e * 2 + 1] = fmaf(wgt, t.y, rs[e * 2 + 1]); }
+            }
+            // input row y feeds output row u = y + a - 1, a = 0..3  ->  j = u - u0 = rr - 3 + a
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+              const int j = rr - 3 + a;
+              if (j >= 0 && j < 4) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[j][e] = fmaf(fv[a], rs[e], acc[j][e]);
+              }
+            }
           }
         }
       }
