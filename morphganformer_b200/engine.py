@@ -636,6 +636,10 @@ class SynthesisEngine:
 
     # -------------------------------------------------------------------------------------------- autograd entry
     def __call__(self, ws, pos=None, mask=None, noise_mode="const", fused_modconv=None, want_probs=False, **_ignored):
+        if self.net.training:
+            # train mode means attention dropout and w_avg tracking in the reference (networks.py:505-513, :928-929); this engine folds frozen
+            # weights and is an inference / projection engine -- use engine="ops" for training-mode graphs
+            raise NotImplementedError("tc engine: the synthesis network is in training mode; call G.eval() (or use engine='ops')")
         return _SynthesisFn.apply(ws, self, mask, noise_mode, want_probs)
 
 

@@ -218,3 +218,11 @@ def test_tc_engine_skip_and_orig_architectures(arch):
     rng = max(1.0, ref.abs().max().item())
     assert (img - ref).abs().max().item() < 1e-2 * rng
     assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.998
+
+
+def test_tc_engine_refuses_training_mode():
+    G = util.build_G(32, 0, 1024, 32).cuda()
+    G.synthesis.engine = "tc"
+    G.train()
+    with pytest.raises(NotImplementedError):
+        G.synthesis(util.case_tensor((1, 17, G.num_ws, 32), 1).cuda(), pos=G.pos, mask=torch.ones(1, 16, device="cuda"), noise_mode="const")
