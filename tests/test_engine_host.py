@@ -77,3 +77,32 @@ def test_attention_fold_matches_oracle_layer():
     ctl = A @ VM + bm
     xn = X * torch.rsqrt(X.square().mean(-1, keepdim=True) + 1e-8)
     assert (xn * (1 + ctl) - ref).abs().max() < 1e-9
+
+
+def test_two_stage_upconv_input_gradient_formula():
+    """What the engine computes for an up-convolution's input gradient up to 128^2 (mgf_fir4_pad + a stride-2 3x3 conv over four phase views):
+    g[u,v] = sum_{a,b} F[a,b] dy[u-a+1, v-b+1] on the (2h+1) x (2w+1) grid (F = outer([1,3,3,1]/8)^2 * 4), dx[i,j] = sum_k W_k^T g[2i+ky, 2j+kx]
+    equals autograd through the oracle's conv2d_resample(up=2) (reference conv2d_resample.py:117-134)."""
+    B, I, Oc, h, w = 2, 5, 4, 6, 7
+    x = util.case_tensor((B, I, h, w), 1).requires_grad_(True)
+    W = util.case_tensor((Oc, I, 3, 3), 2) * 0.3
+    f = O.setup_filter([1, 3, 3, 1])
+    y = O.conv2d_resample(x, W, f=f, up=2, padding=1, flip_weight=False)
+    dy = util.case_tensor(tuple(y.shape), 3)
+    gx_ref, = torch.autograd.grad(y, [x], dy)
+    f1 = np.array([1, 3, 3, 1], dtype=np.float64) / 8.0
+    Ff = torch.from_numpy(np.outer(f1, f1) * 4.0).float()
+    dyp = F.pad(dy, (2, 2, 2, 2))
+    g = torch.zeros(B, Oc, 2 * h + 1, 2 * w + 1)
+    for a in range(4):
+        for b in range(4):
+            g += Ff[a, b] * dyp[:, :, 3 - a:3 - a + 2 * h + 1, 3 - b:3 - b + 2 * w + 1]
+    # the engine's tap table: phase view (ky%2, kx%2) of g, shifted by (ky//2, kx//2)
+    gq = F.pad(g, (0, 1, 0, 1))                                       # [.., 2h+2, 2w+2] like the kernel's output buffer
+    dx = torch.zeros_like(x)
+    for ky in range(3):
+        for kx in range(3):
+            view = gq[:, :, ky % 2::2, kx % 2::2]                     # (h+1) x (w+1)
+            sl = view[:, :, ky // 2:ky // 2 + h, kx // 2:kx // 2 + w]
+            dx = dx + torch.einsum("bohw,oc->bchw", sl, W[:, :, ky, kx])
+    assert (dx - gx_ref).abs().max() < 1e-5 * gx_ref.abs().max().clamp(min=1.0)
