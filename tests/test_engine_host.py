@@ -106,3 +106,53 @@ def test_two_stage_upconv_input_gradient_formula():
             sl = view[:, :, ky // 2:ky // 2 + h, kx // 2:kx // 2 + w]
             dx = dx + torch.einsum("bohw,oc->bchw", sl, W[:, :, ky, kx])
     assert (dx - gx_ref).abs().max() < 1e-5 * gx_ref.abs().max().clamp(min=1.0)
+
+
+def test_mapping_pack_layout_reproduces_oracle_mapping():
+    """pack_mapping's flat layout (what mgf_mapping_fwd reads: mapping.cu) interpreted in numpy reproduces the oracle's ws: pins the gain /
+    positional-map folding and the offsets on the CPU."""
+    from morphganformer_b200 import mapping_engine
+    from oracle import ganformer
+    G = util.build_G(16, 3, 512, 32)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for n, p in G.mapping.named_parameters():
+            if n.endswith(".bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * (30.0 if ".l" in n or "out_layer" in n else 0.3))
+    P = mapping_engine.pack_mapping(G).double().numpy()
+    z = util.case_tensor((2, 17, 32), 40)
+    with torch.no_grad():
+        _, ws_ref = ganformer.generator(util.state_dict_cpu(G), z, 16)
+    D, T, W = 32, 16, 1024
+    lrelu = lambda v: np.where(v > 0, v, 0.2 * v)
+    take = lambda off, n, shape: P[off:off + n].reshape(shape)
+    LSZ = 6 * W + 2 * T * D + 4 * D
+    out = np.zeros((2, 17, 32))
+    for b in range(2):
+        zb = z[b].double().numpy()
+        x = zb[:16] / np.sqrt((zb[:16] ** 2).mean() + 1e-8)
+        for l in range(4):
+            o = l * LSZ
+            Wq, Wk, Wv, Wm, W0, W1 = (take(o + i * W, W, (D, D)) for i in range(6))
+            Cq, Ck = take(o + 6 * W, T * D, (T, D)), take(o + 6 * W + T * D, T * D, (T, D))
+            bv, bm, b0, b1 = (take(o + 6 * W + 2 * T * D + i * D, D, (D,)) for i in range(4))
+            q, k, v = x @ Wq.T + Cq, x @ Wk.T + Ck, x @ Wv.T + bv
+            s = q @ k.T / np.sqrt(32.0)
+            A = np.exp(s - s.max(1, keepdims=True)); A /= A.sum(1, keepdims=True)
+            xs = x + (A @ v) @ Wm.T + bm
+            h0 = lrelu(xs @ W0.T + b0) * np.sqrt(2.0)
+            x = lrelu(h0 @ W1.T + b1 + x)
+        o = 4 * LSZ
+        out[b, :16] = lrelu(x @ take(o, W, (D, D)).T + take(o + W, D, (D,))) * np.sqrt(2.0)
+        go = o + W + D
+        xg = zb[16] / np.sqrt((zb[16] ** 2).mean() + 1e-8)
+        GSZ = 2 * W + 2 * D
+        for l in range(4):
+            o2 = go + l * GSZ
+            W0, W1 = take(o2, W, (D, D)), take(o2 + W, W, (D, D))
+            b0, b1 = take(o2 + 2 * W, D, (D,)), take(o2 + 2 * W + D, D, (D,))
+            xg = lrelu(lrelu(xg @ W0.T + b0) * np.sqrt(2.0) @ W1.T + b1 + xg)
+        o2 = go + 4 * GSZ
+        out[b, 16] = lrelu(xg @ take(o2, W, (D, D)).T + take(o2 + W, D, (D,))) * np.sqrt(2.0)
+    assert o2 + W + D == P.size
+    np.testing.assert_allclose(out, ws_ref[:, :, 0].double().numpy(), rtol=1e-5, atol=1e-6)
