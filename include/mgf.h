@@ -34,9 +34,13 @@ int mgf_version(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches claim) */
 int64_t mgf_launch_count(void);
 /* Element type of the 16-bit FORWARD tensors of the engine kernels below (activations, forward GEMM operands, cached LPIPS target
- * features): MGF_BF16 (default) or MGF_F16.  Gradient tensors are always bf16.  Process-wide setting, read at launch time. */
+ * features): MGF_F16 (default: the parity-green mode) or MGF_BF16.  Gradient tensors are always bf16.  Process-wide setting, read at launch time. */
 int mgf_set_forward_dtype(int dtype);
 int mgf_get_forward_dtype(void);
+/* fp16-forward mode stores saturate at +-65504; kernels that write forward activations (conv_tc epilogue, attention, skip FIR+add,
+ * weight modulation, channel scaling) OR 1 into a per-device flag when a value was outside that range.  Reads the flag (synchronises
+ * `stream`), optionally clears it.  A set flag means: results are clipped -- switch to MGF_BF16 forward storage for this checkpoint. */
+int mgf_fp16_overflow_read(int* flag_host, int reset, void* stream);
 
 /* ---- bias_act ---------------------------------------------------------------------------------------
  * Replaces bias_act_plugin.bias_act (torch_utils/ops/bias_act.cpp:24-82, kernel bias_act.cu:15-139).

@@ -23,6 +23,7 @@ SIGNATURES = {
     "mgf_launch_count": (c_int64, []),
     "mgf_set_forward_dtype": (c_int, [c_int]),
     "mgf_get_forward_dtype": (c_int, []),
+    "mgf_fp16_overflow_read": (c_int, [ctypes.POINTER(c_int), c_int, c_void_p]),
     "mgf_bias_act": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_float, c_float, c_int64, c_int64, c_int64, c_void_p]),
     "mgf_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
@@ -128,9 +129,15 @@ def i32x(*v):
     return (c_int32 * len(v))(*v)
 
 
+DEFAULT_FORWARD_DTYPE = "fp16"      # what a freshly loaded library is in (runtime.cu)
+
+
 def set_forward_dtype(name):
-    """'bf16' (default) or 'fp16': element type of the engine's forward activations / forward GEMM operands (gradients stay bf16).
-    fp16 has the same tensor-core rate and 8x finer rounding (meets the 1e-2 image tolerance); bf16 has the fp32 exponent range."""
+    """'fp16' (default) or 'bf16': element type of the engine's forward activations / forward GEMM operands (gradients stay bf16).
+    fp16 has the same tensor-core rate and 8x finer rounding: it is the mode that meets the parity bars (images within 1e-2 max-abs,
+    per-step loss within 1e-3 of the fp32 reference, tests/test_fullsize_parity_gpu.py); stores saturate at +-65504 and raise a device
+    flag (check_fp16_overflow).  bf16 has the fp32 exponent range and ~4e-2 image error: an explicit opt-in for checkpoints whose
+    activations overflow fp16."""
     code = {"bf16": BF16, "fp16": F16}[name]
     check(lib().mgf_set_forward_dtype(code), "mgf_set_forward_dtype")
 
@@ -138,3 +145,18 @@ def set_forward_dtype(name):
 def forward_torch_dtype():
     import torch
     return torch.float16 if lib().mgf_get_forward_dtype() == F16 else torch.bfloat16
+
+
+def fp16_overflow(device=None, reset=True):
+    """True if an fp16-forward store saturated since the last reset (synchronises the current stream)."""
+    v = c_int(0)
+    import torch
+    with torch.cuda.device(device):
+        check(lib().mgf_fp16_overflow_read(ctypes.byref(v), int(reset), stream_ptr(device)), "mgf_fp16_overflow_read")
+    return bool(v.value)
+
+
+def check_fp16_overflow(device=None, who="tc engine"):
+    if fp16_overflow(device):
+        raise MgfError("%s: forward activations left the fp16 range (+-65504) and were clipped; results are not trustworthy. "
+                       "Select bf16 forward storage for this checkpoint: _lib.set_forward_dtype('bf16') / Projector(forward_dtype='bf16')." % who)

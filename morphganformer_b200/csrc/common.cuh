@@ -12,6 +12,7 @@ namespace mgf {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+unsigned int* overflow_flag();   // device word that fp16-forward stores OR a 1 into when a value left the fp16 range (runtime.cu)
 bool fwd_f16();   // true when forward activations / forward GEMM operands are IEEE fp16 (mgf_set_forward_dtype)
 
 #define MGF_FAIL(code, ...) do { ::mgf::set_error(__VA_ARGS__); return (code); } while (0)
@@ -75,6 +76,10 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));     // first source -> upper half
   return r;
 }
+// fp16 overflow guard: kernels that store forward activations keep a running max |v| of what they pack (one FMNMX per value) and raise
+// the library's device flag if it left the fp16 range (the store itself saturates).  Read with mgf_fp16_overflow_read.
+constexpr float F16_MAX = 65504.f;
+__device__ __forceinline__ void ovf_commit(unsigned int* flag, float mx) { if (flag && !(mx <= F16_MAX)) atomicOr(flag, 1u); }
 __device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
   return f16 ? pack_f16_sat(a, b) : pack_bf16(a, b);
 }

@@ -61,6 +61,7 @@ struct alignas(64) Params {
   int tiles_hw;      // halo kernel: tiles per image (tilesW * tilesH)
   long long noise_bstride;       // elements between per-sample noise planes (0: one plane for all samples)
   int superpix;                  // output rows are PAIRS of pixels (32+32 channels): noise differs between the two 32-column halves
+  unsigned int* ovf;             // fp16 overflow flag word (nullptr unless the output is an fp16 forward tensor)
   int x_tma; uint32_t x_bytes;   // X tile arrives by TMA (one 64/32-channel group per tile) instead of per-thread strided loads
 };
 
@@ -182,6 +183,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
       const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
       const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
       const long long obase = pix * p.OC + co0;
+      float ovf_mx = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         uint32_t raw[32];
@@ -292,6 +294,10 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           if (r == 0) tma_store_wait_read<NSTG - 1>();     // (x_tma: the caller already did this before loading X into it)
           group_sync(group);
         }
+        if (p.ovf) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) ovf_mx = fmaxf(ovf_mx, fabsf(v[j]));
+        }
         {
           uint8_t* row = stg + r * (GW32 * 64);
 #pragma unroll
@@ -310,6 +316,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           if (r == 0) tma_store_4d(&p.omap[phase_idx], stg, co0 + (c / GW32) * (GW32 * 32), t.x0, t.y0, t.b0);
         }
       }
+      ovf_commit(p.ovf, ovf_mx);
 }
 
 template <int BN>
@@ -823,6 +830,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     const uint32_t fmt = (f16 && d->ab_fwd) ? 0u : 1u;
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(HBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
+    p.ovf = p.out_f16 ? overflow_flag() : nullptr;
     if (int e = encode_out_maps(p, d, HBN, 8, 16, 1)) return e;
     if (int e = encode_x_map(p, d, HBN, 8, 16, 1, 128)) return e;
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
@@ -887,6 +895,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     const uint32_t fmt = (f16 && d->ab_fwd) ? 0u : 1u;      // InstrDescriptor a_format/b_format: 0 = F16, 1 = BF16
     p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
+    p.ovf = p.out_f16 ? overflow_flag() : nullptr;
   }
   if (int e = encode_out_maps(p, d, BN, TW, TH, TB)) return e;
   if (int e = encode_x_map(p, d, BN, TW, TH, TB, p.rows)) return e;

@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(256) style_bwd_kernel(const float* ds, const f
 
 // ---- per-sample operand weights: out[b][t][n][k] = base[t][n][k] * rs[b][n % nmod] * cs[b][k]   (bf16)
 __global__ void __launch_bounds__(256) modulate_kernel(const float* base, const float* rs, int nmod, const float* cs,
-                                                       __nv_bfloat16* out, long long TN, int K, int NT, bool of16) {
+                                                       __nv_bfloat16* out, long long TN, int K, int NT, bool of16, unsigned int* ovf) {
   const long long b = blockIdx.y;
+  float mx = 0.f;
   const long long per = TN * K;
   const int k4 = K >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TN * k4; i += (long long)gridDim.x * blockDim.x) {
@@ -102,16 +103,20 @@ __global__ void __launch_bounds__(256) modulate_kernel(const float* base, const 
     float4 c = make_float4(1.f, 1.f, 1.f, 1.f);
     if (cs) c = *reinterpret_cast<const float4*>(cs + b * K + k);
     uint2 o;
-    o.x = pack16(w.x * r * c.x, w.y * r * c.y, of16);
-    o.y = pack16(w.z * r * c.z, w.w * r * c.w, of16);
+    const float o0 = w.x * r * c.x, o1 = w.y * r * c.y, o2 = w.z * r * c.z, o3 = w.w * r * c.w;
+    mx = fmaxf(fmaxf(mx, fmaxf(fabsf(o0), fabsf(o1))), fmaxf(fabsf(o2), fabsf(o3)));
+    o.x = pack16(o0, o1, of16);
+    o.y = pack16(o2, o3, of16);
     *reinterpret_cast<uint2*>(out + b * per + row * K + k) = o;
   }
+  ovf_commit(ovf, mx);
 }
 
 // ---- per-(sample, channel) scaling of an NHWC 16-bit tensor: out[b,p,c] = x[b,p,c] * sc[b,c]   (activation-side modulation for
 // the low-resolution layers, where per-sample weight tensors would dwarf the activations)
-__global__ void __launch_bounds__(256) scale_channels_kernel(const __nv_bfloat16* x, const float* sc, __nv_bfloat16* out, long long HW, int C, bool f16) {
+__global__ void __launch_bounds__(256) scale_channels_kernel(const __nv_bfloat16* x, const float* sc, __nv_bfloat16* out, long long HW, int C, bool f16, unsigned int* ovf) {
   const int b = blockIdx.y, vecs = C / 8;
+  float mx = 0.f;
   const long long total = HW * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % vecs);
@@ -121,10 +126,14 @@ __global__ void __launch_bounds__(256) scale_channels_kernel(const __nv_bfloat16
     const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
     const float2 a = unpack16(w4[0], f16), bq = unpack16(w4[1], f16), c = unpack16(w4[2], f16), d = unpack16(w4[3], f16);
     uint4 o;
-    o.x = pack16(a.x * s0.x, a.y * s0.y, f16); o.y = pack16(bq.x * s0.z, bq.y * s0.w, f16);
-    o.z = pack16(c.x * s1.x, c.y * s1.y, f16); o.w = pack16(d.x * s1.z, d.y * s1.w, f16);
+    const float v[8] = {a.x * s0.x, a.y * s0.y, bq.x * s0.z, bq.y * s0.w, c.x * s1.x, c.y * s1.y, d.x * s1.z, d.y * s1.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) mx = fmaxf(mx, fabsf(v[j]));
+    o.x = pack16(v[0], v[1], f16); o.y = pack16(v[2], v[3], f16);
+    o.z = pack16(v[4], v[5], f16); o.w = pack16(v[6], v[7], f16);
     *reinterpret_cast<uint4*>(out + off) = o;
   }
+  ovf_commit(ovf, mx);
 }
 
 // ---- tiny batched GEMM: out[b,m,n] = sum_k A[b,m,k] * Bm[n,k] (+ bias[n]); A strided (sAb, sAm), optional accumulate into out
@@ -496,7 +505,8 @@ extern "C" int mgf_modulate_weights(const float* base, const float* rs, int nmod
   if (B <= 0) return 0;
   const long long TN = T * NT;
   dim3 grid(grid_for(TN * (K / 4), 256, 4), B);
-  modulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(base, rs, nmod > 0 ? nmod : 1, cs, (__nv_bfloat16*)out, TN, (int)K, (int)NT, out_fwd && fwd_f16());
+  modulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(base, rs, nmod > 0 ? nmod : 1, cs, (__nv_bfloat16*)out, TN, (int)K, (int)NT, out_fwd && fwd_f16(),
+                                                          (out_fwd && fwd_f16()) ? overflow_flag() : nullptr);
   MGF_CHECK_LAUNCH("modulate_weights");
   return 0;
 }
@@ -608,7 +618,8 @@ extern "C" int mgf_scale_channels(const void* x, const float* sc, void* out, int
   if (C % 8) MGF_FAIL(MGF_E_SHAPE, "scale_channels: C must be a multiple of 8");
   if (B <= 0 || HW <= 0) return 0;
   dim3 grid(grid_for(HW * (C / 8), 256, 8), B);
-  scale_channels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, sc, (__nv_bfloat16*)out, HW, C, is_fwd && fwd_f16());
+  scale_channels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, sc, (__nv_bfloat16*)out, HW, C, is_fwd && fwd_f16(),
+                                                                      (is_fwd && fwd_f16()) ? overflow_flag() : nullptr);
   MGF_CHECK_LAUNCH("scale_channels");
   return 0;
 }

@@ -444,7 +444,10 @@ __global__ void __launch_bounds__(256) adam_noise_kernel(float* latent, const fl
                                                          int noise_rows, float* latent_n, const float* sched, const int* step_ptr,
                                                          float beta1, float beta2, float eps, float wd, long long n) {
   const int step = *step_ptr;                 // 0-based index of the step being applied
-  const float lr = sched[2 * step], ns = sched[2 * step + 1];
+  // sched has noise_rows rows (one per scheduled step): a launch past the schedule's end re-uses its last row instead of reading
+  // beyond the tensor (the host API refuses to step past the end; this bounds a replayed CUDA graph as well)
+  const int srow = (noise_rows > 0 && step >= noise_rows) ? noise_rows - 1 : step;
+  const float lr = sched[2 * srow], ns = sched[2 * srow + 1];
   const float t = (float)(step + 1);
   const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
   const float* noise_next = (noise_all && step + 1 < noise_rows) ? noise_all + (long long)(step + 1) * n : nullptr;

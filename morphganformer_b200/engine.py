@@ -98,6 +98,10 @@ class SynthesisEngine:
             raise _lib.MgfError("SynthesisEngine needs the module on a CUDA device (no CPU fallback)")
         if synthesis.architecture not in ("resnet", "skip", "orig"):
             raise NotImplementedError("tc engine: unknown synthesis architecture %r" % (synthesis.architecture,))
+        if synthesis.k != 17:
+            # VM buffers, mgf_attn_fwd/bwd and mgf_small_gemm are built for 16 local components + 1 global latent (GANformer default,
+            # reference networks.py:1185-1218 with k = components_num + 1); other counts would read Kf / Sc / maskbias out of bounds
+            raise NotImplementedError("tc engine: built for k = 17 latents (16 components + 1 global), got k = %d (use engine='ops')" % synthesis.k)
         self.res = synthesis.img_res
         self.k = synthesis.k
         self.num_ws = synthesis.num_ws
@@ -214,6 +218,8 @@ class SynthesisEngine:
             t = m.transformer
             if not (t.kmeans and t.parametric and t.num_heads == 1 and t.integration == "mul" and t.norm == "layer"):
                 raise NotImplementedError("tc engine: attention variant outside the GANformer-default configuration")
+            if t.to_len != 16 or t.centroids.shape[-2] != 16:
+                raise NotImplementedError("tc engine: attention over %d components (the kernels are built for 16)" % t.to_len)
             C = O
             rs = 1.0 / math.sqrt(float(t.size_head))
             Wq = t.to_queries.weight.detach().float() * float(t.to_queries.w_gain)
@@ -640,7 +646,10 @@ class SynthesisEngine:
             # train mode means attention dropout and w_avg tracking in the reference (networks.py:505-513, :928-929); this engine folds frozen
             # weights and is an inference / projection engine -- use engine="ops" for training-mode graphs
             raise NotImplementedError("tc engine: the synthesis network is in training mode; call G.eval() (or use engine='ops')")
-        return _SynthesisFn.apply(ws, self, mask, noise_mode, want_probs)
+        img = _SynthesisFn.apply(ws, self, mask, noise_mode, want_probs)
+        if _lib.forward_torch_dtype() == torch.float16 and not torch.cuda.is_current_stream_capturing():
+            _lib.check_fp16_overflow(self.dev, "G.synthesis (tc engine)")     # public entry: a clipped image must not pass silently
+        return img
 
 
 class _SynthesisFn(torch.autograd.Function):
@@ -672,9 +681,9 @@ def smoke():
         img.square().mean().backward()
         torch.cuda.synchronize()
     finally:
-        _lib.set_forward_dtype("bf16")
+        _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)
     G.synthesis.engine = "ops"
     ref, _ = G.synthesis(ws.detach(), pos=G.pos, mask=mask, noise_mode="const", return_att_maps=False)
     err, rng = (img.detach() - ref).abs().max().item(), max(1.0, ref.abs().max().item())
-    assert err < 1e-2 * rng, "tc engine deviates from the ops engine: %g of range %g" % (err, rng)
+    assert err < 1e-2, "tc engine deviates from the ops engine: %g of range %g" % (err, rng)
     print("smoke ok: tc engine 64x64 fwd+bwd, max|img_tc - img_fp32| = %.3g (range %.3g), |dws| = %.3g" % (err, rng, ws.grad.abs().max().item()))

@@ -6,7 +6,8 @@ What the reference offers (loader.py:40-56 `load_network_pkl`, :182-246 the TF->
 * `load_network_pkl(f)` / `load_network(path)` -- reads a snapshot pickle `{G, D, Gs}`.  PyTorch snapshots hold
   `persistence`-decorated modules: each object is pickled as `_reconstruct_persistent_obj(meta)` with `meta.state` = the module's
   `__dict__` and `meta.module_src` = the source text of its defining module.  The reference re-executes that source; this loader
-  does NOT execute anything from the file: a restricted unpickler turns every persistent object into an inert `PersistentStub`,
+  does NOT execute anything from the file: a restricted unpickler (explicit (module, name) allowlist of tensor / ndarray /
+  container constructors, `_allowed_globals`) turns every persistent object into an inert `PersistentStub`,
   the parameter/buffer tree is flattened to a `state_dict`, and the generator is rebuilt from `init_kwargs` with this package's
   `training.networks.Generator` (same parameter names, so `load_state_dict(strict=True)` is the parity check).
   TensorFlow snapshots (`dnnlib.tflib.network.Network` triples) go through `convert_tf_generator`.
@@ -86,13 +87,59 @@ def _reconstruct(meta):
     return PersistentStub(meta)
 
 
-_ALLOWED_PREFIXES = ("torch", "numpy", "collections", "_codecs", "copyreg")
+def _load_storage_from_bytes(b):
+    """Stand-in for torch.storage._load_from_bytes (how a pickled tensor's storage arrives): the nested archive is read with
+    torch's weights-only unpickler, so it cannot name arbitrary globals either."""
+    return torch.load(io.BytesIO(b), weights_only=True)
+
+
+def _allowed_globals():
+    """Explicit (module, name) -> object allowlist: tensor / ndarray / container constructors only.  Everything else in a checkpoint is
+    refused -- a prefix test on the top-level package is not enough (numpy.testing._private.utils.runstring, torch.utils.collect_env.run
+    and friends execute code)."""
+    import copyreg
+    import _codecs
+    table = {
+        ("collections", "OrderedDict"): collections.OrderedDict,
+        ("_codecs", "encode"): _codecs.encode,
+        ("copyreg", "_reconstructor"): copyreg._reconstructor,
+        ("torch._utils", "_rebuild_tensor_v2"): torch._utils._rebuild_tensor_v2,
+        ("torch._utils", "_rebuild_tensor"): torch._utils._rebuild_tensor,
+        ("torch._utils", "_rebuild_parameter"): torch._utils._rebuild_parameter,
+        ("torch.storage", "_load_from_bytes"): _load_storage_from_bytes,
+        ("torch", "Size"): torch.Size,
+        ("torch", "device"): torch.device,
+        ("torch.nn.parameter", "Parameter"): torch.nn.Parameter,
+        ("torch.nn.modules.container", "ModuleList"): torch.nn.ModuleList,
+        ("torch.nn.modules.container", "ModuleDict"): torch.nn.ModuleDict,
+        ("torch.nn.modules.container", "Sequential"): torch.nn.Sequential,
+        ("torch.nn.modules.container", "ParameterList"): torch.nn.ParameterList,
+        ("torch.nn.modules.dropout", "Dropout"): torch.nn.Dropout,
+        ("torch.nn.modules.linear", "Identity"): torch.nn.Identity,
+        ("numpy", "ndarray"): np.ndarray,
+        ("numpy", "dtype"): np.dtype,
+    }
+    for name in ("float16", "float32", "float64", "bfloat16", "int8", "uint8", "int16", "int32", "int64", "bool"):
+        table[("torch", name)] = getattr(torch, name)                 # torch.dtype objects pickle as getattr(torch, name)
+    for name in ("FloatStorage", "DoubleStorage", "HalfStorage", "BFloat16Storage", "LongStorage", "IntStorage", "ShortStorage",
+                 "CharStorage", "ByteStorage", "BoolStorage"):
+        if hasattr(torch, name):
+            table[("torch", name)] = getattr(torch, name)
+    import numpy.core.multiarray as _ma_old      # numpy 1.x pickles name numpy.core.*, numpy 2.x numpy._core.*: same functions
+    for mod in ("numpy.core.multiarray", "numpy._core.multiarray"):
+        table[(mod, "_reconstruct")] = _ma_old._reconstruct
+        table[(mod, "scalar")] = _ma_old.scalar
+    return table
+
+
+_ALLOWED = None
 
 
 class _SafeUnpickler(pickle.Unpickler):
-    """Resolves only tensor/ndarray/container constructors; maps the reference's own classes to inert stubs."""
+    """Resolves only the allowlisted tensor/ndarray/container constructors; maps the reference's own classes to inert stubs."""
 
     def find_class(self, module, name):
+        global _ALLOWED
         if module == "torch_utils.persistence" and name == "_reconstruct_persistent_obj":
             return _reconstruct
         if module == "dnnlib.tflib.network" and name == "Network":
@@ -101,9 +148,15 @@ class _SafeUnpickler(pickle.Unpickler):
             return EasyDict
         if module == "builtins" and name in ("set", "frozenset", "dict", "list", "tuple", "slice", "complex", "bytearray", "object"):
             return super().find_class(module, name)
-        if module.split(".")[0] in _ALLOWED_PREFIXES:
-            return super().find_class(module, name)
-        raise pickle.UnpicklingError("refusing to import %s.%s from a checkpoint" % (module, name))
+        if _ALLOWED is None:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                _ALLOWED = _allowed_globals()
+        obj = _ALLOWED.get((module, name))
+        if obj is None:
+            raise pickle.UnpicklingError("refusing to import %s.%s from a checkpoint" % (module, name))
+        return obj
 
 
 def named_params_and_buffers(module):

@@ -54,6 +54,7 @@ class LpipsEngine:
         self._wf16 = {}
         self.n1 = None
         self.target = None
+        self.generation = 0          # bumped by every forward / set_target: identifies whose activations the buffers hold
 
     def _wfwd(self, ci):
         dt = _lib.forward_torch_dtype()
@@ -105,6 +106,7 @@ class LpipsEngine:
     @torch.no_grad()
     def set_target(self, target):
         """target [B,3,R,R] fp32 in [-1,1]; caches the unit-normalised tap features (the reference recomputes them every step)."""
+        self.generation += 1
         target = target.to(self.dev, torch.float32)
         if getattr(self, "target", None) is not None and tuple(self.target.shape) == tuple(target.shape):
             self.target.copy_(target)                   # keep addresses stable (CUDA-graph replay of the step)
@@ -133,6 +135,7 @@ class LpipsEngine:
     def forward(self, img, want_mse=True):
         """img [B,3,R,R] fp32 -> (lpips [B], mse_sum [B] = sum of squared differences to the target)."""
         assert self.n1 is not None, "call set_target first"
+        self.generation += 1
         img = img.contiguous()
         B = img.shape[0]
         s = _lib.stream_ptr(self.dev)
@@ -211,15 +214,16 @@ class PerceptualLoss(torch.nn.Module):
         if model != "net-lin" or net not in ("vgg", "vgg16"):
             raise NotImplementedError("only the LPIPS-VGG16 ('net-lin', 'vgg') variant is built (SURVEY.md 8f rank 2)")
         self.engine = LpipsEngine(state_dict)
-        self._target_key = None
+        self._target_ref = None           # (the caller's target tensor itself, its _version): a strong reference, so the cached
+                                          # features can never be matched by a NEW tensor that re-uses a freed allocation's address
 
     def forward(self, pred, target, normalize=False):
+        cached = self._target_ref
+        if cached is None or cached[0] is not target or cached[1] != target._version:
+            self.engine.set_target(2 * target - 1 if normalize else target)
+            self._target_ref = (target, target._version)
         if normalize:
-            target, pred = 2 * target - 1, 2 * pred - 1
-        key = (target.data_ptr(), tuple(target.shape), target._version)
-        if key != self._target_key:
-            self.engine.set_target(target)
-            self._target_key = key
+            pred = 2 * pred - 1
         return _LpipsFn.apply(pred, self.engine).reshape(-1, 1, 1, 1)
 
 
@@ -228,10 +232,14 @@ class _LpipsFn(torch.autograd.Function):
     def forward(ctx, pred, eng):
         val, _ = eng.forward(pred.detach().float(), want_mse=False)
         ctx.eng = eng
+        ctx.generation = eng.generation          # the engine keeps ONE set of activations: a later forward invalidates this graph
         return val.clone()
 
     @staticmethod
     def backward(ctx, dval):
         eng = ctx.eng
+        if ctx.generation != eng.generation:
+            raise RuntimeError("PerceptualLoss: backward of a forward pass whose activations were overwritten by a later forward / set_target "
+                               "call on the same module (the engine is single-slot: call backward before the next forward, or use one module per graph)")
         dimg = eng.backward(dval.contiguous().float(), 0.0)
         return dimg, None

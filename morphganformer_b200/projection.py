@@ -131,6 +131,8 @@ class Projector:
     def step(self, use_graph=True):
         """One projection step for the whole batch; no host sync.  Returns the per-image loss tensor (device).
         After capture() the step is one CUDA-graph replay (use_graph=False forces the eager launch sequence)."""
+        if self.i >= self.steps:
+            raise RuntimeError("Projector: step %d is past the %d-step schedule this projector was built for (reset() starts a new job)" % (self.i, self.steps))
         if use_graph and self.graph is not None:
             self.graph.replay()
             self.i += 1
@@ -217,8 +219,13 @@ class Projector:
         return syn._tc
 
     def run(self, steps=None):
-        for _ in range(steps or self.steps):
+        n = self.steps - self.i if steps is None else int(steps)
+        if self.i + n > self.steps:
+            raise RuntimeError("Projector.run: %d more steps from step %d exceed the %d-step schedule" % (n, self.i, self.steps))
+        for _ in range(n):
             self.step()
+        if self.engine == "tc" and _lib.forward_torch_dtype() == torch.float16:
+            _lib.check_fp16_overflow(self.dev, "Projector.run")      # one stream sync at the end of the job, none inside the steps
         return dict(latent=self.latent, best_latent=self.best_latent, best_loss=self.best_loss, losses=self.losses)
 
 

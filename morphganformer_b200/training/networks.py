@@ -231,6 +231,10 @@ class TransformerLayer(torch.nn.Module):
             raise NotImplementedError("gated attention (--ltnt-gate/--img-gate)")
         if kmeans and iterative:
             raise NotImplementedError("iterative (non-parametric) centroids")
+        if kmeans and kmeans_iters != 1:
+            # iterations after the first re-estimate the centroids from the assignments (reference networks.py:776-789); only the
+            # GANformer default (one iteration) is built -- refuse instead of silently producing different images
+            raise NotImplementedError("kmeans_iters = %r (only 1 is built)" % (kmeans_iters,))
         self.dim, self.pos_dim = dim, pos_dim
         self.from_len, self.to_len, self.from_dim, self.to_dim = from_len, to_len, from_dim, to_dim
         self.num_heads, self.size_head = num_heads, int(dim / num_heads)

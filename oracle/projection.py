@@ -61,4 +61,6 @@ def project(g_sd, lpips_sd, target, latent_mean, latent_std, step_noise, res, st
         per_img.sum().backward()
         opt.step()
         losses.append(per_img.detach().clone())
-    return dict(latent=latent.detach().clone(), losses=torch.stack(losses))
+        lat_n_hist.append(latent_n.detach().clone())
+    # latent_n [steps,B,k,32]: the noisy latent each step's loss was evaluated at (lets a test feed the same inputs step by step)
+    return dict(latent=latent.detach().clone(), losses=torch.stack(losses), latent_n=torch.stack(lat_n_hist))

@@ -18,3 +18,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+
+
+@pytest.fixture(autouse=True)
+def _restore_forward_dtype(request):
+    """GPU tests may switch the engine's 16-bit forward type; every test starts from and returns to the library default."""
+    yield
+    if "gpu" in request.keywords:
+        import torch
+        if torch.cuda.is_available():
+            from morphganformer_b200 import _lib
+            _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)

@@ -5,6 +5,7 @@ only).  Run:  python tests/golden/make_golden.py      (records torch version + t
                        in tests/util.py
   gen32_golden.npz     reference Generator (GANformer-default, res 32, channel_base 512 / max 32, seed 0, randomised
                        noise strengths/biases): state-dict checksum, ws, img, att map sample, d(mean img^2)/d ws, d/dz
+  gen256_golden.npz    BASELINE configs[0]: res 256, default widths, batch 1: image, ws, d(ws), d(z)   (python make_golden.py --gen256)
   gen64_golden.npz     same at res 64 with the full 512-channel widths (checksum + outputs only; weights come from the seed)
   lpips_golden.npz     reference PNetLin (vgg, random torchvision init seed 4 + shipped lin weights) distances
   lpips_lin_vgg_v0.1.npz  the five 1x1 `lin` layers shipped in the reference (lpips/weights/v0.1/vgg.pth, 1472 floats)
@@ -62,15 +63,15 @@ def ops_golden(ref):
     print("ops_golden:", len(out), "arrays")
 
 
-def gen_golden(ref, res, cb, cm, fname, with_grads):
+def gen_golden(ref, res, cb, cm, fname, with_grads, batch=2):
     G = util.randomize(refimport.build_generator(res, seed=0, channel_base=cb, channel_max=cm), 1)
     sd = {k: v.detach() for k, v in G.state_dict().items()}
-    z = util.case_tensor((2, 17, 32), 50)
+    z = util.case_tensor((batch, 17, 32), 50)
     out = dict(z=z.numpy(), sd_checksum=np.array(util.sd_checksum(sd)))
     zz = z.clone().requires_grad_(with_grads)
-    ws = G.mapping(zz, None, pos=G.pos, mask=torch.ones(2, 16))
+    ws = G.mapping(zz, None, pos=G.pos, mask=torch.ones(batch, 16))
     wsl = ws.detach().clone().requires_grad_(with_grads)
-    img, att = G.synthesis(wsl, pos=G.pos, mask=torch.ones(2, 16), noise_mode="const")
+    img, att = G.synthesis(wsl, pos=G.pos, mask=torch.ones(batch, 16), noise_mode="const")
     out.update(ws=ws.detach().numpy(), img=img.detach().numpy(), att_shape=np.array(att.shape), att_sample=att.detach()[0, :, :, 0, ::8, ::8].numpy())
     if with_grads:
         loss = img.square().mean()
@@ -98,6 +99,9 @@ def lpips_golden(ref):
 
 if __name__ == "__main__":
     ref = refimport.load()
+    if "--gen256" in sys.argv:      # BASELINE.json configs[0]: generator forward at 256x256, batch 1, default widths (+ d(ws) of mean(img^2))
+        gen_golden(ref, 256, 32768, 512, "gen256_golden.npz", True, batch=1)
+        sys.exit(0)
     ops_golden(ref)
     gen_golden(ref, 32, 512, 32, "gen32_golden.npz", True)
     gen_golden(ref, 64, 32768, 512, "gen64_golden.npz", False)

@@ -5,7 +5,9 @@ plus the image that reference generator produces for a fixed z, so the loader te
 The pickled `module_src` strings (the reference's source text, which its own loader re-executes) are blanked before writing:
 this repo's loader never executes them, and reference sources must not be copied into the repo.
 
-    python tests/golden/make_golden_ckpt.py
+    python tests/golden/make_golden_ckpt.py                 # ref_snapshot_16.pkl (resnet architecture)
+    python tests/golden/make_golden_ckpt.py 64 skip         # ref_snapshot_64_skip.pkl: 64x64, architecture='skip' (what TensorFlow snapshots
+                                                            # convert to, reference loader.py:129) -- the fixture the GPU loader test runs
 """
 import os, pickle, sys
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -16,7 +18,10 @@ import util
 
 ref = refimport.load()
 from torch_utils import persistence          # the reference's (sys.path set by refimport.load)
-Gr = util.randomize(refimport.build_generator(16, seed=11, channel_base=512, channel_max=32), 12)
+RES = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+ARCH = sys.argv[2] if len(sys.argv) > 2 else "resnet"
+STEM = "ref_snapshot_%d%s" % (RES, "" if ARCH == "resnet" else "_" + ARCH)
+Gr = util.randomize(refimport.build_generator(RES, seed=11, channel_base=512 if RES == 16 else 2048, channel_max=32, architecture=ARCH), 12)
 assert persistence.is_persistent(Gr)
 
 # blank the embedded source text: patch the reduce meta on the fly
@@ -41,7 +46,7 @@ assert b"def modulated_conv2d" not in out and b"class Generator" not in out
 z = util.case_tensor((2, 17, 32), 13)
 with torch.no_grad():
     img = Gr(z, noise_mode="const")[0]
-open(os.path.join(HERE, "ref_snapshot_16.pkl"), "wb").write(out)
-np.savez_compressed(os.path.join(HERE, "ref_snapshot_16_io.npz"), z=z.numpy(), img=img.numpy(),
+open(os.path.join(HERE, STEM + ".pkl"), "wb").write(out)
+np.savez_compressed(os.path.join(HERE, STEM + "_io.npz"), z=z.numpy(), img=img.numpy(),
                     checksum=np.float64(util.sd_checksum({k: v.detach() for k, v in Gr.state_dict().items()})))
 print("wrote", len(out), "bytes; img", tuple(img.shape), "torch", torch.__version__)

@@ -57,7 +57,7 @@ def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd):
         assert rel(dVM, gVM) < 1.5e-2, rel(dVM, gVM)
         assert rel(R, Rr) < 1.5e-2, rel(R, Rr)
     finally:
-        _lib.set_forward_dtype("bf16")
+        _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)
 
 
 def test_attn_rejects_bad_shapes():

@@ -7,9 +7,14 @@ from oracle import ganformer
 import util
 
 pytestmark = pytest.mark.gpu
-# (max-abs as a fraction of the image range, relative RMS).  fp16-forward mode meets the north_star's 1e-2 max-abs bar;
-# bf16 forward storage does not (2^-9 rounding of every stored tile, ~25 deep) -- its measured envelope is asserted instead.
+# (max-abs, relative RMS).  fp16-forward mode (the library default) meets the north_star's 1e-2 max-abs bar as an ABSOLUTE bound;
+# bf16 forward storage (opt-in for checkpoints that overflow fp16) does not (2^-9 rounding of every stored tile, ~25 deep) -- its
+# measured envelope, relative to the image range, is asserted instead.
 TOL = {"bf16": (4e-2, 2e-2), "fp16": (1e-2, 3e-3)}
+
+
+def _img_bound(fwd, ref):
+    return TOL[fwd][0] * (1.0 if fwd == "fp16" else max(1.0, ref.abs().max().item()))
 
 
 @pytest.fixture(params=["bf16", "fp16"])
@@ -17,7 +22,6 @@ def fwd_dtype(request):
     from morphganformer_b200 import _lib
     _lib.set_forward_dtype(request.param)
     yield request.param
-    _lib.set_forward_dtype("bf16")
 
 
 def _setup(res, cb, cm, B, seed=0):
@@ -39,8 +43,7 @@ def test_tc_engine_image_within_tolerance(cfg, fwd_dtype):
     e = img.cpu() - ref
     err, rel_rms = e.abs().max().item(), (e.square().mean().sqrt() / ref.square().mean().sqrt()).item()
     print("img max-abs err", err, "scale", ref.abs().max().item(), "rel rms", rel_rms)
-    maxabs, relrms = TOL[fwd_dtype]
-    assert err < maxabs * max(1.0, ref.abs().max().item()) and rel_rms < relrms, (fwd_dtype, err, rel_rms)
+    assert err < _img_bound(fwd_dtype, ref) and rel_rms < TOL[fwd_dtype][1], (fwd_dtype, err, rel_rms)
 
 
 def test_tc_engine_grads_wrt_ws(fwd_dtype):
@@ -62,10 +65,14 @@ def test_tc_engine_grads_wrt_ws(fwd_dtype):
         e = (g[:, :, l] - gref[:, :, l]).abs().max().item(); s = gref[:, :, l].abs().max().item()
         print("ws slot %2d  err %.3e  scale %.3e" % (l, e, s))
     # bf16 envelope: deepest slot (4x4 stem, 16 pixels, demodulation term cancels most of the direct style gradient) ~10 %
-    assert err < 0.15 * scale, "dws err %g vs scale %g" % (err, scale)
     cos = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
-    print("dws cosine", cos, fwd_dtype)
-    assert cos > 0.998, cos
+    rel_l2 = ((g - gref).norm() / gref.norm()).item()
+    print("dws cosine", cos, "rel-L2", rel_l2, "max err / scale", err / scale, fwd_dtype)
+    # fp16 forward storage: relative L2 within 2e-2 (the bound tests/test_fullsize_parity_gpu.py holds at 256^2 / 1024^2);
+    # bf16 forward storage: its measured envelope
+    assert rel_l2 < (2e-2 if fwd_dtype == "fp16" else 6e-2), rel_l2
+    assert err < (0.05 if fwd_dtype == "fp16" else 0.15) * scale, "dws err %g vs scale %g" % (err, scale)
+    assert cos > (0.9998 if fwd_dtype == "fp16" else 0.998), cos
 
 
 def test_tc_engine_noise_none_and_mask():
@@ -101,11 +108,11 @@ def test_tc_engine_noise_random_matches_ops_engine_under_same_seed():
         G.synthesis.engine = "tc"
         other, _ = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="random")
     finally:
-        _lib.set_forward_dtype("bf16")
+        _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)
     ref, gref = out["ops"]; img, g = out["tc"]
     rng = max(1.0, ref.abs().max().item())
-    assert (img - ref).abs().max().item() < 1e-2 * rng
-    assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.999
+    assert (img - ref).abs().max().item() < 1e-2                  # absolute (north_star), fp16 forward storage
+    assert ((g - gref).norm() / gref.norm()).item() < 2e-2
     assert (other - img).abs().max().item() > 1e-3 * rng          # a different seed really gives different noise
     assert (img[0] - img[1]).abs().max().item() > 0               # and the planes differ per sample
 
@@ -131,13 +138,13 @@ def test_full_size_1024_tc_engine_vs_exact_fp32_ops_engine():
         img, _ = G.synthesis(w1, pos=G.pos, mask=mask, noise_mode="const")
         g, = torch.autograd.grad((img - tgt).square().mean(), [w1])
     finally:
-        _lib.set_forward_dtype("bf16")
+        _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)
     e = (img.detach() - ref)
     rng = max(1.0, ref.abs().max().item())
     cos = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
     print("1024^2: max-abs %.4g of range %.3g, rel rms %.3g, dws cosine %.6f" % (e.abs().max().item(), rng, (e.square().mean().sqrt() / ref.square().mean().sqrt()).item(), cos))
-    assert e.abs().max().item() < 1e-2 * rng
-    assert cos > 0.999
+    assert e.abs().max().item() < 1e-2                            # absolute (north_star), fp16 forward storage
+    assert ((g - gref).norm() / gref.norm()).item() < 2e-2 and cos > 0.9999
 
 
 def test_tc_engine_attention_maps_match_ops_engine():
@@ -158,7 +165,7 @@ def test_tc_engine_attention_maps_match_ops_engine():
             _, att = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const", return_att_maps=True)
             _, none = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const")
     finally:
-        _lib.set_forward_dtype("bf16")
+        _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)
     assert tuple(none.shape) == (1,)
     assert tuple(att.shape) == tuple(att_ref.shape) and att.shape[1] == 16 and att.shape[-1] == res
     assert (att - att_ref).abs().max().item() < 5e-3
@@ -184,10 +191,10 @@ def test_tc_engine_other_resolutions_and_batches(res, B, cb, cm):
             g, = torch.autograd.grad((img - tgt).square().mean(), [w])
             out[eng] = (img.detach(), g)
     finally:
-        _lib.set_forward_dtype("bf16")
+        _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)
     ref, gref = out["ops"]; img, g = out["tc"]
     rng = max(1.0, ref.abs().max().item())
-    assert (img - ref).abs().max().item() < 1e-2 * rng
+    assert (img - ref).abs().max().item() < 1e-2          # absolute, fp16 forward storage
     assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.998
 
 
@@ -213,10 +220,10 @@ def test_tc_engine_skip_and_orig_architectures(arch):
             g, = torch.autograd.grad((img - tgt).square().mean(), [w])
             out[eng] = (img.detach(), g)
     finally:
-        _lib.set_forward_dtype("bf16")
+        _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)
     ref, gref = out["ops"]; img, g = out["tc"]
     rng = max(1.0, ref.abs().max().item())
-    assert (img - ref).abs().max().item() < 1e-2 * rng
+    assert (img - ref).abs().max().item() < 1e-2          # absolute, fp16 forward storage
     assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.998
 
 

@@ -1,0 +1,127 @@
+"""GPU parity at the BENCHMARKED sizes, with the north_star tolerances as written (absolute, not range-scaled):
+   * generated images within 1e-2 max-abs of the fp32 reference arithmetic (the CPU oracle, itself pinned to the real reference by
+     tests/golden/gen*_golden.npz incl. the 256^2 config-1 case and tests/test_oracle_vs_reference.py),
+   * d(ws) within 2e-2 relative L2,
+   * per-image projection loss (0.5 LPIPS-VGG + 0.5 MSE) and the LPIPS value within 1e-3 relative,
+for the library-default mode (fp16 forward storage) of the tcgen05 engine + LpipsEngine: 256^2 x 2 images (BASELINE configs 1/2 size)
+and 1024^2 x 1 image (configs 3-5 size, the bench generator).  The oracle costs ~2-4 s per case on the GPU box's host cores.
+Reference path: training/networks.py:1244-1264, 1024_example_percept_MSE.py:113-175, lpips/networks_basic.py:64-92."""
+import os
+import numpy as np
+import pytest
+import torch
+from oracle import ganformer, lpips_ref, projection as oproj
+import util
+
+pytestmark = pytest.mark.gpu
+
+IMG_ABS_TOL = 1e-2        # north_star: "generated images within 1e-2 max-abs" at 16-bit storage
+DWS_REL_L2_TOL = 2e-2
+LOSS_REL_TOL = 1e-3       # north_star: "per-step loss within 1e-3 relative"
+
+
+def _oracle_case(res, B):
+    torch.set_num_threads(os.cpu_count() or 1)
+    G = util.build_G(res, 0)
+    sd, lsd = util.state_dict_cpu(G), util.build_vgg_lpips_sd(4)
+    z = util.case_tensor((B, 17, 32), 31)
+    tgt = torch.tanh(util.case_tensor((B, 3, res, res), 32))
+    img, ws = ganformer.generator(sd, z.clone().requires_grad_(True), res)
+    ws.retain_grad()
+    mse = (img - tgt).square().mean(dim=[1, 2, 3])
+    lp = lpips_ref.lpips(lsd, img, tgt).reshape(B)
+    loss = 0.5 * lp + 0.5 * mse
+    loss.sum().backward()
+    return G, lsd, tgt, dict(img=img.detach(), ws=ws.detach(), dws=ws.grad.detach(), lpips=lp.detach(), mse=mse.detach(), loss=loss.detach())
+
+
+@pytest.mark.parametrize("res,B", [(256, 2), (1024, 1)])
+def test_tc_engine_and_lpips_engine_vs_oracle_at_benchmarked_size(res, B):
+    from morphganformer_b200 import _lib
+    from morphganformer_b200.lpips_engine import LpipsEngine
+    assert _lib.forward_torch_dtype() == torch.float16, "the parity-green mode must be the library default"
+    G, lsd, tgt, ref = _oracle_case(res, B)
+    Gc = G.cuda(); Gc.synthesis.engine = "tc"
+    w = ref["ws"].cuda().requires_grad_(True)
+    img, _ = Gc.synthesis(w, pos=Gc.pos, mask=torch.ones(B, 16, device="cuda"), noise_mode="const")
+    eng = LpipsEngine(lsd)
+    eng.set_target(tgt.cuda())
+    val, mse_sum = eng.forward(img.detach())
+    n = 3 * res * res
+    per = 0.5 * val + 0.5 * mse_sum / n
+    dimg = eng.backward(torch.full((B,), 0.5, device="cuda"), 0.5 * 2.0 / n)
+    img.backward(dimg)
+    err = (img.detach().cpu() - ref["img"]).abs().max().item()
+    g = w.grad.cpu()
+    dws_rel = ((g - ref["dws"]).norm() / ref["dws"].norm()).item()
+    rel = lambda a, b: ((a.cpu() - b).abs() / b.abs()).max().item()
+    r_lp, r_mse, r_loss = rel(val, ref["lpips"]), rel(mse_sum / n, ref["mse"]), rel(per, ref["loss"])
+    print("%d^2 x%d: image max-abs %.3g (range %.3g) | d(ws) rel-L2 %.3g | LPIPS rel %.2e | MSE rel %.2e | loss rel %.2e"
+          % (res, B, err, ref["img"].abs().max().item(), dws_rel, r_lp, r_mse, r_loss))
+    assert err <= IMG_ABS_TOL
+    assert dws_rel <= DWS_REL_L2_TOL
+    assert r_lp <= LOSS_REL_TOL and r_loss <= LOSS_REL_TOL and r_mse <= LOSS_REL_TOL
+
+
+def test_projector_step_at_1024_vs_oracle_loop():
+    """One full Projector step (mapping kernels -> tcgen05 synthesis -> LPIPS-VGG + MSE -> backward -> Adam) at 1024^2, one image, against
+    oracle.projection.project: per-image loss of step 0 and step 1 (i.e. after one Adam update through every gradient) within 1e-3."""
+    from morphganformer_b200.projection import Projector, latent_stats
+    res, B, steps = 1024, 1, 2
+    torch.set_num_threads(os.cpu_count() or 1)
+    G = util.build_G(res, 0)
+    gsd, lsd = util.state_dict_cpu(G), util.build_vgg_lpips_sd(4)
+    mean, std = latent_stats(util.case_tensor((2000, 17, 32), 70))
+    noise = util.case_tensor((steps, B, 17, 32), 71)
+    tgt = torch.tanh(util.case_tensor((B, 3, res, res), 72))
+    ref = oproj.project(gsd, lsd, tgt, mean, std, noise, res, steps, total_steps=1000)
+    P = Projector(G.cuda(), lsd, B, 1000, latent_mean=mean, latent_std=std, step_noise=torch.cat([noise, torch.zeros(998, B, 17, 32)]))
+    P.set_targets(tgt)
+    P.run(steps)
+    torch.cuda.synchronize()
+    got, want = P.losses[:steps].cpu(), ref["losses"]
+    rel = ((got - want).abs() / want.abs())
+    dz = (P.latent.cpu() - ref["latent"]).abs().max().item()
+    print("1024^2 projector: loss rel err per step %s; latent max diff after %d Adam steps %.3g" % (rel.flatten().tolist(), steps, dz))
+    assert rel.max().item() <= LOSS_REL_TOL
+    assert dz < 2e-2          # two Adam steps of lr ramp-up size: the sign pattern of the gradient must agree almost everywhere
+
+
+def test_fp16_overflow_guard_raises_instead_of_clipping_silently():
+    """fp16 forward storage saturates at 65504: a checkpoint whose activations leave that range must be reported (device flag read at the
+    public entry points), and bf16 forward storage must remain available for it."""
+    from morphganformer_b200 import _lib
+    G = util.build_G(64, 0, 2048, 64).cuda()
+    with torch.no_grad():
+        G.synthesis.b4.const.mul_(3e5)
+        for r in (8, 16, 32, 64):
+            blk = getattr(G.synthesis, f"b{r}")
+            blk.skip.weight.mul_(40.0)                      # the un-normalised resnet branch carries the blow-up to the output
+    ws = util.case_tensor((1, 17, G.num_ws, 32), 5).cuda()
+    G.synthesis.engine = "tc"
+    assert not _lib.fp16_overflow()
+    with pytest.raises(_lib.MgfError, match="fp16 range"):
+        G.synthesis(ws, pos=G.pos, mask=torch.ones(1, 16, device="cuda"), noise_mode="const")
+    assert not _lib.fp16_overflow()                          # reading cleared it
+    _lib.set_forward_dtype("bf16")
+    img, _ = G.synthesis(ws, pos=G.pos, mask=torch.ones(1, 16, device="cuda"), noise_mode="const")
+    assert torch.isfinite(img).all()
+
+
+def test_both_engines_vs_reference_golden_at_config1_size():
+    """BASELINE configs[0] (generator forward 256^2, batch 1) against vectors produced by the REAL reference (tests/golden/gen256_golden.npz,
+    make_golden.py --gen256): exact-fp32 ops engine within 1e-4, tcgen05 engine (default fp16 forward storage) within 1e-2, both absolute;
+    d(ws) of mean(img^2) within 1e-3 / 2e-2 relative L2."""
+    g = np.load(os.path.join(util.GOLDEN, "gen256_golden.npz"))
+    G = util.build_G(256, 0).cuda()
+    ref_img, ref_g = torch.from_numpy(g["img"]), torch.from_numpy(g["gws"])
+    mask = torch.ones(1, 16, device="cuda")
+    for engine, img_tol, g_tol in (("ops", 1e-4, 1e-3), ("tc", IMG_ABS_TOL, DWS_REL_L2_TOL)):
+        G.synthesis.engine = engine
+        ws = torch.from_numpy(g["ws"]).cuda().requires_grad_(True)
+        img = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const", return_att_maps=False)[0]
+        gws, = torch.autograd.grad(img.square().mean(), [ws])
+        err = (img.detach().cpu() - ref_img).abs().max().item()
+        grel = ((gws.cpu() - ref_g).norm() / ref_g.norm()).item()
+        print("256^2 vs reference golden, engine %s: image max-abs %.3g, d(ws) rel-L2 %.3g" % (engine, err, grel))
+        assert err <= img_tol and grel <= g_tol, (engine, err, grel)

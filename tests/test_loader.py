@@ -37,6 +37,37 @@ def test_unpickler_refuses_foreign_globals():
         loader.load_network_pkl(pickle.dumps(dict(G=Evil())))
 
 
+@pytest.mark.parametrize("target", ["numpy.testing._private.utils:runstring", "torch.utils.collect_env:run", "torch.storage:_load_from_bytes_nested",
+                                    "torch.hub:load", "numpy:load", "torch:load", "collections:namedtuple"])
+def test_unpickler_refuses_code_executing_members_of_allowed_packages(target, tmp_path):
+    """A prefix test on the top-level package is not enough: torch / numpy hold functions that run code.  Each of these pickles used
+    to execute its payload through load_network_pkl; all must now be refused without side effects."""
+    import importlib
+    marker = tmp_path / "pwned"
+    modname, fname = target.split(":")
+    if fname == "_load_from_bytes_nested":
+        # the storage hook is reachable, but its nested archive goes through torch's weights-only unpickler: a nested full pickle with a
+        # foreign global must fail instead of executing
+        class Inner:
+            def __reduce__(self):
+                return (os.system, ("touch %s" % marker,))
+        buf = io.BytesIO(); torch.save(Inner(), buf)
+        payload = (torch.storage._load_from_bytes, (buf.getvalue(),))
+    else:
+        fn = getattr(importlib.import_module(modname), fname)
+        args = {"runstring": ("open(%r, 'w').close()" % str(marker), {}), "run": ("touch %s" % marker,), "load": (str(marker),),
+                "namedtuple": ("X", "a b")}[fname]
+        payload = (fn, args)
+
+    class Evil:
+        def __reduce__(self):
+            return payload
+    with pytest.raises(Exception) as ei:
+        loader.load_network_pkl(pickle.dumps(dict(G=Evil())))
+    assert isinstance(ei.value, (pickle.UnpicklingError, RuntimeError)), ei.value
+    assert not marker.exists()
+
+
 def _fake_persistent_pickle(G):
     """Pickles `G` the way torch_utils/persistence.py:110-119 does, without the reference tree."""
     mod = types.ModuleType("torch_utils.persistence")
@@ -144,3 +175,29 @@ def test_copy_params_and_buffers():
     assert all(torch.equal(v, B.state_dict()[k]) for k, v in A.state_dict().items())
     with pytest.raises(KeyError):
         loader.copy_params_and_buffers({"pos": A.pos}, B, require_all=True)
+
+
+def test_skip_architecture_snapshot_fixture_loads_on_cpu():
+    """tests/golden/ref_snapshot_64_skip.pkl (make_golden_ckpt.py 64 skip): the architecture TensorFlow snapshots convert to."""
+    io_ = np.load(os.path.join(util.GOLDEN, "ref_snapshot_64_skip_io.npz"))
+    G = loader.load_network(os.path.join(util.GOLDEN, "ref_snapshot_64_skip.pkl"))["Gs"]
+    assert G.synthesis.architecture == "skip" and G.img_resolution == 64
+    sd = util.state_dict_cpu(G)
+    assert abs(util.sd_checksum(sd) - float(io_["checksum"])) < 1e-6 * abs(float(io_["checksum"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stem", ["ref_snapshot_16", "ref_snapshot_64_skip"])
+def test_loaded_reference_snapshot_runs_on_both_cuda_engines(stem):
+    """SURVEY 8f-1 end to end: a snapshot pickled by the REAL reference -> loader -> .cuda() -> G(z) on the exact-fp32 ops engine (1e-4)
+    and on the tcgen05 engine (1e-2, absolute) against the image the reference generator itself produced for the same z."""
+    io_ = np.load(os.path.join(util.GOLDEN, stem + "_io.npz"))
+    G = loader.load_network(os.path.join(util.GOLDEN, stem + ".pkl"))["Gs"].cuda()
+    z, want = torch.from_numpy(io_["z"]).cuda(), torch.from_numpy(io_["img"])
+    for engine, tol in (("ops", 1e-4), ("tc", 1e-2)):
+        G.synthesis.engine = engine
+        with torch.no_grad():
+            img = G(z, noise_mode="const")[0]
+        err = (img.cpu() - want).abs().max().item()
+        print(stem, engine, "max-abs vs the reference's image", err)
+        assert err < tol, (engine, err)

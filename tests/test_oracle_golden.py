@@ -49,7 +49,7 @@ def test_generator_init_matches_reference_checksum():
     assert abs(util.sd_checksum(util.state_dict_cpu(Gm)) - float(g["sd_checksum"])) < 1e-6 * abs(float(g["sd_checksum"]))
 
 
-@pytest.mark.parametrize("cfg", [(32, 512, 32, "gen32_golden.npz"), (64, 32768, 512, "gen64_golden.npz")])
+@pytest.mark.parametrize("cfg", [(32, 512, 32, "gen32_golden.npz"), (64, 32768, 512, "gen64_golden.npz"), (256, 32768, 512, "gen256_golden.npz")])
 def test_generator_oracle_matches_golden(cfg):
     res, cb, cm, fn = cfg
     g = np.load(os.path.join(util.GOLDEN, fn))
@@ -68,6 +68,19 @@ def test_generator_oracle_grads_match_golden():
     img = ganformer.synthesis(sd, ws, sd["pos"], torch.ones(2, 16), 32)
     gws, = torch.autograd.grad(img.square().mean(), [ws])
     np.testing.assert_allclose(gws.numpy(), g["gws"], rtol=0, atol=1e-6 + 1e-4 * np.abs(g["gws"]).max())
+
+
+def test_generator_oracle_grads_match_golden_at_config1_size():
+    """BASELINE configs[0] size (256^2, default widths, batch 1): the oracle's d(mean img^2)/d(ws) and d/dz against the real reference."""
+    g = np.load(os.path.join(util.GOLDEN, "gen256_golden.npz"))
+    sd = util.state_dict_cpu(util.build_G(256, 0))
+    ws = torch.from_numpy(g["ws"]).requires_grad_(True)
+    img = ganformer.synthesis(sd, ws, sd["pos"], torch.ones(1, 16), 256)
+    gws, = torch.autograd.grad(img.square().mean(), [ws])
+    np.testing.assert_allclose(gws.numpy(), g["gws"], rtol=0, atol=1e-6 + 1e-4 * np.abs(g["gws"]).max())
+    z = torch.from_numpy(g["z"]).requires_grad_(True)
+    gz, = torch.autograd.grad(ganformer.generator(sd, z, 256)[0].square().mean(), [z])
+    np.testing.assert_allclose(gz.numpy(), g["gz"], rtol=0, atol=1e-6 + 1e-4 * np.abs(g["gz"]).max())
 
 
 def test_lpips_oracle_matches_golden():

@@ -45,4 +45,4 @@ def test_vgg_conv1_fwd_bwd(B, R, fwd):
         assert (dimg2 - gx).abs().max().item() < 2.0 ** -7 * gx.abs().max().item()
         assert (dimg - (gx + 0.37 * (img - tgt))).abs().max().item() < 2.0 ** -7 * gx.abs().max().item()
     finally:
-        _lib.set_forward_dtype("bf16")
+        _lib.set_forward_dtype(_lib.DEFAULT_FORWARD_DTYPE)
