@@ -122,6 +122,10 @@ typedef struct {
   /* elements between the noise planes of consecutive samples: 0 = one [OH, OW] plane shared by all samples (noise_mode 'const'),
    * OH*OW = per-sample planes [NB, OH, OW] (noise_mode 'random', reference networks.py:1015-1017) */
   int64_t noise_bstride;
+  /* per-phase tap lists (transposed convolution, conv2d_resample.py:117-134 first stage): when phase_ntaps[0] > 0 the `taps` array is the
+   * concatenation of `phases` lists (phase p owns phase_ntaps[p] entries), every phase reads the SAME [T][Cout][K] weights (w_NT == Cout)
+   * and writes its own strided output view (osy/osx/ofy/ofx).  Forward-type launches only (no reduce_out / X). */
+  int32_t phase_ntaps[4];
 } mgf_conv_tc_desc;
 int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream);
 /* debugging / A-B measurement: 0 disables the halo (shared-memory tap reuse) variant that mgf_conv_tc picks for C = 64/128 3x3 layers */
@@ -155,6 +159,14 @@ int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, const float* 
                 float alpha, float gain, int mode, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
 /* g [B,H+2,W+2,C] bf16 = 4-tap separable FIR (taps fk4, zero padding 2, * gain) of dy [B,H,W,C] bf16: first stage of the up-convolution's
  * input gradient (adjoint of upfirdn2d(pad 1, gain 4) after conv_transpose2d, conv2d_resample.py:117-134) */
+/* same-resolution 4x4 separable FIR with zero padding on an NHWC 16-bit tensor (fir.cu): out[b,Y,X,c] = gain * sum_{t,u} fk4[t] fk4[u]
+ * in[b,Y+off+t,X+off+u,c]; outputs outside the valid (Hv, Wv) window of the allocated (Ho, Wo) tensor are written as zeros.
+ * off = -1: second stage of the up-convolution (conv_transpose2d(stride 2) -> upfirdn2d(pad 1, gain 4), conv2d_resample.py:117-134) with
+ * the layer tail fused when noise / bias / act are given: (v + noise * nstr + bias) -> leaky-ReLU(alpha) (act == 1) -> * act_gain
+ * (networks.py:1036-1040); in_fwd / out_fwd select forward-dtype tensors (else bf16 gradients).  off = -2: the adjoint (mgf_fir4_pad). */
+int mgf_fir4(const void* in, void* out, const float* fk4, float gain, int off, int B, int Hi, int Wi, int Ho, int Wo, int Hv, int Wv,
+             int C, int in_fwd, int out_fwd, const float* noise, const float* nstr, int64_t noise_bstride, const float* bias, int act,
+             float alpha, float act_gain, void* stream);
 int mgf_fir4_pad(const void* dy, void* g, const float* fk4, float gain, int B, int H, int W, int C, void* stream);
 int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
 int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream);

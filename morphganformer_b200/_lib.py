@@ -38,6 +38,8 @@ SIGNATURES = {
     "mgf_torgb_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_void_p]),
     "mgf_torgb_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int64, c_int, c_void_p]),
     "mgf_act_bwd": (c_int, [c_void_p] * 7 + [c_float, c_float, c_int, c_int, c_int64, c_int, c_int64, c_void_p]),
+    "mgf_fir4": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int] + [c_int] * 8 + [c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int,
+                         c_float, c_float, c_void_p]),
     "mgf_fir4_pad": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_upfir2_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_upfir2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),

@@ -62,6 +62,8 @@ struct alignas(64) Params {
   long long noise_bstride;       // elements between per-sample noise planes (0: one plane for all samples)
   int superpix;                  // output rows are PAIRS of pixels (32+32 channels): noise differs between the two 32-column halves
   unsigned int* ovf;             // fp16 overflow flag word (nullptr unless the output is an fp16 forward tensor)
+  int ph_taps;                   // per-phase tap lists: phase ph owns taps [ph_tap0[ph], ph_tap0[ph+1]); weights are shared by the phases
+  int ph_tap0[5]; int ph_tiles;  // ph_tiles = tiles of one phase (tile order is phase-major so the persistent CTAs stay balanced)
   int x_tma; uint32_t x_bytes;   // X tile arrives by TMA (one 64/32-channel group per tile) instead of per-thread strided loads
 };
 
@@ -166,7 +168,13 @@ struct Cfg {
 struct TileCoord { int n0, x0, y0, b0; };
 __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int BN) {
   TileCoord t;
-  const int nb = tile % p.n_tiles; int m = tile / p.n_tiles;
+  int nb, m;
+  if (p.ph_taps) {       // phase-major order: n0 = ph * Cout + (column block inside the phase)
+    const int ph = tile / p.ph_tiles, rem = tile % p.ph_tiles, nbp = p.Cout / BN;
+    nb = ph * nbp + rem % nbp; m = rem / nbp;
+  } else {
+    nb = tile % p.n_tiles; m = tile / p.n_tiles;
+  }
   t.n0 = nb * BN;
   t.x0 = (m % p.tilesW) * p.TW; m /= p.tilesW;
   t.y0 = (m % p.tilesH) * p.TH; m /= p.tilesH;
@@ -366,15 +374,17 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BN);
       const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
+      int tp0 = 0, tp1 = p.ntaps, wn0 = t.n0;
+      if (p.ph_taps) { const int ph = t.n0 / p.Cout; tp0 = p.ph_tap0[ph]; tp1 = p.ph_tap0[ph + 1]; wn0 = t.n0 - ph * p.Cout; }
       for (int kc = 0; kc < p.kchunks; kc++) {
-        for (int tp = 0; tp < p.ntaps; tp++) {
+        for (int tp = tp0; tp < tp1; tp++) {
           const Tap tap = p.taps[tp];
           mbar_wait(&empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&full[stage], p.tx_bytes);
             uint8_t* sa = smem + stage * C::STAGE;
             tma_load_4d(&p.amap[tap.amap], &full[stage], sa, kc * BK, t.x0 + tap.dx, t.y0 + tap.dy, t.b0);
-            tma_load_3d(&p.bmap, &full[stage], sa + C::A_BYTES, kc * BK, t.n0, wbase + tap.wz);
+            tma_load_3d(&p.bmap, &full[stage], sa + C::A_BYTES, kc * BK, wn0, wbase + tap.wz);
           }
           __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -387,7 +397,9 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-      for (int it = 0; it < iters; it++) {
+      int iters_t = iters;
+      if (p.ph_taps) { const int ph = tile / p.ph_tiles; iters_t = p.kchunks * (p.ph_tap0[ph + 1] - p.ph_tap0[ph]); }
+      for (int it = 0; it < iters_t; it++) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -474,27 +486,31 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 //   * the 3x3 weights of the current (sample, N-block) stay resident in shared memory across tiles (KC*9 tiles of BN x 64),
 //     re-loaded only when the CTA moves to another sample / N-block.
 // L2->SM traffic per 128-pixel tile drops from 9*(16+BN/8) KB to 36 KB per channel chunk.
-template <int BN, int KC, int BK>
+constexpr int HALO_PITCH = 10;      // haloed tile row pitch in pixels: 8 output pixels + 1 halo pixel each side (no padding pixels)
+template <int BN, int KC, int BK, int NSTG_>
 struct HaloCfg {
-  static constexpr int A_STAGE = 288 * BK * 2;                    // 18 rows x 16 px x (128 B | 64 B for 32-channel layers)
+  static constexpr int A_BOX = 18 * HALO_PITCH * BK * 2;          // bytes one TMA box delivers: 18 rows x 10 px x (128 B | 64 B)
+  static constexpr int A_STAGE = ((A_BOX + 1023) / 1024) * 1024;  // stages start on swizzle-atom boundaries
   static constexpr int B_TILE = BN * BK * 2;
   static constexpr int B_BYTES = KC * 9 * B_TILE;
   static constexpr int SMEM_MAX = 227 * 1024;
-  static constexpr int NSTG = 2;
-  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * NSTG * STG_BYTES - 2 * RACC * 4 - 512) / A_STAGE;
-  static constexpr int NS = NS_RAW > 6 ? 6 : NS_RAW;
-  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + 256;
+  static constexpr int NSTG = NSTG_;
+  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * NSTG * STG_BYTES - 2 * RACC * 4 - 1024) / A_STAGE;
+  static constexpr int NS = NS_RAW > 8 ? 8 : NS_RAW;
+  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + 512;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(NS >= 2, "halo kernel needs at least two activation stages");
 };
 
 template <int BK>
 __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr) {
-  // K-major, 128B swizzle, rows of a core-matrix group 128 B apart, groups (8 px = one tile row) 2048 B apart.
-  // base_offset stays 0: measured on B200 (scripts/debug_halo.py) the swizzle XOR is taken from the shared-memory ADDRESS bits,
-  // exactly like the TMA write side, so a start address shifted by dx*128 B inside the atom needs no phase correction
-  // (setting base_offset = dx, as a literal reading of the descriptor format suggests, corrupts the dx != -1 taps).
-  constexpr uint64_t sbo = 16 * BK * 2;            // one tile row = 16 haloed pixels
+  // K-major, 128B swizzle, rows of a core-matrix group 128 B apart, groups (8 px = one tile row) one haloed row (HALO_PITCH px) apart.
+  // base_offset stays 0: measured on B200 the swizzle XOR is taken from the shared-memory ADDRESS bits, exactly like the TMA write
+  // side, so neither a start address shifted by dx*128 B inside the atom nor a group stride that is not a multiple of the 1024-byte
+  // atom needs a phase correction (setting base_offset = dx, as a literal reading of the descriptor format suggests, corrupts the
+  // dx != -1 taps).  The 10-pixel pitch keeps the tile at 180 px (23 KB) instead of 288 px (36 KB): more stages in flight, 37 % less
+  // L2 -> shared-memory traffic.
+  constexpr uint64_t sbo = HALO_PITCH * BK * 2;
   constexpr uint64_t layout = (BK == 64) ? 2 : 4;  // 128B / 64B swizzle
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
@@ -508,9 +524,9 @@ __device__ __forceinline__ HaloTile decode_halo(const Params& p, int tile, int B
   return t;
 }
 
-template <int BN, int KC, int BK>
+template <int BN, int KC, int BK, int NSTG_>
 __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant__ Params p) {
-  using C = HaloCfg<BN, KC, BK>;
+  using C = HaloCfg<BN, KC, BK, NSTG_>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sA = smem + C::B_BYTES;
@@ -562,7 +578,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       for (int kc = 0; kc < KC; kc++) {
         mbar_wait(&aempty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&afull[stage], (uint32_t)C::A_STAGE);
+          mbar_arrive_expect_tx(&afull[stage], (uint32_t)C::A_BOX);
           tma_load_4d(&p.amap[0], &afull[stage], sA + stage * C::A_STAGE, kc * BK, t.x0 - 1, t.y0 - 1, t.b0);
         }
         __syncwarp();
@@ -576,7 +592,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
     // tap -> byte offset of its shifted view inside the haloed tile (warp-uniform, hoisted out of the tile loop)
     uint32_t tap_off[9];
 #pragma unroll
-    for (int tp = 0; tp < 9; tp++) tap_off[tp] = (uint32_t)(((p.taps[tp].dy + 1) * 16 + p.taps[tp].dx + 1) * (BK * 2));
+    for (int tp = 0; tp < 9; tp++) tap_off[tp] = (uint32_t)(((p.taps[tp].dy + 1) * HALO_PITCH + p.taps[tp].dx + 1) * (BK * 2));
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const HaloTile t = decode_halo(p, tile, BN);
       if (t.key != cur_key) { mbar_wait(bfull, bphase); bphase ^= 1; cur_key = t.key; }
@@ -730,26 +746,33 @@ static int launch(const Params& p, int grid, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, int KC, int BK>
+template <int BN, int KC, int BK, int NSTG_>
 static int launch_halo(const Params& p, int grid, cudaStream_t st) {
-  using C = HaloCfg<BN, KC, BK>;
+  using C = HaloCfg<BN, KC, BK, NSTG_>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, KC, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, KC, BK, NSTG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc(halo): cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_halo_kernel<BN, KC, BK><<<grid, 320, C::SMEM, st>>>(p);
+  conv_halo_kernel<BN, KC, BK, NSTG_><<<grid, 320, C::SMEM, st>>>(p);
   MGF_CHECK_LAUNCH("conv_tc(halo)");
   return 0;
 }
 
 static bool g_halo_enabled = true;
+static int g_halo_nstg = 1;        // epilogue staging tiles per group in the halo kernel (A/B switch: mgf_conv_tc_set_halo(1 | 2 << 1))
 
 }  // namespace tc
 }  // namespace mgf
 
-extern "C" int mgf_conv_tc_set_halo(int enabled) { mgf::tc::g_halo_enabled = enabled != 0; return 0; }
+extern "C" int mgf_conv_tc_set_halo(int mode) {
+  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2)
+  mgf::tc::g_halo_enabled = (mode & 1) != 0;
+  const int n = (mode >> 1) & 3;
+  mgf::tc::g_halo_nstg = (n == 2) ? 2 : 1;
+  return 0;
+}
 
 extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   using namespace mgf;
@@ -764,7 +787,14 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   const int BK = (Cc % 64 == 0) ? 64 : 32;
   if (d->phases < 1 || d->phases > 4 || d->Cout < 32 || d->Cout % 32) MGF_FAIL(MGF_E_SHAPE, "conv_tc: Cout (%d) must be a multiple of 32, phases 1..4", d->Cout);
   const long long NT = (long long)d->phases * d->Cout;
-  if (d->w_NT != NT) MGF_FAIL(MGF_E_SHAPE, "conv_tc: weight NT (%lld) != phases*Cout (%lld)", (long long)d->w_NT, NT);
+  const bool ph_taps = d->phase_ntaps[0] > 0;
+  if (ph_taps) {
+    int tot = 0;
+    for (int i = 0; i < d->phases; i++) { if (d->phase_ntaps[i] < 1) MGF_FAIL(MGF_E_BADARG, "conv_tc: phase %d has no taps", i); tot += d->phase_ntaps[i]; }
+    if (tot != d->ntaps) MGF_FAIL(MGF_E_BADARG, "conv_tc: phase tap lists hold %d taps, ntaps = %d", tot, d->ntaps);
+    if (d->reduce_out || d->X || d->superpix) MGF_FAIL(MGF_E_UNSUP, "conv_tc: per-phase tap lists are a forward-only form (no reduce_out / X / superpix)");
+    if (d->w_NT != d->Cout) MGF_FAIL(MGF_E_SHAPE, "conv_tc: per-phase tap lists share one [T][Cout][K] weight tensor (w_NT %lld != Cout %d)", (long long)d->w_NT, d->Cout);
+  } else if (d->w_NT != NT) MGF_FAIL(MGF_E_SHAPE, "conv_tc: weight NT (%lld) != phases*Cout (%lld)", (long long)d->w_NT, NT);
   if (d->OC < d->Cout || d->OC % 8) MGF_FAIL(MGF_E_SHAPE, "conv_tc: bad output channel stride");
   int BN = d->bn;
   if (BN == 0) BN = (d->Cout % 256 == 0) ? 256 : (d->Cout % 128 == 0) ? 128 : (d->Cout % 64 == 0) ? 64 : 32;
@@ -780,7 +810,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   // resident weights for many tiles
   // (measured: a win for C = 64 -- 0.95 -> 0.68 ms on 64->64 @1024^2 x8 -- but not for C = 128, where the generic kernel's
   // 128-wide N tile beats two 64-wide halo passes; scripts/bench_conv_tc.py)
-  bool halo = g_halo_enabled && d->n_a == 1 && d->ntaps == 9 && (Cc == 64 || Cc == 32) && d->bn == 0 && d->GW >= 16 &&
+  bool halo = g_halo_enabled && !ph_taps && d->n_a == 1 && d->ntaps == 9 && (Cc == 64 || Cc == 32) && d->bn == 0 && d->GW >= 16 &&
               (long long)d->GH * d->GW >= 256LL * 256 && (per_sample || d->w_G == 1);
   if (halo) {
     int seen = 0;
@@ -809,7 +839,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     {
       cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
       cuuint64_t strides[3] = {(cuuint64_t)a.sW * 2, (cuuint64_t)a.sH * 2, (cuuint64_t)a.sN * 2};
-      cuuint32_t box[4] = {(cuuint32_t)HBK, 16, 18, 1};
+      cuuint32_t box[4] = {(cuuint32_t)HBK, (cuuint32_t)HALO_PITCH, 18, 1};
       if (int e = encode(&p.amap[0], a.ptr, 4, dims, strides, box, HBK)) return e;
     }
     {
@@ -835,10 +865,9 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     if (int e = encode_x_map(p, d, HBN, 8, 16, 1, 128)) return e;
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
     cudaStream_t st = (cudaStream_t)stream;
-    if (HBK == 64 && HBN == 64) return launch_halo<64, 1, 64>(p, grid, st);
-    if (HBK == 64 && HBN == 32) return launch_halo<32, 1, 64>(p, grid, st);
-    if (HBK == 32 && HBN == 64) return launch_halo<64, 1, 32>(p, grid, st);
-    if (HBK == 32 && HBN == 32) return launch_halo<32, 1, 32>(p, grid, st);
+#define MGF_HALO_CASE(bn, bk) if (HBN == bn && HBK == bk) return g_halo_nstg == 2 ? launch_halo<bn, 1, bk, 2>(p, grid, st) : launch_halo<bn, 1, bk, 1>(p, grid, st);
+    MGF_HALO_CASE(64, 64) MGF_HALO_CASE(32, 64) MGF_HALO_CASE(64, 32) MGF_HALO_CASE(32, 32)
+#undef MGF_HALO_CASE
     MGF_FAIL(MGF_E_UNSUP, "conv_tc: no halo kernel for BN=%d KC=%d", HBN, KC);
   }
   // tile shape: TW x TH x TB pixels = at most 128 rows
@@ -860,6 +889,12 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   if (total > 0x7fffffffLL) MGF_FAIL(MGF_E_SHAPE, "conv_tc: too many tiles");
   p.total_tiles = (int)total;
   p.ntaps = d->ntaps; p.kchunks = (int)(Cc / BK);
+  p.ph_taps = ph_taps ? 1 : 0;
+  if (ph_taps) {
+    p.ph_tap0[0] = 0;
+    for (int i = 0; i < d->phases; i++) p.ph_tap0[i + 1] = p.ph_tap0[i] + d->phase_ntaps[i];
+    p.ph_tiles = p.total_tiles / d->phases;
+  }
   for (int i = 0; i < d->ntaps; i++) {
     if (d->taps[i].amap < 0 || d->taps[i].amap >= d->n_a || d->taps[i].wz < 0 || d->taps[i].wz >= d->w_T)
       MGF_FAIL(MGF_E_BADARG, "conv_tc: tap %d out of range", i);

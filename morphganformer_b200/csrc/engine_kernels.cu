@@ -292,175 +292,6 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&R[(long long)b * C + i], racc[i]);
 }
 
-// ---- NHWC FIR up-sampling x2 with the 4-tap separable filter (zero-insert, pad [2,1,2,1], gain 4) + residual add:
-// out[b,Y,X,c] = add[b,Y,X,c] + g * sum_{fy,fx} fk[fy]*fk[fx] * v[b,(Y+fy-2)/2,(X+fx-2)/2,c]   over taps where the index is even
-// (reference Conv2dLayer.forward :245-250 -> conv2d_resample 1x1-up branch -> upfirdn2d(up=2, pad=[2,1,2,1], gain=4) -> bias_act gain).
-// fk = flipped normalised 1-D taps * 2 (gain 4 split per axis).
-template <bool f16>
-__global__ void __launch_bounds__(256) upfir2_add_kernel(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ out,
-                                                         float4 fk, float g, int h, int w, int C, int vshift) {
-  // grid: x = chunks of one output row (X, channel-vector), y = output row Y, z = sample.  vecs = C/8 = 1 << vshift.
-  const int vecs = 1 << vshift;
-  const int b = blockIdx.z, Y = blockIdx.y;
-  const int rowlen = (2 * w) << vshift;
-  const float f[4] = {fk.x, fk.y, fk.z, fk.w};
-  const int fy0 = Y & 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += gridDim.x * blockDim.x) {
-    const int cv = i & (vecs - 1), X = i >> vshift;
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) acc[e] = 0.f;
-#pragma unroll
-    for (int a = 0; a < 2; a++) {
-      const int fy = fy0 + 2 * a, iy = (Y + fy - 2) >> 1;
-      if (iy < 0 || iy >= h) continue;
-#pragma unroll
-      for (int c2 = 0; c2 < 2; c2++) {
-        const int fx = (X & 1) + 2 * c2, ix = (X + fx - 2) >> 1;
-        if (ix < 0 || ix >= w) continue;
-        const float cf = f[fy] * f[fx];
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(v + ((((long long)b * h + iy) * w + ix) << (vshift + 3))) + cv);
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; e++) { const float2 q = unpack16(w4[e], f16); acc[e * 2] = fmaf(cf, q.x, acc[e * 2]); acc[e * 2 + 1] = fmaf(cf, q.y, acc[e * 2 + 1]); }
-      }
-    }
-    const long long off = ((((long long)b * 2 * h + Y) * 2 * w + X) << (vshift + 3)) + cv * 8;
-    float av[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) av[e] = 0.f;
-    if (add) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(add + off));
-      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int e = 0; e < 4; e++) { const float2 q = unpack16(w4[e], f16); av[e * 2] = q.x; av[e * 2 + 1] = q.y; }
-    }
-    uint4 o;
-    o.x = pack16(acc[0] * g + av[0], acc[1] * g + av[1], f16); o.y = pack16(acc[2] * g + av[2], acc[3] * g + av[3], f16);
-    o.z = pack16(acc[4] * g + av[4], acc[5] * g + av[5], f16); o.w = pack16(acc[6] * g + av[6], acc[7] * g + av[7], f16);
-    *reinterpret_cast<uint4*>(out + off) = o;
-  }
-}
-
-// ---- 4x4 separable FIR with zero padding 2, no resampling: g[b,u,v,c] = gain * sum_{a,b'} fk[a] fk[b'] dy[b, u-a+1, v-b'+1, c] for
-// u in [0, H], v in [0, W] (dy is [B,H,W,C]; g is [B,H+2,W+2,C], the last row / column are written as zeros).
-// First stage of the up-convolution's input gradient: the reference's up path is conv_transpose2d(stride 2) -> upfirdn2d(pad 1, gain 4)
-// (conv2d_resample.py:117-134), so its adjoint is this FIR (H -> H+1) followed by a stride-2 3x3 convolution: 9 taps on the tensor
-// cores instead of the 36 of the folded four-phase form (7 loads per output instead of 16: see the kernel).
-__global__ void __launch_bounds__(256, 2) fir4_pad_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ g, float4 fk, float gain,
-                                                       int H, int W, int C, int vshift) {
-  // thread = one output column v x one 8-channel vector x FOUR consecutive output rows u0 .. u0+3: consecutive threads walk along the row, so
-  // every load / store instruction of a warp covers 512 contiguous bytes (the first version ran four columns per thread: 256-byte strides
-  // between lanes, twice the L1 wavefronts).  Row sums (horizontal taps) of the 7 input rows are scattered into the four outputs they feed.
-  const int vecs = 1 << vshift;
-  const int b = blockIdx.z, u0 = blockIdx.y * 4;
-  const float f[4] = {fk.x * gain, fk.y * gain, fk.z * gain, fk.w * gain};     // gain folded into the horizontal taps
-  const float fv[4] = {fk.x, fk.y, fk.z, fk.w};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ((W + 2) << vshift); i += gridDim.x * blockDim.x) {
-    const int cv = i & (vecs - 1), v = i >> vshift;
-    float acc[4][8];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-      for (int e = 0; e < 8; e++) acc[j][e] = 0.f;
-    if (v <= W) {
-      // branch-free: out-of-range taps read a clamped (valid) address with a zero weight, so all loads of a batch of rows are issued
-      // before the first use (the branchy version serialised 7 dependent row round trips per thread: latency-bound at 2 TB/s)
-      float wx[4]; int xc[4];
-#pragma unroll
-      for (int bb = 0; bb < 4; bb++) {
-        const int x = v - bb + 1;
-        const bool ok = x >= 0 && x < W;
-        wx[bb] = ok ? f[bb] : 0.f; xc[bb] = ok ? x : 0;
-      }
-#pragma unroll
-      for (int r0 = 0; r0 < 7; r0 += 4) {                        // two batches: input rows u0-2 .. u0+1, then u0+2 .. u0+4
-        uint4 q[4][4];
-        float wy[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int rr = r0 + k;
-          const int y = u0 - 2 + rr;
-          const bool ok = rr < 7 && y >= 0 && y < H;
-          wy[k] = ok ? 1.f : 0.f;
-          const long long rowbase = ((long long)b * H + (ok ? y : 0)) * W;
-#pragma unroll
-          for (int bb = 0; bb < 4; bb++)
-            if (rr < 7) q[k][bb] = __ldg(reinterpret_cast<const uint4*>(dy + ((rowbase + xc[bb]) << (vshift + 3))) + cv);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int rr = r0 + k;
-          if (rr < 7) {
-            float rs[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) rs[e] = 0.f;
-#pragma unroll
-            for (int bb = 0; bb < 4; bb++) {
-              const float wgt = wx[bb] * wy[k];
-              const uint32_t w4[4] = {q[k][bb].x, q[k][bb].y, q[k][bb].z, q[k][bb].w};
-#pragma unroll
-              for (int e = 0; e < 4; e++) { const float2 t = unpack_bf16(w4[e]); rs[e * 2] = fmaf(wgt, t.x, rs[e * 2]); rs[e * 2 + 1] = fmaf(wgt, t.y, rs[e * 2 + 1]); }
-            }
-            // input row y feeds output row u = y + a - 1, a = 0..3  ->  j = u - u0 = rr - 3 + a
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-              const int j = rr - 3 + a;
-              if (j >= 0 && j < 4) {
-#pragma unroll
-                for (int e = 0; e < 8; e++) acc[j][e] = fmaf(fv[a], rs[e], acc[j][e]);
-              }
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int u = u0 + j;
-      if (u < H + 2) {
-        const bool live = (u <= H) && (v <= W);
-        uint4 o;
-        o.x = live ? pack_bf16(acc[j][0], acc[j][1]) : 0u; o.y = live ? pack_bf16(acc[j][2], acc[j][3]) : 0u;
-        o.z = live ? pack_bf16(acc[j][4], acc[j][5]) : 0u; o.w = live ? pack_bf16(acc[j][6], acc[j][7]) : 0u;
-        *(reinterpret_cast<uint4*>(g + ((((long long)b * (H + 2) + u) * (W + 2) + v) << (vshift + 3))) + cv) = o;
-      }
-    }
-  }
-}
-
-// adjoint of the above (without the add): dv[b,iy,ix,c] = g * sum_{fy,fx} fk[fy] fk[fx] dout[b, 2iy+2-fy, 2ix+2-fx, c]
-__global__ void __launch_bounds__(256) upfir2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dv, float4 fk, float g, int h, int w, int C, int vshift) {
-  const int vecs = 1 << vshift;
-  const int b = blockIdx.z, iy = blockIdx.y;
-  const int rowlen = w << vshift;
-  const float f[4] = {fk.x, fk.y, fk.z, fk.w};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += gridDim.x * blockDim.x) {
-    const int cv = i & (vecs - 1), ix = i >> vshift;
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) acc[e] = 0.f;
-#pragma unroll
-    for (int fy = 0; fy < 4; fy++) {
-      const int Y = 2 * iy + 2 - fy;
-      if (Y < 0 || Y >= 2 * h) continue;
-#pragma unroll
-      for (int fx = 0; fx < 4; fx++) {
-        const int X = 2 * ix + 2 - fx;
-        if (X < 0 || X >= 2 * w) continue;
-        const float cf = f[fy] * f[fx];
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dout + ((((long long)b * 2 * h + Y) * 2 * w + X) << (vshift + 3))) + cv);
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; e++) { const float2 q = unpack_bf16(w4[e]); acc[e * 2] = fmaf(cf, q.x, acc[e * 2]); acc[e * 2 + 1] = fmaf(cf, q.y, acc[e * 2 + 1]); }
-      }
-    }
-    uint4 o;
-    o.x = pack_bf16(acc[0] * g, acc[1] * g); o.y = pack_bf16(acc[2] * g, acc[3] * g);
-    o.z = pack_bf16(acc[4] * g, acc[5] * g); o.w = pack_bf16(acc[6] * g, acc[7] * g);
-    *reinterpret_cast<uint4*>(dv + ((((long long)b * h + iy) * w + ix) << (vshift + 3)) + cv * 8) = o;
-  }
-}
 
 static inline unsigned grid_for(long long work, int per_block = 256, int waves = 8) {
   long long blocks = (work + per_block - 1) / per_block;
@@ -573,45 +404,8 @@ extern "C" int mgf_act_bwd(const void* dz, const void* z, void* dy, float* R, co
 
 static int log2_exact(int v) { int s = 0; while ((1 << s) < v) s++; return (1 << s) == v ? s : -1; }
 
-extern "C" int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream) {
-  if (!v || !out || !fk4) MGF_FAIL(MGF_E_BADARG, "upfir2_add: null tensor");
-  const int vs = (C % 8) ? -1 : log2_exact(C / 8);
-  if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: C/8 must be a power of two");
-  if (2 * h > 65535 || B > 65535) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: image too tall");
-  const int rowlen = (2 * w) << vs;
-  dim3 grid((rowlen + 255) / 256, 2 * h, B);
-  if (fwd_f16()) upfir2_add_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)add, (__nv_bfloat16*)out,
-                                                                                  make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, vs);
-  else upfir2_add_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)v, (const __nv_bfloat16*)add, (__nv_bfloat16*)out,
-                                                                         make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, vs);
-  MGF_CHECK_LAUNCH("upfir2_add");
-  return 0;
-}
 
-extern "C" int mgf_fir4_pad(const void* dy, void* g, const float* fk4, float gain, int B, int H, int W, int C, void* stream) {
-  if (!dy || !g || !fk4) MGF_FAIL(MGF_E_BADARG, "fir4_pad: null tensor");
-  const int vs = (C % 8) ? -1 : log2_exact(C / 8);
-  if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "fir4_pad: C/8 must be a power of two");
-  if (H + 2 > 65535 || B > 65535 || B <= 0 || H <= 0 || W <= 0) MGF_FAIL(MGF_E_SHAPE, "fir4_pad: bad image size");
-  const int items = (W + 2) << vs;
-  dim3 grid((items + 255) / 256, (H + 2 + 3) / 4, B);
-  fir4_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)g, make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, H, W, C, vs);
-  MGF_CHECK_LAUNCH("fir4_pad");
-  return 0;
-}
 
-extern "C" int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream) {
-  if (!dout || !dv || !fk4) MGF_FAIL(MGF_E_BADARG, "upfir2_bwd: null tensor");
-  const int vs = (C % 8) ? -1 : log2_exact(C / 8);
-  if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "upfir2_bwd: C/8 must be a power of two");
-  if (h > 65535 || B > 65535) MGF_FAIL(MGF_E_SHAPE, "upfir2_bwd: image too tall");
-  const int rowlen = w << vs;
-  dim3 grid((rowlen + 255) / 256, h, B);
-  upfir2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dv,
-                                                            make_float4(fk4[0], fk4[1], fk4[2], fk4[3]), gain, h, w, C, vs);
-  MGF_CHECK_LAUNCH("upfir2_bwd");
-  return 0;
-}
 
 extern "C" int mgf_scale_channels(const void* x, const float* sc, void* out, int is_fwd, int B, int64_t HW, int C, void* stream) {
   if (!x || !sc || !out) MGF_FAIL(MGF_E_BADARG, "scale_channels: null tensor");

@@ -1,0 +1,324 @@
+// fir.cu -- the [1,3,3,1] FIR passes of the synthesis engine on NHWC 16-bit tensors, as register sliding windows.
+//
+// All of these are HBM-bound (upfirdn2d): every kernel here reads each input element from DRAM once and writes each
+// output once.  A thread owns one (column, 8-channel vector) and walks DOWN a strip of rows: per input row it loads the few
+// horizontally neighbouring pixels (16-byte vectors; the neighbours of the same warp hit L1), forms the horizontal partial sum in fp32
+// registers and feeds a ring of vertical accumulators -- no shared memory, no re-reads of rows, 3-4 loads per output instead of 7-16.
+//   fir4_kernel       same-resolution 4x4 FIR with zero padding.  Two users:
+//                       * second stage of the up-convolution (reference conv2d_resample.py:117-134: conv_transpose2d(stride 2) ->
+//                         upfirdn2d(pad 1, gain 4)) with the layer tail fused: + noise * strength, + bias, leaky-ReLU * gain
+//                         (networks.py:1036-1040);
+//                       * first stage of that layer's input gradient (the adjoint FIR onto the (2h+1)^2 grid).
+//   upfir2_add_kernel resnet skip: FIR x2 up-sampling of the 1x1-conv output + residual add (networks.py:245-250, :1157-1160).
+//   upfir2_bwd_kernel its adjoint.
+#include "common.cuh"
+
+namespace mgf {
+
+template <bool F16>
+__device__ __forceinline__ void ld8(const uint16_t* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; e++) { const float2 f = unpack16(w[e], F16); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+template <bool F16>
+__device__ __forceinline__ void st8(uint16_t* p, const float (&v)[8]) {
+  uint4 o;
+  o.x = pack16(v[0], v[1], F16); o.y = pack16(v[2], v[3], F16); o.z = pack16(v[4], v[5], F16); o.w = pack16(v[6], v[7], F16);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+struct Fir4Args {
+  const uint16_t* in; uint16_t* out;
+  float fh[4], fv[4];            // horizontal taps (gain folded in) and vertical taps: out[Y,X] = sum_{t,u} fv[t] fh[u] in[Y+off+t, X+off+u]
+  int off;                       // -1: second stage of the up-convolution; -2: its adjoint onto the padded gradient grid
+  int Hi, Wi, Ho, Wo, Hv, Wv;    // input size, allocated output size, valid output size (rows/columns beyond it are written as zeros)
+  int vshift, rows;              // channels / 8 = 1 << vshift; output rows per strip (multiple of 3)
+  const float* noise; const float* nstr; long long noise_bstride; const float* bias; int act; float alpha, gain;
+  unsigned int* ovf;
+};
+
+template <bool IN_F16, bool OUT_F16, bool EPI>
+__global__ void __launch_bounds__(256) fir4_kernel(const Fir4Args a) {
+  const int vecs = 1 << a.vshift;
+  const int b = blockIdx.z, Y0 = blockIdx.y * a.rows;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (a.Wo << a.vshift)) return;
+  const int cv = i & (vecs - 1), X = i >> a.vshift;
+  float wx[4]; int xo[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) {               // out-of-range taps: zero weight on a clamped (valid) address, so the loads stay unconditional
+    const int x = X + a.off + t;
+    const bool ok = x >= 0 && x < a.Wi && X < a.Wv;
+    wx[t] = ok ? a.fh[t] : 0.f; xo[t] = (ok ? x : 0) << (a.vshift + 3);
+  }
+  const uint16_t* inb = a.in + (((long long)b * a.Hi * a.Wi) << (a.vshift + 3)) + cv * 8;
+  uint16_t* outb = a.out + ((((long long)b * a.Ho) * a.Wo + X) << (a.vshift + 3)) + cv * 8;
+  const long long orow = (long long)a.Wo << (a.vshift + 3);
+  float bias[8];
+  float nstr = 0.f;
+  if (EPI) {
+#pragma unroll
+    for (int e = 0; e < 8; e++) bias[e] = a.bias ? __ldg(a.bias + cv * 8 + e) : 0.f;
+    if (a.noise) nstr = a.nstr ? __ldg(a.nstr) : 1.f;
+  }
+  const float* nz = (EPI && a.noise) ? a.noise + (long long)b * a.noise_bstride + X : nullptr;
+  float mx = 0.f;
+  float P[8], Q[8], S[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) P[e] = Q[e] = S[e] = 0.f;
+
+  // one input row: horizontal sum h, then out = OLD + fv3*h is complete (output row Yo), MID += fv2*h, YOUNG += fv1*h, OLD = fv0*h
+#define FIR4_STEP(OLD, MID, YOUNG, k)                                                                                   \
+  {                                                                                                                      \
+    const int r = Y0 + a.off + (k);                                                                                      \
+    float h[8];                                                                                                          \
+    _Pragma("unroll") for (int e = 0; e < 8; e++) h[e] = 0.f;                                                            \
+    if (r >= 0 && r < a.Hi) {                                                                                            \
+      const uint16_t* rowp = inb + (((long long)r * a.Wi) << (a.vshift + 3));                                            \
+      float q0[8], q1[8], q2[8], q3[8];                                                                                  \
+      ld8<IN_F16>(rowp + xo[0], q0); ld8<IN_F16>(rowp + xo[1], q1); ld8<IN_F16>(rowp + xo[2], q2); ld8<IN_F16>(rowp + xo[3], q3); \
+      _Pragma("unroll") for (int e = 0; e < 8; e++) h[e] = fmaf(wx[3], q3[e], fmaf(wx[2], q2[e], fmaf(wx[1], q1[e], wx[0] * q0[e]))); \
+    }                                                                                                                    \
+    const int Yo = Y0 + (k) - 3;                                                                                         \
+    if ((k) >= 3 && Yo < a.Ho) {                                                                                         \
+      float o[8];                                                                                                        \
+      const bool live = Yo < a.Hv;                                                                                       \
+      _Pragma("unroll") for (int e = 0; e < 8; e++) o[e] = live ? fmaf(a.fv[3], h[e], OLD[e]) : 0.f;                     \
+      if (EPI) {                                                                                                         \
+        const float n = nz ? __ldg(nz + (long long)Yo * a.Wo) * nstr : 0.f;                                              \
+        _Pragma("unroll") for (int e = 0; e < 8; e++) {                                                                  \
+          float v = o[e] + n + bias[e];                                                                                  \
+          if (a.act == 1) v = v > 0.f ? v : v * a.alpha;                                                                 \
+          o[e] = v * a.gain;                                                                                             \
+        }                                                                                                                \
+      }                                                                                                                  \
+      if (OUT_F16) { _Pragma("unroll") for (int e = 0; e < 8; e++) mx = fmaxf(mx, fabsf(o[e])); }                        \
+      st8<OUT_F16>(outb + (long long)Yo * orow, o);                                                                      \
+    }                                                                                                                    \
+    _Pragma("unroll") for (int e = 0; e < 8; e++) {                                                                      \
+      MID[e] = fmaf(a.fv[2], h[e], MID[e]); YOUNG[e] = fmaf(a.fv[1], h[e], YOUNG[e]); OLD[e] = a.fv[0] * h[e];           \
+    }                                                                                                                    \
+  }
+  for (int k = 0; k < a.rows + 3; k += 3) {
+    if (Y0 + k - 3 >= a.Ho) break;
+    FIR4_STEP(P, Q, S, k)
+    FIR4_STEP(Q, S, P, k + 1)
+    FIR4_STEP(S, P, Q, k + 2)
+  }
+#undef FIR4_STEP
+  if (OUT_F16) ovf_commit(a.ovf, mx);
+}
+
+// ---- resnet skip: out[b,Y,X,c] = add[b,Y,X,c] + g * sum_{fy,fx} fk[fy] fk[fx] v[b,(Y+fy-2)/2,(X+fx-2)/2,c] over the taps with even index
+// (reference Conv2dLayer.forward :245-250 -> conv2d_resample 1x1-up branch -> upfirdn2d(up=2, pad=[2,1,2,1], gain=4) -> bias_act gain).
+// Polyphase form: rows 2m, 2m+1 and columns 2n, 2n+1 of the output read the 3x3 low-resolution neighbourhood of (m, n):
+//   hE[m] = f0 v[m,n-1] + f2 v[m,n]    hO[m] = f1 v[m,n] + f3 v[m,n+1]
+//   out[2m] = f0 h[m-1] + f2 h[m]      out[2m+1] = f1 h[m] + f3 h[m+1]
+// A thread owns (n, 8-channel vector) and walks down the low-resolution rows: 3 loads of v, 4 loads of add, 4 stores per step.
+struct Upfir2Args {
+  const uint16_t* v; const uint16_t* add; uint16_t* out;
+  float fh[4], fv[4];            // horizontal taps with the gain folded in, vertical taps
+  int h, w, vshift, rows;        // low-resolution size, channels / 8 = 1 << vshift, low-resolution rows per strip
+  unsigned int* ovf;
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(256) upfir2_add_kernel2(const Upfir2Args a) {
+  const int vecs = 1 << a.vshift;
+  const int b = blockIdx.z, m0 = blockIdx.y * a.rows;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (a.w << a.vshift)) return;
+  const int cv = i & (vecs - 1), n = i >> a.vshift;
+  const float wl = n > 0 ? a.fh[0] : 0.f, wr = n + 1 < a.w ? a.fh[3] : 0.f;
+  const int sh = a.vshift + 3;
+  const int ol = (n > 0 ? n - 1 : 0) << sh, oc = n << sh, orr = (n + 1 < a.w ? n + 1 : n) << sh;
+  const uint16_t* vb = a.v + (((long long)b * a.h * a.w) << sh) + cv * 8;
+  const long long W2 = 2LL * a.w;
+  const uint16_t* ab = a.add ? a.add + ((((long long)b * 2 * a.h) * W2 + 2 * n) << sh) + cv * 8 : nullptr;
+  uint16_t* ob = a.out + ((((long long)b * 2 * a.h) * W2 + 2 * n) << sh) + cv * 8;
+  const long long orow = W2 << sh;
+  const int pstep = 1 << sh;                 // one output pixel
+  float mx = 0.f;
+  float hE[3][8], hO[3][8];                  // ring of horizontal sums: rows m-1, m, m+1
+
+  auto hrow = [&](int r, float (&e_)[8], float (&o_)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; e++) e_[e] = o_[e] = 0.f;
+    if (r >= 0 && r < a.h) {
+      const uint16_t* rp = vb + (((long long)r * a.w) << sh);
+      float l[8], c[8], rr[8];
+      ld8<F16>(rp + ol, l); ld8<F16>(rp + oc, c); ld8<F16>(rp + orr, rr);
+#pragma unroll
+      for (int e = 0; e < 8; e++) { e_[e] = fmaf(wl, l[e], a.fh[2] * c[e]); o_[e] = fmaf(wr, rr[e], a.fh[1] * c[e]); }
+    }
+  };
+  auto emit = [&](int Y, const float (&ta)[8], float ca, const float (&tb)[8], float cb, const float (&ua)[8], const float (&ub)[8]) {
+    // row Y: even column from (ta, tb), odd column from (ua, ub), vertical weights ca / cb
+    float oe[8], oo[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) { oe[e] = fmaf(ca, ta[e], cb * tb[e]); oo[e] = fmaf(ca, ua[e], cb * ub[e]); }
+    const long long ro = (long long)Y * orow;
+    if (ab) {
+      float x0[8], x1[8];
+      ld8<F16>(ab + ro, x0); ld8<F16>(ab + ro + pstep, x1);
+#pragma unroll
+      for (int e = 0; e < 8; e++) { oe[e] += x0[e]; oo[e] += x1[e]; }
+    }
+    if (F16) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) mx = fmaxf(mx, fmaxf(fabsf(oe[e]), fabsf(oo[e])));
+    }
+    st8<F16>(ob + ro, oe); st8<F16>(ob + ro + pstep, oo);
+  };
+  hrow(m0 - 1, hE[0], hO[0]);
+  hrow(m0, hE[1], hO[1]);
+#define UPFIR2_STEP(PREV, CUR, NEXT, m)                                                             \
+  if ((m) < a.h && (m) < m0 + a.rows) {                                                             \
+    hrow((m) + 1, hE[NEXT], hO[NEXT]);                                                              \
+    emit(2 * (m), hE[PREV], a.fv[0], hE[CUR], a.fv[2], hO[PREV], hO[CUR]);                          \
+    emit(2 * (m) + 1, hE[CUR], a.fv[1], hE[NEXT], a.fv[3], hO[CUR], hO[NEXT]);                      \
+  }
+  for (int m = m0; m < m0 + a.rows && m < a.h; m += 3) {
+    UPFIR2_STEP(0, 1, 2, m)
+    UPFIR2_STEP(1, 2, 0, m + 1)
+    UPFIR2_STEP(2, 0, 1, m + 2)
+  }
+#undef UPFIR2_STEP
+  if (F16) ovf_commit(a.ovf, mx);
+}
+
+// ---- adjoint of the skip FIR (without the add): dv[b,m,n,c] = g * sum_{fy,fx} fk[fy] fk[fx] dout[b, 2m+2-fy, 2n+2-fx, c]   (bf16 gradients)
+// H[Y] = sum_fx fk[fx] dout[Y, 2n+2-fx] (4 loads per row); dv[m] = f3 H[2m-1] + f2 H[2m] + f1 H[2m+1] + f0 H[2m+2]: two new rows per step.
+struct Upfir2BwdArgs {
+  const uint16_t* dout; uint16_t* dv;
+  float fh[4], fv[4];
+  int h, w, vshift, rows;
+};
+
+__global__ void __launch_bounds__(256) upfir2_bwd_kernel2(const Upfir2BwdArgs a) {
+  const int vecs = 1 << a.vshift;
+  const int b = blockIdx.z, m0 = blockIdx.y * a.rows;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (a.w << a.vshift)) return;
+  const int cv = i & (vecs - 1), n = i >> a.vshift;
+  const int sh = a.vshift + 3;
+  const int H2 = 2 * a.h, W2 = 2 * a.w;
+  float wx[4]; int xo[4];
+#pragma unroll
+  for (int fx = 0; fx < 4; fx++) {
+    const int X = 2 * n + 2 - fx;
+    const bool ok = X >= 0 && X < W2;
+    wx[fx] = ok ? a.fh[fx] : 0.f; xo[fx] = (ok ? X : 0) << sh;
+  }
+  const uint16_t* db = a.dout + (((long long)b * H2 * W2) << sh) + cv * 8;
+  uint16_t* ob = a.dv + ((((long long)b * a.h) * a.w + n) << sh) + cv * 8;
+  const long long orow = (long long)a.w << sh;
+  float Ha[8], Hb[8], Hc[8], Hd[8];          // H[2m-1], H[2m], H[2m+1], H[2m+2]
+  auto hrow = [&](int Y, float (&h_)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; e++) h_[e] = 0.f;
+    if (Y >= 0 && Y < H2) {
+      const uint16_t* rp = db + (((long long)Y * W2) << sh);
+      float q0[8], q1[8], q2[8], q3[8];
+      ld8<false>(rp + xo[0], q0); ld8<false>(rp + xo[1], q1); ld8<false>(rp + xo[2], q2); ld8<false>(rp + xo[3], q3);
+#pragma unroll
+      for (int e = 0; e < 8; e++) h_[e] = fmaf(wx[3], q3[e], fmaf(wx[2], q2[e], fmaf(wx[1], q1[e], wx[0] * q0[e])));
+    }
+  };
+  hrow(2 * m0 - 1, Ha);
+  hrow(2 * m0, Hb);
+  for (int m = m0; m < m0 + a.rows && m < a.h; m++) {
+    hrow(2 * m + 1, Hc);
+    hrow(2 * m + 2, Hd);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) o[e] = fmaf(a.fv[3], Ha[e], fmaf(a.fv[2], Hb[e], fmaf(a.fv[1], Hc[e], a.fv[0] * Hd[e])));
+    st8<false>(ob + (long long)m * orow, o);
+#pragma unroll
+    for (int e = 0; e < 8; e++) { Ha[e] = Hc[e]; Hb[e] = Hd[e]; }
+  }
+}
+
+static inline int log2_exact_(int v) { int s = 0; while ((1 << s) < v) s++; return (1 << s) == v ? s : -1; }
+
+// rows per strip: long strips amortise the 3-row warm-up, but small images still have to fill 148 SMs
+static inline int strip_rows(int out_rows, long long ctas_per_row_strip, int unit, int max_rows) {
+  int rows = max_rows;
+  while (rows > unit && ((out_rows + rows - 1) / rows) * ctas_per_row_strip < 2LL * num_sms()) rows -= unit;
+  return rows;
+}
+}  // namespace mgf
+
+using namespace mgf;
+
+extern "C" int mgf_fir4(const void* in, void* out, const float* fk4, float gain, int off, int B, int Hi, int Wi, int Ho, int Wo, int Hv, int Wv,
+                        int C, int in_fwd, int out_fwd, const float* noise, const float* nstr, int64_t noise_bstride, const float* bias, int act,
+                        float alpha, float act_gain, void* stream) {
+  if (!in || !out || !fk4) MGF_FAIL(MGF_E_BADARG, "fir4: null tensor");
+  const int vs = (C % 8) ? -1 : log2_exact_(C / 8);
+  if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "fir4: C/8 must be a power of two (C = %d)", C);
+  if (B <= 0 || B > 65535 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0 || Hv > Ho || Wv > Wo) MGF_FAIL(MGF_E_SHAPE, "fir4: bad sizes");
+  if (off != -1 && off != -2) MGF_FAIL(MGF_E_BADARG, "fir4: off must be -1 (up-convolution second stage) or -2 (its adjoint)");
+  Fir4Args a;
+  a.in = (const uint16_t*)in; a.out = (uint16_t*)out;
+  for (int t = 0; t < 4; t++) { a.fh[t] = fk4[t] * gain; a.fv[t] = fk4[t]; }
+  a.off = off; a.Hi = Hi; a.Wi = Wi; a.Ho = Ho; a.Wo = Wo; a.Hv = Hv; a.Wv = Wv; a.vshift = vs;
+  const bool epi = noise || bias || act || act_gain != 1.f;
+  a.noise = noise; a.nstr = nstr; a.noise_bstride = noise_bstride; a.bias = bias; a.act = act; a.alpha = alpha; a.gain = act_gain;
+  const bool if16 = in_fwd && fwd_f16(), of16 = out_fwd && fwd_f16();
+  a.ovf = of16 ? overflow_flag() : nullptr;
+  const int items = Wo << vs;
+  const int bx = (items + 255) / 256;
+  a.rows = strip_rows(Ho, (long long)bx * B, 3, 30);
+  dim3 grid(bx, (Ho + a.rows - 1) / a.rows, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (if16 && of16) { if (epi) fir4_kernel<true, true, true><<<grid, 256, 0, st>>>(a); else fir4_kernel<true, true, false><<<grid, 256, 0, st>>>(a); }
+  else if (!if16 && !of16) { if (epi) fir4_kernel<false, false, true><<<grid, 256, 0, st>>>(a); else fir4_kernel<false, false, false><<<grid, 256, 0, st>>>(a); }
+  else MGF_FAIL(MGF_E_UNSUP, "fir4: input and output must have the same 16-bit type");
+  MGF_CHECK_LAUNCH("fir4");
+  return 0;
+}
+
+extern "C" int mgf_fir4_pad(const void* dy, void* g, const float* fk4, float gain, int B, int H, int W, int C, void* stream) {
+  // g [B,H+2,W+2,C] = FIR of dy [B,H,W,C] onto the (H+1) x (W+1) grid, zero padding 2, last row / column zero (bf16 gradients)
+  const float flipped[4] = {fk4[3], fk4[2], fk4[1], fk4[0]};
+  return mgf_fir4(dy, g, flipped, gain, -2, B, H, W, H + 2, W + 2, H + 1, W + 1, C, 0, 0, nullptr, nullptr, 0, nullptr, 0, 0.f, 1.f, stream);
+}
+
+extern "C" int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream) {
+  if (!v || !out || !fk4) MGF_FAIL(MGF_E_BADARG, "upfir2_add: null tensor");
+  const int vs = (C % 8) ? -1 : log2_exact_(C / 8);
+  if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: C/8 must be a power of two");
+  if (B <= 0 || B > 65535 || h <= 0 || w <= 0) MGF_FAIL(MGF_E_SHAPE, "upfir2_add: bad image size");
+  Upfir2Args a;
+  a.v = (const uint16_t*)v; a.add = (const uint16_t*)add; a.out = (uint16_t*)out;
+  for (int t = 0; t < 4; t++) { a.fh[t] = fk4[t] * gain; a.fv[t] = fk4[t]; }
+  a.h = h; a.w = w; a.vshift = vs;
+  a.ovf = fwd_f16() ? overflow_flag() : nullptr;
+  const int bx = ((w << vs) + 255) / 256;
+  a.rows = strip_rows(h, (long long)bx * B, 3, 15);
+  dim3 grid(bx, (h + a.rows - 1) / a.rows, B);
+  if (fwd_f16()) upfir2_add_kernel2<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  else upfir2_add_kernel2<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  MGF_CHECK_LAUNCH("upfir2_add");
+  return 0;
+}
+
+extern "C" int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream) {
+  if (!dout || !dv || !fk4) MGF_FAIL(MGF_E_BADARG, "upfir2_bwd: null tensor");
+  const int vs = (C % 8) ? -1 : log2_exact_(C / 8);
+  if (vs < 0) MGF_FAIL(MGF_E_SHAPE, "upfir2_bwd: C/8 must be a power of two");
+  if (B <= 0 || B > 65535 || h <= 0 || w <= 0) MGF_FAIL(MGF_E_SHAPE, "upfir2_bwd: bad image size");
+  Upfir2BwdArgs a;
+  a.dout = (const uint16_t*)dout; a.dv = (uint16_t*)dv;
+  for (int t = 0; t < 4; t++) { a.fh[t] = fk4[t] * gain; a.fv[t] = fk4[t]; }
+  a.h = h; a.w = w; a.vshift = vs;
+  const int bx = ((w << vs) + 255) / 256;
+  a.rows = strip_rows(h, (long long)bx * B, 1, 16);
+  dim3 grid(bx, (h + a.rows - 1) / a.rows, B);
+  upfir2_bwd_kernel2<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  MGF_CHECK_LAUNCH("upfir2_bwd");
+  return 0;
+}

@@ -29,7 +29,8 @@ SQRT_HALF = math.sqrt(0.5)
 import os as _os
 BWD_SIDE_REDUCTIONS = _os.environ.get("MGF_BWD_SIDE", "1") != "0"      # A/B switch: d(style) reductions on the side stream
 LRELU_ALPHA = 0.2
-TWO_STAGE_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_MAX_RES", "128"))   # A/B switch: up-conv dgrad as FIR + 9-tap strided conv up to this output size
+TWO_STAGE_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_MAX_RES", "65536"))   # A/B switch: up-conv dgrad as FIR + 9-tap strided conv up to this output size
+TWO_STAGE_FWD_MIN_RES = int(_os.environ.get("MGF_TWO_STAGE_FWD_MIN_RES", "8"))  # A/B switch: up-conv forward as transposed conv (9 taps) + FIR pass from this output size
 FIR4_TAPS = (ctypes.c_float * 4)(0.125, 0.375, 0.375, 0.125)      # [1,3,3,1] / 8 (symmetric: flipping is a no-op); gain 4 = up^2 passed separately
 
 
@@ -164,9 +165,21 @@ class SynthesisEngine:
             L.phases = 1
         else:
             Weff = torch.einsum("ptk,oik->ptoi", self.Cm.to(dev), Wk)                  # [4, 9, O, I]
-            L.Bf = Weff.permute(1, 0, 2, 3).reshape(9, 4 * O, I).contiguous()           # [9, 4*O, I]
-            L.taps_f = [(0, ty - 1, tx - 1, ty * 3 + tx) for ty in range(3) for tx in range(3)]
             L.phases = 4
+            # forward in the reference's own two-stage form (conv2d_resample.py:117-134): ct = conv_transpose2d(x, w, stride 2) on the
+            # (2h+1) x (2w+1) grid, then the 4x4 FIR (mgf_fir4, with the layer tail fused).  The four parities of ct are four small GEMMs
+            # over the low-resolution grid with 4 / 2 / 2 / 1 taps (9 in all, on the plain [9, O, I] weights) instead of the 4 x 9 taps of
+            # the FIR-folded phase kernels: a quarter of the tensor work and of the L2 -> shared-memory operand traffic, for one extra
+            # HBM round trip of the (2h+1)^2 tensor.  ct[2m+ey, 2n+ex] = sum_{a,b} x[m-a, n-b] w[2a+ey, 2b+ex] over the taps that exist.
+            L.two_stage_fwd = L.res >= TWO_STAGE_FWD_MIN_RES
+            if L.two_stage_fwd:
+                L.Bf = Wk.permute(2, 0, 1).contiguous()                                   # [9, O, I]
+                L.taps_f = ([(0, -a, -b, (2 * a) * 3 + 2 * b) for a in (0, 1) for b in (0, 1)] + [(0, -a, 0, (2 * a) * 3 + 1) for a in (0, 1)]
+                            + [(0, 0, -b, 3 + 2 * b) for b in (0, 1)] + [(0, 0, 0, 4)])
+                L.phase_ntaps = (4, 2, 2, 1)
+            else:
+                L.Bf = Weff.permute(1, 0, 2, 3).reshape(9, 4 * O, I).contiguous()       # [9, 4*O, I]
+                L.taps_f = [(0, ty - 1, tx - 1, ty * 3 + tx) for ty in range(3) for tx in range(3)]
             # input gradient in the reference's own two-stage form (adjoint of conv_transpose2d(stride 2) -> FIR): g = FIR4(dy) on the
             # (2h+1) x (2w+1) grid (mgf_fir4_pad), then dx[i,j] = sum_k W_k^T g[2i+ky, 2j+kx]: a stride-2 3x3 conv = 9 taps over the four
             # phase views of g (view (ky%2, kx%2), shift (ky//2, kx//2)) instead of 36 taps of the folded four-phase kernels
@@ -186,6 +199,7 @@ class SynthesisEngine:
         L._Bf16 = None
         if m.up == 1:
             L.two_stage = False
+            L.two_stage_fwd = False
         # 32 -> 32 channel 3x3 layers (the 1024^2 block): 64-byte pixel rows halve the TMA efficiency, so view two neighbouring pixels as
         # one 64-channel super-pixel (same memory) and expand the weights to the block form [9][(po,o)][(pi,i)]
         L.superpix = (m.up == 1 and O == 32 and I == 32 and L.res >= 64 and not L.shared_w and m.transformer is None)
@@ -345,9 +359,24 @@ class SynthesisEngine:
         noise, nbs = self._noise_of(L, st, B, H, Wd, draw=True)
         nstr = L.nstr if noise is not None else None
         kw = dict(osy=L.up, osx=L.up, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1))
+        if L.two_stage_fwd:
+            # transposed convolution onto the (2h+1) x (2w+1) grid (buffer padded to even sizes; the extra row / column come out as exact
+            # zeros: their taps read only TMA zero fill), then the FIR pass -- fused with noise + bias + leaky-ReLU unless attention follows
+            ct = self._buf(st, f"ct{L.idx}", (B, H + 2, Wd + 2, L.O), fwd=True)
+            tc.conv_tc([a_in], Wf, L.taps_f, (B, h + 1, w + 1), 4, L.O, ct, scale_n=scale_n, tag="g.fwd", phase_ntaps=L.phase_ntaps,
+                       alg_scale=float(h * w) / float((h + 1) * (w + 1)), **kw)
+            out = self._buf(st, f"y{L.idx}" if L.attn else f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
+            tail = L.has_bias and not L.attn
+            _lib.check(_L().mgf_fir4(_p(ct), _p(out), FIR4_TAPS, 4.0, -1, B, H + 2, Wd + 2, H, Wd, H, Wd, L.O, 1, 1,
+                                     _p(noise) if not L.attn else None, _p(nstr) if not L.attn else None, nbs, _p(L.bias) if tail else None,
+                                     1 if tail else 0, LRELU_ALPHA, L.gain if tail else 1.0, _s(self.dev)), "mgf_fir4")
+            if not L.attn:
+                return out
+            y = out
         if L.attn:
             y = self._buf(st, f"y{L.idx}", (B, H, Wd, L.O), fwd=True)
-            tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, scale_n=scale_n, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
+            if not L.two_stage_fwd:
+                tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, scale_n=scale_n, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             probs = None
             if st.get("want_probs"):                            # attention maps requested: [B, HW, 16] fp32 per attention layer, in layer order

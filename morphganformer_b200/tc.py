@@ -30,7 +30,8 @@ class ConvTcDesc(ctypes.Structure):
                 ("add", c_void_p),
                 ("actgrad", c_int32), ("ag_alpha", c_float), ("ag_gain", c_float),
                 ("bn", c_int32), ("reduce_per_sample", c_int32),
-                ("ab_fwd", c_int32), ("out_fwd", c_int32), ("x_fwd", c_int32), ("add_fwd", c_int32), ("superpix", c_int32), ("noise_bstride", c_int64)]
+                ("ab_fwd", c_int32), ("out_fwd", c_int32), ("x_fwd", c_int32), ("add_fwd", c_int32), ("superpix", c_int32), ("noise_bstride", c_int64),
+                ("phase_ntaps", c_int32 * 4)]
 
 
 _lib.SIGNATURES["mgf_conv_tc"] = (ctypes.c_int, [ctypes.POINTER(ConvTcDesc), c_void_p])
@@ -56,7 +57,8 @@ PROFILE = None
 
 def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 0), ofx=(0, 0, 0, 0), scale_n=None,
             reduce_out=None, X=None, noise=None, noise_strength=None, bias=None, act=0, alpha=0.2, gain=1.0, add=None,
-            actgrad=False, ag_alpha=0.2, ag_gain=1.0, bn=0, reduce_per_sample=False, alg_scale=1.0, tag="", fwd=True, superpix=False, noise_bstride=0):
+            actgrad=False, ag_alpha=0.2, ag_gain=1.0, bn=0, reduce_per_sample=False, alg_scale=1.0, tag="", fwd=True, superpix=False, noise_bstride=0,
+            phase_ntaps=None):
     # fwd=True: a forward launch -- operands, output and `add` are forward-dtype tensors (bf16 or fp16, _lib.set_forward_dtype);
     # fwd=False: a gradient launch -- operands/output/add are bf16 gradients; X (saved activation) is a forward tensor either way.
     """acts: list of NHWC bf16 tensors or descriptor tuples; w: [G, T, NT, K] bf16 contiguous; taps: [(amap, dy, dx, wz)];
@@ -93,6 +95,10 @@ def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 
     d.bn, d.reduce_per_sample = bn, int(bool(reduce_per_sample))
     d.superpix = int(bool(superpix))
     d.noise_bstride = int(noise_bstride)
+    if phase_ntaps is not None:          # per-phase tap lists: `taps` is their concatenation, all phases share the [T][Cout][K] weights
+        assert len(phase_ntaps) == phases and sum(phase_ntaps) == len(taps)
+        for i, n in enumerate(phase_ntaps):
+            d.phase_ntaps[i] = n
     prof = PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -101,7 +107,7 @@ def conv_tc(acts, w, taps, grid, phases, cout, out, osy=1, osx=1, ofy=(0, 0, 0, 
         _lib.check(_lib.lib().mgf_conv_tc(ctypes.byref(d), _lib.stream_ptr(out.device)), "mgf_conv_tc")
     if prof is not None:
         e1.record()
-        ex = 2.0 * d.NB * d.GH * d.GW * (phases * cout) * w.shape[3] * len(taps)
+        ex = 2.0 * d.NB * d.GH * d.GW * (cout if phase_ntaps is not None else phases * cout) * w.shape[3] * len(taps)
         prof.append((tag, e0, e1, ex * alg_scale, ex, "B%d %dx%d C%d->%d x%d taps%d %s" % (d.NB, d.GH, d.GW, w.shape[3], cout, phases, len(taps),
                      "+".join(k for k, v in (("red", reduce_out), ("X", X), ("add", add), ("noise", noise), ("bias", bias)) if v is not None))))
     return out

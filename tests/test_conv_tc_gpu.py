@@ -10,6 +10,15 @@ import util
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _bf16_operands():
+    """Kernel-level tests of mgf_conv_tc build their operands as bf16 tensors: run the library in bf16 forward storage here (the fp16
+    forward mode of the same kernel -- one instruction-descriptor bit and the pack/unpack type -- is covered by the engine tests)."""
+    from morphganformer_b200 import _lib
+    _lib.set_forward_dtype("bf16")
+    yield
+
+
 def _bf(t):
     return t.to(torch.bfloat16)
 

@@ -108,6 +108,40 @@ def test_two_stage_upconv_input_gradient_formula():
     assert (dx - gx_ref).abs().max() < 1e-5 * gx_ref.abs().max().clamp(min=1.0)
 
 
+def test_two_stage_upconv_forward_tap_table_and_fir_offsets():
+    """What the engine computes for an up-convolution's FORWARD pass: the transposed convolution as four parity GEMMs over the (h+1) x (w+1)
+    grid with 4 / 2 / 2 / 1 taps on the plain [9, O, I] weights (tc.conv_tc(phase_ntaps=...), written into the [2h+2, 2w+2] buffer through the
+    strided phase views), then mgf_fir4(off = -1): out[Y, X] = 4 * sum_{t,u} f[t] f[u] ct[Y-1+t, X-1+u] with zero padding -- equals the oracle's
+    conv2d_resample(up=2, padding=1, flip_weight=False) (reference conv2d_resample.py:117-134)."""
+    B, I, Oc, h, w = 2, 5, 4, 6, 7
+    x = util.case_tensor((B, I, h, w), 1)
+    W = util.case_tensor((Oc, I, 3, 3), 2) * 0.3
+    f = O.setup_filter([1, 3, 3, 1])
+    ref = O.conv2d_resample(x, W, f=f, up=2, padding=1, flip_weight=False)
+    taps = ([(0, -a, -b, (2 * a) * 3 + 2 * b) for a in (0, 1) for b in (0, 1)] + [(0, -a, 0, (2 * a) * 3 + 1) for a in (0, 1)]
+            + [(0, 0, -b, 3 + 2 * b) for b in (0, 1)] + [(0, 0, 0, 4)])             # engine._fold_layer, two_stage_fwd
+    counts, ofy, ofx = (4, 2, 2, 1), (0, 0, 1, 1), (0, 1, 0, 1)
+    Wk = W.reshape(Oc, I, 9)
+    ct = torch.full((B, Oc, 2 * h + 2, 2 * w + 2), float("nan"))
+    xp = F.pad(x, (1, 1, 1, 1))                                                  # TMA zero fill outside the image
+    t0 = 0
+    for ph in range(4):
+        acc = torch.zeros(B, Oc, h + 1, w + 1)
+        for (_, dy, dx, wz) in taps[t0:t0 + counts[ph]]:
+            sl = xp[:, :, 1 + dy:1 + dy + h + 1, 1 + dx:1 + dx + w + 1]         # x[m + dy, n + dx] for m in [0, h], n in [0, w]
+            acc = acc + torch.einsum("bihw,oi->bohw", sl, Wk[:, :, wz])
+        ct[:, :, ofy[ph]::2, ofx[ph]::2] = acc
+        t0 += counts[ph]
+    assert torch.isfinite(ct).all() and ct[:, :, 2 * h + 1].abs().max() == 0 and ct[:, :, :, 2 * w + 1].abs().max() == 0
+    f1 = torch.tensor([1, 3, 3, 1.0]) / 8
+    cp = F.pad(ct, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for t in range(4):
+        for u in range(4):
+            out += 4 * f1[t] * f1[u] * cp[:, :, t:t + 2 * h, u:u + 2 * w]          # ct[Y - 1 + t, X - 1 + u]
+    assert (out - ref).abs().max() < 1e-5
+
+
 def test_mapping_pack_layout_reproduces_oracle_mapping():
     """pack_mapping's flat layout (what mgf_mapping_fwd reads: mapping.cu) interpreted in numpy reproduces the oracle's ws: pins the gain /
     positional-map folding and the offsets on the CPU."""
