@@ -184,16 +184,22 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
 
 // Fused layer tail for one 128 x BN accumulator tile (called by all four warps of an epilogue group after the tfull wait).
 // Row `valid`/(x, y, b) identify this thread's pixel; tacc = TMEM address of the tile (lane quarter already applied).
-template <int BN, int NSTG>
-__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane, float nz, float nz1,
+template <int BN, int NSTG, int GW32>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane,
+                                              float nz0, float nz1, float nz2, float nz3,
                                               uint8_t* stg, int group, int r, float* racc, uint64_t* xbar, uint32_t xphase, uint64_t* tempty_bar) {
-      const int phase_idx = t.n0 / p.Cout, co0 = t.n0 % p.Cout;
-      const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
-      const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
-      const long long obase = pix * p.OC + co0;
+      // A tile may span several output phases (BN > Cout, e.g. the four parities of an up-convolution in one 128- or 256-column tile, so
+      // the activation tiles are fetched once for all of them): phase and channel offset are per 32-column chunk; a staged group of
+      // GW32 * 32 columns never straddles two phases (host check).  nz0..nz3: noise of this thread's pixel in the tile's phases
+      // (super-pixel rows: nz0 / nz1 = left / right pixel of the pair).
+      const int phase_lo = t.n0 / p.Cout;
       float ovf_mx = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
+        const int col = t.n0 + c * 32;
+        const int phase_idx = col / p.Cout, co = col - phase_idx * p.Cout;
+        const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
+        const long long obase = (((long long)b * p.OH + oy) * p.OW + ox) * p.OC + co;      // this chunk's 32 output channels of this pixel
         uint32_t raw[32];
         tmem_ld32(tacc + (uint32_t)(c * 32), raw);
         if (c == BN / 32 - 1) {          // the accumulator now lives in registers: hand the TMEM stage back to the MMA issuer at once
@@ -205,7 +211,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         for (int j = 0; j < 32; j++) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
         float xv[32];
         const bool needX = (p.X != nullptr) && (p.reduce_out != nullptr || p.actgrad);
-        constexpr int GX32 = (BN >= 64) ? 2 : 1;
+        constexpr int GX32 = GW32;
         if (needX && p.x_tma) {
           // the X tile of this (single-group) output tile was TMA-loaded into the staging buffer while the MMAs were running:
           // read this thread's row (same swizzle as the store path); the outputs later overwrite exactly the slots read here.
@@ -222,7 +228,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           }
         } else if (needX) {
           if (valid) {
-            const uint4* xp = reinterpret_cast<const uint4*>(p.X + obase + c * 32);
+            const uint4* xp = reinterpret_cast<const uint4*>(p.X + obase);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
               const uint4 u = __ldg(xp + q);
@@ -261,12 +267,13 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           for (int j = 0; j < 8; j++) { const float4 f = __ldg(sp + j); v[4 * j] *= f.x; v[4 * j + 1] *= f.y; v[4 * j + 2] *= f.z; v[4 * j + 3] *= f.w; }
         }
         if (p.noise) {
-          const float nzc = (p.superpix && (c & 1)) ? nz1 : nz;      // super-pixel rows: odd 32-column chunk = right pixel of the pair
+          const int k = p.superpix ? (c & 1) : phase_idx - phase_lo;  // super-pixel rows: odd 32-column chunk = right pixel of the pair
+          const float nzc = k == 0 ? nz0 : k == 1 ? nz1 : k == 2 ? nz2 : nz3;
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] += nzc;
         }
         if (p.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + co0 + c * 32);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + co);
 #pragma unroll
           for (int j = 0; j < 8; j++) { const float4 f = __ldg(bp + j); v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w; }
         }
@@ -281,7 +288,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           for (int j = 0; j < 32; j++) v[j] *= p.gain;
         }
         if (p.add && valid) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.add + obase + c * 32);
+          const uint4* ap = reinterpret_cast<const uint4*>(p.add + obase);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const uint4 u = __ldg(ap + q);
@@ -296,10 +303,13 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         }
         // stage this thread's 32 outputs (64 B) into the swizzled shared-memory tile; a 64-channel group (or the whole tile for
         // BN = 32) then leaves with ONE TMA store: fully coalesced, asynchronous, clipped at the image border by the hardware.
-        constexpr int GW32 = (BN >= 64) ? 2 : 1;           // 32-column chunks per staged group
+        // GW32 = 32-column chunks per staged group (2: 128-byte rows, 1: 64-byte rows).  Tiles wider than one group with GW32 == 1
+        // (32-channel phases inside a 128-column tile) alternate between the two 8 KB halves of the staging tile.
         const int h = c % GW32;
-        if (h == 0 && !p.x_tma) {                          // the previous store must have finished reading the staging tile
-          if (r == 0) tma_store_wait_read<NSTG - 1>();     // (x_tma: the caller already did this before loading X into it)
+        constexpr bool SPLIT = (GW32 == 1 && BN > 32);
+        uint8_t* stg_c = SPLIT ? stg + (c & 1) * (STG_BYTES / 2) : stg;
+        if (h == 0 && (!p.x_tma || SPLIT)) {               // the previous store must have finished reading the staging tile
+          if (r == 0) { if (SPLIT) tma_store_wait_read<1>(); else tma_store_wait_read<NSTG - 1>(); }   // (x_tma: the caller already did this before loading X into it)
           group_sync(group);
         }
         if (p.ovf) {
@@ -307,7 +317,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           for (int j = 0; j < 32; j++) ovf_mx = fmaxf(ovf_mx, fabsf(v[j]));
         }
         {
-          uint8_t* row = stg + r * (GW32 * 64);
+          uint8_t* row = stg_c + r * (GW32 * 64);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             uint4 u;
@@ -321,7 +331,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         if (h == GW32 - 1) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           group_sync(group);
-          if (r == 0) tma_store_4d(&p.omap[phase_idx], stg, co0 + (c / GW32) * (GW32 * 32), t.x0, t.y0, t.b0);
+          if (r == 0) tma_store_4d(&p.omap[phase_idx], stg_c, co - h * 32, t.x0, t.y0, t.b0);
         }
       }
       ovf_commit(p.ovf, ovf_mx);
@@ -339,9 +349,10 @@ __device__ __forceinline__ void flush_reduce(const Params& p, float* racc, int k
   group_sync(group);
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool G32 = false>     // G32: staged output groups are 32 columns wide (32-channel phases inside a wider tile)
 __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ Params p) {
   using C = Cfg<BN, BK>;
+  constexpr int GW32 = (BN >= 64 && !G32) ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];                      // swizzled tiles need 1024-byte aligned bases
   uint8_t* stg_base = smem + C::STAGES * C::STAGE;                       // 2 x 16 KB epilogue staging, 1024-byte aligned
   float* racc_base = reinterpret_cast<float*>(stg_base + 2 * C::NSTG * STG_BYTES); // 2 x 256 floats: per-group d(style) partial sums
@@ -447,19 +458,24 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
           tma_load_4d(&p.xmap, &xbar[as], stg, t.n0, t.x0, t.y0, t.b0);
         }
       }
-      float nz = 0.f, nz1 = 0.f;              // noise value(s) of this thread's pixel, fetched before the accumulator wait
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};     // noise value(s) of this thread's pixel, fetched before the accumulator wait
       if (p.noise && valid) {
         if (p.superpix) {                     // row = pixel pair (2x, 2x+1) of a [H, 2*GW] noise plane
           const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)b * p.noise_bstride + (long long)y * (2 * p.OW) + 2 * x));
-          nz = n2.x * nstr; nz1 = n2.y * nstr;
+          nz[0] = n2.x * nstr; nz[1] = n2.y * nstr;
         } else {
-          const int ph = t.n0 / p.Cout;
-          nz = __ldg(p.noise + (long long)b * p.noise_bstride + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+          const int ph0 = t.n0 / p.Cout;      // one value per output phase the tile covers (BN > Cout: several)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int ph = ph0 + k;
+            if (k == 0 || (k * p.Cout < BN && ph < 4))
+              nz[k] = __ldg(p.noise + (long long)b * p.noise_bstride + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+          }
         }
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, C::NSTG>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz, nz1,
+      epilogue_tile<BN, C::NSTG, GW32>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz[0], nz[1], nz[2], nz[3],
                                  stg, as, r, racc, &xbar[as], aphase, &tempty[as]);
       aphase ^= 1;
     }
@@ -645,19 +661,24 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
           tma_load_4d(&p.xmap, &xbar[as], stg, t.n0, t.x0, t.y0, t.b0);
         }
       }
-      float nz = 0.f, nz1 = 0.f;              // noise value(s) of this thread's pixel, fetched before the accumulator wait
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};     // noise value(s) of this thread's pixel, fetched before the accumulator wait
       if (p.noise && valid) {
         if (p.superpix) {                     // row = pixel pair (2x, 2x+1) of a [H, 2*GW] noise plane
           const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)b * p.noise_bstride + (long long)y * (2 * p.OW) + 2 * x));
-          nz = n2.x * nstr; nz1 = n2.y * nstr;
+          nz[0] = n2.x * nstr; nz[1] = n2.y * nstr;
         } else {
-          const int ph = t.n0 / p.Cout;
-          nz = __ldg(p.noise + (long long)b * p.noise_bstride + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+          const int ph0 = t.n0 / p.Cout;      // one value per output phase the tile covers (BN > Cout: several)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int ph = ph0 + k;
+            if (k == 0 || (k * p.Cout < BN && ph < 4))
+              nz[k] = __ldg(p.noise + (long long)b * p.noise_bstride + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+          }
         }
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      epilogue_tile<BN, C::NSTG>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz, nz1,
+      epilogue_tile<BN, C::NSTG, (BN >= 64 ? 2 : 1)>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz[0], nz[1], nz[2], nz[3],
                                  stg, as, r, racc, &xbar[as], aphase, &tempty[as]);
       aphase ^= 1;
     }
@@ -702,8 +723,8 @@ static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* d
 
 
 // output tensor maps for the TMA-store epilogue: one per output phase, box = {64 or 32 channels, TW, TH, TB} of the phase grid
-static int encode_out_maps(Params& p, const mgf_conv_tc_desc* d, int BN, int TW, int TH, int TB) {
-  const int gwd = BN >= 64 ? 64 : 32;
+static int encode_out_maps(Params& p, const mgf_conv_tc_desc* d, int BN, int TW, int TH, int TB, bool g32 = false) {
+  const int gwd = (BN >= 64 && !g32) ? 64 : 32;
   if (((uintptr_t)d->out & 15) || (d->OC * 2) % 16) MGF_FAIL(MGF_E_ALIGN, "conv_tc: output must be 16-byte aligned with OC %% 8 == 0");
   for (int ph = 0; ph < d->phases; ph++) {
     const long long ofy = d->ofy[ph], ofx = d->ofx[ph];
@@ -732,16 +753,16 @@ static int encode_x_map(Params& p, const mgf_conv_tc_desc* d, int BN, int TW, in
   return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool G32 = false>
 static int launch(const Params& p, int grid, cudaStream_t st) {
   using C = Cfg<BN, BK>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, G32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc: cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_tc_kernel<BN, BK><<<grid, 320, C::SMEM, st>>>(p);
+  conv_tc_kernel<BN, BK, G32><<<grid, 320, C::SMEM, st>>>(p);
   MGF_CHECK_LAUNCH("conv_tc");
   return 0;
 }
@@ -761,16 +782,18 @@ static int launch_halo(const Params& p, int grid, cudaStream_t st) {
 }
 
 static bool g_halo_enabled = true;
+static bool g_halo_phases = false;  // halo kernel also for multi-phase (up-convolution) launches; default: those run as one wide tile per pixel block
 static int g_halo_nstg = 1;        // epilogue staging tiles per group in the halo kernel (A/B switch: mgf_conv_tc_set_halo(1 | 2 << 1))
 
 }  // namespace tc
 }  // namespace mgf
 
 extern "C" int mgf_conv_tc_set_halo(int mode) {
-  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2)
+  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2); bit 3: halo kernel for multi-phase launches too
   mgf::tc::g_halo_enabled = (mode & 1) != 0;
   const int n = (mode >> 1) & 3;
   mgf::tc::g_halo_nstg = (n == 2) ? 2 : 1;
+  mgf::tc::g_halo_phases = (mode & 8) != 0;
   return 0;
 }
 
@@ -797,8 +820,14 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   } else if (d->w_NT != NT) MGF_FAIL(MGF_E_SHAPE, "conv_tc: weight NT (%lld) != phases*Cout (%lld)", (long long)d->w_NT, NT);
   if (d->OC < d->Cout || d->OC % 8) MGF_FAIL(MGF_E_SHAPE, "conv_tc: bad output channel stride");
   int BN = d->bn;
-  if (BN == 0) BN = (d->Cout % 256 == 0) ? 256 : (d->Cout % 128 == 0) ? 128 : (d->Cout % 64 == 0) ? 64 : 32;
-  if (!(BN == 32 || BN == 64 || BN == 128 || BN == 256) || d->Cout % BN) MGF_FAIL(MGF_E_SHAPE, "conv_tc: BN=%d does not divide Cout=%d", BN, d->Cout);
+  // a tile either lies inside one phase (BN divides Cout) or covers whole phases (Cout divides BN, BN divides phases * Cout): the latter
+  // fetches every activation tile once for all the phases it covers (the four parities of an up-convolution in one tile)
+  auto bn_ok = [&](int bn) { return (d->Cout % bn == 0) || (!ph_taps && !d->superpix && bn % d->Cout == 0 && NT % bn == 0); };
+  if (BN == 0) BN = bn_ok(256) ? 256 : bn_ok(128) ? 128 : bn_ok(64) ? 64 : 32;
+  if (!(BN == 32 || BN == 64 || BN == 128 || BN == 256) || !bn_ok(BN)) MGF_FAIL(MGF_E_SHAPE, "conv_tc: BN=%d does not fit Cout=%d x %d phases", BN, d->Cout, d->phases);
+  if ((d->reduce_out || d->X || d->add) && d->bn == 0) {        // epilogues that read per-pixel tensors stay inside one phase
+    BN = (d->Cout % 256 == 0) ? 256 : (d->Cout % 128 == 0) ? 128 : (d->Cout % 64 == 0) ? 64 : 32;
+  }
   if (d->GW < 1 || d->GH < 1 || d->NB < 1) MGF_FAIL(MGF_E_SHAPE, "conv_tc: empty grid");
   const int per_sample = d->w_G > 1 ? 1 : 0;
   if (per_sample && d->w_G != d->NB) MGF_FAIL(MGF_E_SHAPE, "conv_tc: per-sample weights need G == NB");
@@ -810,7 +839,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   // resident weights for many tiles
   // (measured: a win for C = 64 -- 0.95 -> 0.68 ms on 64->64 @1024^2 x8 -- but not for C = 128, where the generic kernel's
   // 128-wide N tile beats two 64-wide halo passes; scripts/bench_conv_tc.py)
-  bool halo = g_halo_enabled && !ph_taps && d->n_a == 1 && d->ntaps == 9 && (Cc == 64 || Cc == 32) && d->bn == 0 && d->GW >= 16 &&
+  bool halo = g_halo_enabled && !ph_taps && (d->phases == 1 || g_halo_phases) && d->n_a == 1 && d->ntaps == 9 && (Cc == 64 || Cc == 32) && d->bn == 0 && d->GW >= 16 &&
               (long long)d->GH * d->GW >= 256LL * 256 && (per_sample || d->w_G == 1);
   if (halo) {
     int seen = 0;
@@ -882,8 +911,10 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     // tiny images: a 128 x 256 tile leaves most of the 148 SMs idle while a few CTAs stream the whole weight tensor through their
     // own L2 port (measured 0.12 ms for a 4x4 layer).  Narrow the N tile until the grid covers the machine.
     const long long mt = (long long)p.tilesW * p.tilesH * p.tilesB;
-    while (BN > 32 && mt * (NT / BN) < num_sms() / 2) BN >>= 1;
+    while (BN > 32 && mt * (NT / BN) < num_sms() / 2 && bn_ok(BN >> 1)) BN >>= 1;
   }
+  const bool g32 = BN >= 64 && (d->Cout % 64) != 0;      // phases of 32 channels inside a wider tile: 32-column staged groups
+  if (BN > d->Cout && (d->reduce_out || d->X || d->add)) MGF_FAIL(MGF_E_UNSUP, "conv_tc: tiles that span phases are a forward-only form (no reduce_out / X / add)");
   p.NT = (int)NT; p.Cout = d->Cout; p.n_tiles = (int)(NT / BN); p.per_sample = per_sample; p.w_T = (int)d->w_T;
   const long long total = (long long)p.tilesW * p.tilesH * p.tilesB * p.n_tiles;
   if (total > 0x7fffffffLL) MGF_FAIL(MGF_E_SHAPE, "conv_tc: too many tiles");
@@ -932,10 +963,17 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
     p.ovf = p.out_f16 ? overflow_flag() : nullptr;
   }
-  if (int e = encode_out_maps(p, d, BN, TW, TH, TB)) return e;
+  if (int e = encode_out_maps(p, d, BN, TW, TH, TB, g32)) return e;
   if (int e = encode_x_map(p, d, BN, TW, TH, TB, p.rows)) return e;
   int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g32) {
+    if (BN == 128 && BK == 64) return launch<128, 64, true>(p, grid, st);
+    if (BN == 128 && BK == 32) return launch<128, 32, true>(p, grid, st);
+    if (BN == 64 && BK == 64) return launch<64, 64, true>(p, grid, st);
+    if (BN == 64 && BK == 32) return launch<64, 32, true>(p, grid, st);
+    MGF_FAIL(MGF_E_UNSUP, "conv_tc: no 32-column-group kernel for BN=%d BK=%d", BN, BK);
+  }
 #define MGF_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch<bn, bk>(p, grid, st);
   MGF_TC_CASE(256, 64) MGF_TC_CASE(128, 64) MGF_TC_CASE(64, 64) MGF_TC_CASE(32, 64)
   MGF_TC_CASE(256, 32) MGF_TC_CASE(128, 32) MGF_TC_CASE(64, 32) MGF_TC_CASE(32, 32)

@@ -30,7 +30,12 @@ import os as _os
 BWD_SIDE_REDUCTIONS = _os.environ.get("MGF_BWD_SIDE", "1") != "0"      # A/B switch: d(style) reductions on the side stream
 LRELU_ALPHA = 0.2
 TWO_STAGE_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_MAX_RES", "65536"))   # A/B switch: up-conv dgrad as FIR + 9-tap strided conv up to this output size
-TWO_STAGE_FWD_MIN_RES = int(_os.environ.get("MGF_TWO_STAGE_FWD_MIN_RES", "8"))  # A/B switch: up-conv forward as transposed conv (9 taps) + FIR pass from this output size
+# A/B switches: up-conv forward as transposed conv (9 taps over four parity GEMMs) + FIR pass for output sizes in [MIN, MAX]; above MAX the
+# FIR-folded four-phase form runs in ONE tile per pixel block (BN = 4 * Cout columns, activation tiles fetched once for the four phases)
+# with the layer tail fused -- measured: the folded form costs 4x the tensor work, which only matters while the layer is compute-bound
+# (<= 128^2 outputs, C >= 256); at 256^2 .. 1024^2 the extra HBM round trip + FIR pass of the two-stage form costs more than it saves
+TWO_STAGE_FWD_MIN_RES = int(_os.environ.get("MGF_TWO_STAGE_FWD_MIN_RES", "8"))
+TWO_STAGE_FWD_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_FWD_MAX_RES", "128"))
 FIR4_TAPS = (ctypes.c_float * 4)(0.125, 0.375, 0.375, 0.125)      # [1,3,3,1] / 8 (symmetric: flipping is a no-op); gain 4 = up^2 passed separately
 
 
@@ -171,7 +176,7 @@ class SynthesisEngine:
             # over the low-resolution grid with 4 / 2 / 2 / 1 taps (9 in all, on the plain [9, O, I] weights) instead of the 4 x 9 taps of
             # the FIR-folded phase kernels: a quarter of the tensor work and of the L2 -> shared-memory operand traffic, for one extra
             # HBM round trip of the (2h+1)^2 tensor.  ct[2m+ey, 2n+ex] = sum_{a,b} x[m-a, n-b] w[2a+ey, 2b+ex] over the taps that exist.
-            L.two_stage_fwd = L.res >= TWO_STAGE_FWD_MIN_RES
+            L.two_stage_fwd = TWO_STAGE_FWD_MIN_RES <= L.res <= TWO_STAGE_FWD_MAX_RES
             if L.two_stage_fwd:
                 L.Bf = Wk.permute(2, 0, 1).contiguous()                                   # [9, O, I]
                 L.taps_f = ([(0, -a, -b, (2 * a) * 3 + 2 * b) for a in (0, 1) for b in (0, 1)] + [(0, -a, 0, (2 * a) * 3 + 1) for a in (0, 1)]

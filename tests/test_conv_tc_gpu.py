@@ -171,3 +171,34 @@ def test_halo_per_sample_dgrad_epilogue_and_phases():
     for ph, (py, px) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
         ref4[:, :, py::2, px::2] = F.conv2d(x.float().permute(0, 3, 1, 2), w4[ph].float(), padding=1)
     _check(out4, ref4)
+
+
+@pytest.mark.parametrize("cfg", [(2, 40, 24, 64, 32), (1, 32, 32, 128, 64), (2, 16, 16, 256, 128), (1, 8, 8, 64, 256)])
+@pytest.mark.parametrize("halo_mode", [1, 9])
+def test_four_phase_upconv_form_in_one_tile_with_fused_tail(cfg, halo_mode):
+    """FIR-folded up-convolution form: 4 output phases x Cout columns.  The tile spans whole phases when 4 * Cout fits 128 / 256 columns
+    (32-channel phases use the 32-column staged groups), so activation tiles are fetched once for the four phases; noise (per phase!),
+    bias and leaky-ReLU run in the epilogue.  halo_mode 9 forces the older one-phase-per-tile halo kernel where it applies (same result)."""
+    from morphganformer_b200 import tc, _lib
+    b, h, w, ci, co = cfg
+    x = _bf(util.case_tensor((b, h, w, ci), 11))
+    w4 = _bf(util.case_tensor((4, co, ci, 3, 3), 12) * (1.0 / np.sqrt(9 * ci)))
+    wp4 = w4.permute(3, 4, 0, 1, 2).reshape(1, 9, 4 * co, ci).contiguous()
+    noise = util.case_tensor((2 * h, 2 * w), 13)
+    nstr = torch.tensor([0.4])
+    bias = util.case_tensor((co,), 14) * 0.3
+    scale = util.case_tensor((b, 4 * co), 15).abs() + 0.5
+    out4 = torch.full((b, 2 * h, 2 * w, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.lib().mgf_conv_tc_set_halo(halo_mode)
+    try:
+        tc.conv_tc([x.cuda()], wp4.cuda(), tc.TAPS_3X3, (b, h, w), 4, co, out4, osy=2, osx=2, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1),
+                   scale_n=scale.cuda(), noise=noise.cuda(), noise_strength=nstr.cuda(), bias=bias.cuda(), act=1, alpha=0.2, gain=1.3)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().mgf_conv_tc_set_halo(1)
+    ref4 = torch.zeros(b, co, 2 * h, 2 * w)
+    for ph, (py, px) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
+        y = F.conv2d(x.float().permute(0, 3, 1, 2), w4[ph].float(), padding=1) * scale[:, ph * co:(ph + 1) * co].reshape(b, co, 1, 1)
+        ref4[:, :, py::2, px::2] = y
+    ref4 = F.leaky_relu(ref4 + noise * nstr + bias.reshape(1, co, 1, 1), 0.2) * 1.3
+    _check(out4, ref4)

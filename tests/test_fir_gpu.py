@@ -68,7 +68,8 @@ def test_fir4_pad_adjoint_of_the_second_stage(shape):
     y = O.upfirdn2d(ct, O.setup_filter([1, 3, 3, 1]), padding=[1, 1, 1, 1], gain=4)
     ref, = torch.autograd.grad(y, [ct], dy)
     g = torch.full((B, H + 2, W + 2, C), float("nan"), dtype=torch.bfloat16, device="cuda")
-    _lib.check(L.mgf_fir4_pad(_nhwc(dy, torch.bfloat16).data_ptr(), g.data_ptr(), FK, 4.0, B, H, W, C, _lib.stream_ptr()), "mgf_fir4_pad")
+    dyq = _nhwc(dy, torch.bfloat16)
+    _lib.check(L.mgf_fir4_pad(dyq.data_ptr(), g.data_ptr(), FK, 4.0, B, H, W, C, _lib.stream_ptr()), "mgf_fir4_pad")
     got = _nchw(g)
     assert (got[:, :, H + 1] == 0).all() and (got[:, :, :, W + 1] == 0).all()
     assert ((got[:, :, :H + 1, :W + 1] - ref).abs() <= 2.0 ** -7 * ref.abs() + 1e-5).all()
@@ -87,17 +88,19 @@ def test_upfir2_add_and_its_adjoint(fwd, shape):
     up = O.upfirdn2d(v, O.setup_filter([1, 3, 3, 1]), up=2, padding=[2, 1, 2, 1], gain=4) * gain
     ref = up + add
     out = torch.full((B, 2 * h, 2 * w, C), float("nan"), dtype=dt, device="cuda")
-    _lib.check(L.mgf_upfir2_add(_nhwc(v.detach(), dt).data_ptr(), _nhwc(add, dt).data_ptr(), out.data_ptr(), FK, 4.0 * gain, B, h, w, C,
+    vq, addq = _nhwc(v.detach(), dt), _nhwc(add, dt)          # keep the device tensors alive across the launches
+    _lib.check(L.mgf_upfir2_add(vq.data_ptr(), addq.data_ptr(), out.data_ptr(), FK, 4.0 * gain, B, h, w, C,
                                 _lib.stream_ptr()), "mgf_upfir2_add")
     got = _nchw(out)
     assert ((got - ref.detach()).abs() <= ulp * ref.detach().abs() + 1e-5).all(), (got - ref.detach()).abs().max()
     out2 = torch.full_like(out, float("nan"))
-    _lib.check(L.mgf_upfir2_add(_nhwc(v.detach(), dt).data_ptr(), None, out2.data_ptr(), FK, 4.0 * gain, B, h, w, C, _lib.stream_ptr()), "mgf_upfir2_add")
+    _lib.check(L.mgf_upfir2_add(vq.data_ptr(), None, out2.data_ptr(), FK, 4.0 * gain, B, h, w, C, _lib.stream_ptr()), "mgf_upfir2_add")
     assert ((_nchw(out2) - up.detach()).abs() <= ulp * up.detach().abs() + 1e-5).all()
     dout = util.case_tensor((B, C, 2 * h, 2 * w), 7).to(torch.bfloat16).float()
     gref, = torch.autograd.grad(up, [v], dout)
     dv = torch.full((B, h, w, C), float("nan"), dtype=torch.bfloat16, device="cuda")
-    _lib.check(L.mgf_upfir2_bwd(_nhwc(dout, torch.bfloat16).data_ptr(), dv.data_ptr(), FK, 4.0 * gain, B, h, w, C, _lib.stream_ptr()), "mgf_upfir2_bwd")
+    doutq = _nhwc(dout, torch.bfloat16)
+    _lib.check(L.mgf_upfir2_bwd(doutq.data_ptr(), dv.data_ptr(), FK, 4.0 * gain, B, h, w, C, _lib.stream_ptr()), "mgf_upfir2_bwd")
     assert ((_nchw(dv) - gref).abs() <= 2.0 ** -7 * gref.abs() + 1e-5).all()
 
 
@@ -116,7 +119,8 @@ def test_transposed_conv_as_four_parity_gemms(fwd, cfg):
             + [(0, 0, -b, 3 + 2 * b) for b in (0, 1)] + [(0, 0, 0, 4)])
     wk = W.reshape(Oc, I, 9).permute(2, 0, 1).reshape(1, 9, Oc, I).to(dt).contiguous().cuda()
     ct = torch.full((B, 2 * h + 2, 2 * w + 2, Oc), float("nan"), dtype=dt, device="cuda")
-    tc.conv_tc([_nhwc(x, dt)], wk, taps, (B, h + 1, w + 1), 4, Oc, ct, osy=2, osx=2, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1), phase_ntaps=(4, 2, 2, 1))
+    xq = _nhwc(x, dt)
+    tc.conv_tc([xq], wk, taps, (B, h + 1, w + 1), 4, Oc, ct, osy=2, osx=2, ofy=(0, 0, 1, 1), ofx=(0, 1, 0, 1), phase_ntaps=(4, 2, 2, 1))
     got = _nchw(ct)
     assert (got[:, :, 2 * h + 1] == 0).all() and (got[:, :, :, 2 * w + 1] == 0).all()
     got = got[:, :, :2 * h + 1, :2 * w + 1]
