@@ -32,10 +32,12 @@ LRELU_ALPHA = 0.2
 TWO_STAGE_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_MAX_RES", "65536"))   # A/B switch: up-conv dgrad as FIR + 9-tap strided conv up to this output size
 # A/B switches: up-conv forward as transposed conv (9 taps over four parity GEMMs) + FIR pass for output sizes in [MIN, MAX]; above MAX the
 # FIR-folded four-phase form runs in ONE tile per pixel block (BN = 4 * Cout columns, activation tiles fetched once for the four phases)
-# with the layer tail fused -- measured: the folded form costs 4x the tensor work, which only matters while the layer is compute-bound
-# (<= 128^2 outputs, C >= 256); at 256^2 .. 1024^2 the extra HBM round trip + FIR pass of the two-stage form costs more than it saves
+# with the layer tail fused.  Measured: the folded form costs 4x the tensor work, which only matters while the layer is compute-bound
+# (<= 128^2 outputs, C >= 256: two-stage saves ~0.1 ms on each of the 64^2 / 128^2 layers); at 256^2 .. 1024^2 the extra HBM round trip +
+# FIR pass of the two-stage form costs more than it saves.  DEFAULT OFF (MAX = 0): the 16-bit (2h+1)^2 intermediate is one more rounding
+# per up-convolution -- image error 8.4e-3 -> 1.2e-2 at 64^2 -- and the 1e-2 image tolerance has no room for it.
 TWO_STAGE_FWD_MIN_RES = int(_os.environ.get("MGF_TWO_STAGE_FWD_MIN_RES", "8"))
-TWO_STAGE_FWD_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_FWD_MAX_RES", "128"))
+TWO_STAGE_FWD_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_FWD_MAX_RES", "0"))
 FIR4_TAPS = (ctypes.c_float * 4)(0.125, 0.375, 0.375, 0.125)      # [1,3,3,1] / 8 (symmetric: flipping is a no-op); gain 4 = up^2 passed separately
 
 
