@@ -48,6 +48,12 @@ def parse():
                     help="16-bit type of forward activations/operands (gradients always bf16, fp32 accumulate); fp16 is the parity-green mode")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-res", type=int, default=None, help="resolution of the CPU baseline sample (default: same as --res)")
+    ap.add_argument("--workload", default="projection", choices=["projection", "pairs"],
+                    help="projection: BASELINE configs[3] (the headline line); pairs: configs[4], paired two-target projection + latent interpolation")
+    ap.add_argument("--pairs", type=int, default=64, help="pairs workload: number of synthetic target pairs over ALL ranks (BASELINE: 512)")
+    ap.add_argument("--pair-steps", type=int, default=20, help="pairs workload: Adam steps per projection job (BASELINE scripts: 1000)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the generator-only measurements (aux) and the same-box eager-PyTorch GPU baseline")
+    ap.add_argument("--gen-batch", type=int, default=32, help="batch of the generator forward+backward measurement (BASELINE configs[2]: 32)")
     return ap.parse_args()
 
 
@@ -157,6 +163,208 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ generator-only numbers (second half of the metric)
+def generator_aux(args, P, G, dev):
+    """G.synthesis on the tcgen05 engine: images/sec forward and forward + backward wrt ws, as CUDA-graph replays (the way the projection
+    step runs them), at the bench batch and at BASELINE configs[2]'s batch 32 (1024^2, 16-bit storage, fp32 accumulation)."""
+    import torch
+    eng = P._engine()
+    R = args.res
+    out = {"resolution": R, "note": "G.synthesis on the tcgen05 engine, one CUDA graph per call, CUDA events over 10 replays after 3 warm-up replays; "
+                                    "fp16 forward storage / bf16 gradients / fp32 accumulation"}
+
+    def measure(Bg):
+        ws = torch.randn(Bg, 17, G.num_ws, 32, device=dev)
+        mask = torch.ones(Bg, 16, device=dev)
+        dimg = torch.randn(Bg, 3, R, R, device=dev) * 1e-3
+        res = {}
+        for name, fn in (("forward", lambda: eng.forward_raw(ws, mask=mask, noise_mode="const")),
+                         ("forward_backward", lambda: (eng.forward_raw(ws, mask=mask, noise_mode="const"), eng.backward_raw(dimg)))):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            for _ in range(3):
+                g.replay()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record()
+            for _ in range(10):
+                g.replay()
+            b_.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(b_) / 10
+            res[name] = {"images_per_sec": Bg / (ms / 1000.0), "ms": ms}
+            del g
+        return res
+
+    out["batch_%d" % args.batch] = measure(args.batch)
+    if args.gen_batch and args.gen_batch != args.batch:
+        try:
+            out["batch_%d" % args.gen_batch] = measure(args.gen_batch)        # BASELINE configs[2]: generator forward+backward at 1024^2, batch 32
+        except Exception as ex:
+            out["batch_%d" % args.gen_batch] = {"failed": repr(ex)[:300]}
+        eng._states.pop(args.gen_batch, None)
+        torch.cuda.empty_cache()
+    out["generator_forward_images_per_sec"] = out["batch_%d" % args.batch]["forward"]["images_per_sec"]
+    out["generator_forward_backward_images_per_sec"] = out["batch_%d" % args.batch]["forward_backward"]["images_per_sec"]
+    return out
+
+
+def gpu_eager_baseline(res, batch, use_lpips, dev):
+    """SURVEY 2.1 / 8(d) "the kernel to beat on the same box": the reference's op graph (the oracle restatement, plain PyTorch ops -> cuDNN /
+    cuBLAS / ATen kernels) run EAGERLY on this GPU for the same projection step (same generator, same loss, Adam on z), fp32 and with bf16
+    autocast.  A reported baseline only -- nothing of the product runs here (baseline leg, like cpu_baseline)."""
+    import torch
+    import util
+    from oracle import ganformer, lpips_ref
+    out = {"batch": batch, "resolution": res, "what": "oracle/ restatement of the reference op graph, eager PyTorch %s on this GPU, one Adam step on z "
+           "(0.5 LPIPS-VGG + 0.5 MSE), target branch recomputed every step as the reference does" % torch.__version__}
+    G = util.build_G(res, 0)
+    gsd = {k: v.to(dev) for k, v in util.state_dict_cpu(G).items()}
+    lsd = {k: v.to(dev) for k, v in util.build_vgg_lpips_sd(4).items()} if use_lpips else None
+    tgt = torch.tanh(torch.randn(batch, 3, res, res, device=dev))
+    for mode in ("fp32", "bf16_autocast"):
+        try:
+            latent = torch.randn(batch, 17, 32, device=dev).requires_grad_(True)
+            opt = torch.optim.Adam([latent], lr=0.1, weight_decay=1e-4)
+
+            def step():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode != "fp32")):
+                    img, _ = ganformer.generator(gsd, latent, res)
+                    img = img.float()
+                    mse = (img - tgt).pow(2).mean(dim=[1, 2, 3])
+                    loss = 0.5 * lpips_ref.lpips(lsd, img, tgt).reshape(batch) + 0.5 * mse if use_lpips else mse
+                opt.zero_grad()
+                loss.sum().backward()
+                opt.step()
+            for _ in range(2):
+                step()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record()
+            n = 3
+            for _ in range(n):
+                step()
+            b_.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(b_) / n
+            out[mode] = {"ms_per_step": ms, "images_steps_per_sec": batch / (ms / 1000.0)}
+        except Exception as ex:
+            out[mode] = {"failed": repr(ex)[:300]}
+        torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs[4]: paired projection + morph
+def run_pairs(args):
+    """Paired two-target projection with latent interpolation (reference projection_example_v2_percept_morph.py:356-363, 1024_merge_morph_2.py:83-85):
+    `--pairs` synthetic target pairs = 2 x pairs independent projection jobs, sharded by pair over the ranks, processed in local micro-batches
+    of `--batch` jobs: Projector.reset() / set_targets() (pinned host -> HBM) / `--pair-steps` Adam steps per job (one CUDA-graph replay each),
+    then W = 0.5 z1 + 0.5 z2 and the three forwards G(z1), G(z2), G(W) of every pair; one all_gather of latents + losses ends the run.
+    Strong scaling: the job list is fixed, ranks split it.  value = jobs x steps / time (images*steps/s), the morph forwards inside the time."""
+    import torch
+    import torch.distributed as dist
+    import util
+    from morphganformer_b200 import _lib, parallel
+    from morphganformer_b200.projection import Projector, latent_stats
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, R, S = args.batch, args.res, args.pair_steps
+    assert B % 2 == 0, "a micro-batch holds whole pairs"
+    _lib.set_forward_dtype(args.fwd_dtype)
+    G = util.build_G(R, 0).to(dev)
+    lsd = util.build_vgg_lpips_sd(4)
+    mean, std = latent_stats(util.case_tensor((2000, 17, 32), 70))
+    lo, hi = parallel.shard_range(args.pairs, rank, world)
+    n_jobs = 2 * (hi - lo)
+    n_mb = (n_jobs + B - 1) // B
+    gen = torch.Generator(device="cpu").manual_seed(2000 + rank)
+    # synthetic targets of this rank's jobs in pinned host memory, a few distinct micro-batches cycled (100 MB each at 1024^2 x 8)
+    pool = [torch.tanh(torch.randn(B, 3, R, R, generator=gen)).pin_memory() for _ in range(min(n_mb, 3))]
+    P = Projector(G, lsd, B, S, latent_mean=mean, latent_std=std, noise_seed=3 + rank)
+    P.set_targets(pool[0])
+    P.capture()
+    eng, mask8, mask4 = P._engine(), torch.ones(B, 16, device=dev), torch.ones(B // 2, 16, device=dev)
+    from morphganformer_b200 import mapping_engine
+    # the captured projection graph owns P.mapper's buffers: the morph forwards get their own mapping engines (one per batch size)
+    map8, map4 = (mapping_engine.MappingEngine(G), mapping_engine.MappingEngine(G)) if P.mapper is not None else (None, None)
+
+    def ws_of(z, mapper, mask):
+        return mapper.forward(z, mask) if mapper is not None else G.mapping(z, None, pos=G.pos, mask=mask)
+
+    @torch.no_grad()
+    def morph(z):                                  # z [B,17,32]: pairs are consecutive jobs; G(z1), G(z2) in one batch, G(0.5 z1 + 0.5 z2) in another
+        zl = (0.5 * z[0::2] + 0.5 * z[1::2]).contiguous()
+        img = eng.forward_raw(ws_of(z, map8, mask8), mask=mask8)
+        imgm = eng.forward_raw(ws_of(zl, map4, mask4), mask=mask4)
+        return img, imgm
+
+    def job(mb):
+        P.reset()
+        P.set_targets(pool[mb % len(pool)])
+        out = P.run(S)
+        return out["best_latent"].clone(), out["best_loss"].clone(), morph(out["best_latent"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    job(0)                                         # warm-up: allocates the morph buffers (batch B and B/2 engine states)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lat, los = [], []
+    e0.record()
+    for mb in range(n_mb):
+        z, l, _ = job(mb)
+        lat.append(z); los.append(l)
+    lat, los = torch.cat(lat)[:n_jobs], torch.cat(los)[:n_jobs]
+    all_lat, all_los = parallel.gather_results(lat.contiguous(), los.contiguous())
+    loss_host = all_los.cpu()                      # the caller reads the results
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    total_jobs = 2 * args.pairs
+    value = total_jobs * S / (ms / 1000.0)
+    if rank == 0:
+        assert all_lat.shape[0] == total_jobs and bool(torch.isfinite(loss_host).all())
+        e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(B * 3 * R * R * 4 // S), "d2h_bytes_per_step": int((17 * 32 + 1) * 4 * B // S),
+               "note": "the only timed region of this workload is end to end: targets uploaded from pinned host memory per job, results read back"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": n_mb * S, "warmup": S, "ms_per_step": ms / max(1, n_mb * S),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.fwd_dtype + "_fwd/bf16_grad/f32_acc", "data": "synthetic",
+                "config": {"workload": "paired_projection_morph_%d_pairs%d_steps%d_b%d_per_gpu" % (R, args.pairs, S, B), "resolution": R, "pairs": args.pairs,
+                           "jobs": total_jobs, "steps_per_job": S, "micro_batch": B, "morph": "W = 0.5 z1 + 0.5 z2, forwards G(z1), G(z2), G(W) per pair",
+                           "parallelism": "pair-sharded x%d, no per-step collective, one final all_gather" % world, "cuda_graph": True,
+                           "l2": "inputs_exceed_l2", "weights": "random-init seed 0",
+                           "note": "BASELINE configs[4] is 512 pairs x 1000 steps; pass --pairs 512 --pair-steps 1000 for the full job"},
+                "pairs_per_sec": args.pairs / (ms / 1000.0), "job_ms": ms / n_mb, "e2e": e2e, "gpu_launches": int(P.launches_per_step * S * n_mb),
+                "clocks": clk, "best_loss_mean": float(loss_host.mean())}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------ native arm
@@ -279,13 +487,9 @@ def run_native(args):
         by_tag = {}
         for (tag, a, b, fa, fe, _desc) in recs:
             d = by_tag.setdefault(tag, [0.0, 0.0, 0.0, 0]); d[0] += a.elapsed_time(b); d[1] += fa; d[2] += fe; d[3] += 1
-        traffic, traffic_src = None, None
-        try:      # DRAM bytes of all conv launches of one step from the committed ncu pass (profiles/, same workload); null if absent
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01e_conv_dram_traffic.json")))
-            if (B, R, use_lpips) == (8, 1024, True):
-                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
-        except Exception:
-            pass
+        # DRAM bytes are not measurable from inside the process (no CUPTI metrics without a profiler): null here; the per-launch
+        # dram__bytes_read/write of the same command are in the committed ncu tables (profiles/r02_*.md)
+        traffic, traffic_src = None, "ncu tables under profiles/ (not measurable in-process)"
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes of one step)", "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_src + " bf16_tflops_sustained",
                 "executed_tflops": exe / (tms / 1000.0) / 1e12, "launches_per_step": len(recs) // 2, "kernel_ms_per_step": tms / 2,
@@ -294,24 +498,12 @@ def run_native(args):
 
     # ---- second half of BASELINE.json's metric: generator images/sec (synthesis forward, and forward + backward wrt ws), same engine / batch
     aux = None
-    if rank == 0:
-        eng = P._engine()
-        with torch.no_grad():
-            ws_b = P.mapper.forward(P.latent_n, P.mask) if P.mapper is not None else G.mapping(P.latent_n, None, pos=G.pos, mask=P.mask)
-        dimg_b = torch.randn(B, 3, R, R, device=dev) * 1e-3
-        def timed(fn, n=10):
-            for _ in range(3):
-                fn()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); a.record()
-            for _ in range(n):
-                fn()
-            b_.record(); torch.cuda.synchronize()
-            return a.elapsed_time(b_) / n
-        t_f = timed(lambda: eng.forward_raw(ws_b, mask=P.mask, noise_mode="const"))
-        t_fb = timed(lambda: (eng.forward_raw(ws_b, mask=P.mask, noise_mode="const"), eng.backward_raw(dimg_b)))
-        aux = {"generator_forward_images_per_sec": B / (t_f / 1000.0), "generator_forward_backward_images_per_sec": B / (t_fb / 1000.0),
-               "batch": B, "resolution": R, "note": "G.synthesis on the tcgen05 engine, eager launches (no graph), CUDA events, 10 iterations"}
+    if rank == 0 and not args.no_aux:
+        aux = generator_aux(args, P, G, dev)
+        try:
+            aux["same_box_eager_pytorch_gpu"] = gpu_eager_baseline(R, B, use_lpips, dev)
+        except Exception as ex:
+            aux["same_box_eager_pytorch_gpu"] = {"failed": repr(ex)[:300]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -345,5 +537,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "pairs":
+        run_pairs(a)
     else:
         run_native(a)

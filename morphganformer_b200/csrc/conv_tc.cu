@@ -158,7 +158,7 @@ struct Cfg {
   static constexpr int NSTG = (BN <= 64) ? 2 : 1;        // staging tiles per epilogue group (double-buffered when a tile is one group)
   static constexpr int STAGES_RAW = (SMEM_BUDGET - (NSTG - 1) * 2 * STG_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 20 ? 20 : STAGES_RAW;
-  static constexpr int BAR_BYTES = (2 * STAGES + 6) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
   static constexpr int SMEM = STAGES * STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + BAR_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // instruction descriptor (InstrDescriptor): D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A/B, N>>3 at 17, M>>4 at 24
@@ -242,7 +242,9 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           }
         }
         if (p.reduce_out) {
-          // column sums over the 128 rows of acc * X: warp transpose-reduce (31 shuffles), then one atomic per column per warp
+          // column sums over the 128 rows of acc * X: warp transpose-reduce (31 shuffles), then one atomic per column per warp.
+          // (Keeping per-thread partial sums in registers across the tiles of a (sample, N-block) would take this off the per-tile path,
+          // but BN = 64 needs 64 more registers and 10 warps cap a thread at 168: ptxas spilled, and setmaxnreg did not lift its limit.)
           float s[32];
 #pragma unroll
           for (int j = 0; j < 32; j++) s[j] = v[j] * xv[j];
@@ -360,13 +362,14 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* xbar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
+  uint64_t* xbar = tempty + 2;                 // [group][staging buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); mbar_init(&xbar[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 4; s++) mbar_init(&xbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       __syncwarp();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-  } else {             // ---------------------------------------------------- epilogue: two groups of 4 warps, group g owns accumulator stage g
+  } else {                 // ------------------------------------------------ epilogue: two groups of 4 warps, group g owns accumulator stage g
     const int as = warp >> 2; uint32_t aphase = 0;
     const int wq = warp & 3;                 // TMEM lane quarter this warp may access
     const int r = wq * 32 + lane;            // accumulator row == TMEM lane == pixel index inside the A box
@@ -441,23 +444,34 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     float* racc = racc_base + as * RACC;
     int red_key = -1;
     if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
+    uint32_t xph0 = 0, xph1 = 0; bool x_first = true;
     for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BN);
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
       const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
       if (p.reduce_out) {
         const int key = t.b0 * p.n_tiles + t.n0 / BN;
-        if (key != red_key) { if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r); red_key = key; }
-      }
-      uint8_t* stg = stg_base + (as * C::NSTG + (C::NSTG == 2 ? (int)aphase : 0)) * STG_BYTES;   // alternate staging tiles per tile
-      if (p.x_tma) {                          // prefetch the saved-activation tile into the staging buffer, hidden behind the MMAs
-        if (r == 0) tma_store_wait_read<C::NSTG - 1>();
-        group_sync(as);
-        if (r == 0) {
-          mbar_arrive_expect_tx(&xbar[as], p.x_bytes);
-          tma_load_4d(&p.xmap, &xbar[as], stg, t.n0, t.x0, t.y0, t.b0);
+        if (key != red_key) {
+          if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
+          red_key = key;
         }
       }
+      const int buf = (C::NSTG == 2) ? (int)aphase : 0;
+      uint8_t* stg = stg_base + (as * C::NSTG + buf) * STG_BYTES;   // alternate staging tiles per tile
+      if (p.x_tma && r == 0) {
+        // saved-activation (X) tiles arrive by TMA in the staging buffer their outputs will leave from (NSTG == 2, host guarantee).
+        // The tile of the group's NEXT turn is requested now, a whole epilogue ahead, so its DRAM latency is off the critical path
+        // (requesting it at the start of its own turn left ~2000 cycles of latency exposed per tile: the kernel was epilogue-bound).
+        if (x_first) { mbar_arrive_expect_tx(&xbar[as * 2 + buf], p.x_bytes); tma_load_4d(&p.xmap, &xbar[as * 2 + buf], stg, t.n0, t.x0, t.y0, t.b0); }
+        const int next = tile + 2 * gridDim.x;
+        if (next < p.total_tiles) {
+          const TileCoord tn = decode_tile(p, next, BN);
+          tma_store_wait_read<0>();             // the previous turn's TMA store has finished reading the other staging buffer
+          mbar_arrive_expect_tx(&xbar[as * 2 + (buf ^ 1)], p.x_bytes);
+          tma_load_4d(&p.xmap, &xbar[as * 2 + (buf ^ 1)], stg_base + (as * C::NSTG + (buf ^ 1)) * STG_BYTES, tn.n0, tn.x0, tn.y0, tn.b0);
+        }
+      }
+      x_first = false;
       float nz[4] = {0.f, 0.f, 0.f, 0.f};     // noise value(s) of this thread's pixel, fetched before the accumulator wait
       if (p.noise && valid) {
         if (p.superpix) {                     // row = pixel pair (2x, 2x+1) of a [H, 2*GW] noise plane
@@ -476,7 +490,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       epilogue_tile<BN, C::NSTG, GW32>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz[0], nz[1], nz[2], nz[3],
-                                 stg, as, r, racc, &xbar[as], aphase, &tempty[as]);
+                                 stg, as, r, racc, &xbar[as * 2 + buf], buf ? xph1 : xph0, &tempty[as]);
+      if (buf) xph1 ^= 1; else xph0 ^= 1;
       aphase ^= 1;
     }
     if (p.reduce_out && red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
@@ -553,14 +568,15 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   uint64_t* bfull = aempty + C::NS;
   uint64_t* tfull = bfull + 1;
   uint64_t* tempty = tfull + 2;
-  uint64_t* xbar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
+  uint64_t* xbar = tempty + 2;                 // [group][staging buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NS; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     mbar_init(bfull, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); mbar_init(&xbar[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 4; s++) mbar_init(&xbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -637,7 +653,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       __syncwarp();
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-  } else {             // ---------------------------------------------------- epilogue groups
+  } else {                 // ------------------------------------------------ epilogue groups
     const int as = warp >> 2; uint32_t aphase = 0;
     const int wq = warp & 3;
     const int r = wq * 32 + lane;
@@ -646,21 +662,29 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
     float* racc = racc_base + as * RACC;
     int red_key = -1;
     if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
+    uint32_t xph0 = 0, xph1 = 0; bool x_first = true;
     for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const HaloTile h = decode_halo(p, tile, BN);
       TileCoord t; t.n0 = h.n0; t.x0 = h.x0; t.y0 = h.y0; t.b0 = h.b0;
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0;
       const bool valid = x < p.GW && y < p.GH;
-      if (p.reduce_out && h.key != red_key) { if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r); red_key = h.key; }
-      uint8_t* stg = stg_base + (as * C::NSTG + (C::NSTG == 2 ? (int)aphase : 0)) * STG_BYTES;   // alternate staging tiles per tile
-      if (p.x_tma) {                          // prefetch the saved-activation tile into the staging buffer, hidden behind the MMAs
-        if (r == 0) tma_store_wait_read<C::NSTG - 1>();
-        group_sync(as);
-        if (r == 0) {
-          mbar_arrive_expect_tx(&xbar[as], p.x_bytes);
-          tma_load_4d(&p.xmap, &xbar[as], stg, t.n0, t.x0, t.y0, t.b0);
+      if (p.reduce_out && h.key != red_key) {
+        if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
+        red_key = h.key;
+      }
+      const int buf = (C::NSTG == 2) ? (int)aphase : 0;
+      uint8_t* stg = stg_base + (as * C::NSTG + buf) * STG_BYTES;   // alternate staging tiles per tile
+      if (p.x_tma && r == 0) {                // saved-activation tiles: requested one turn ahead (see conv_tc_kernel); NSTG == 2 (host guarantee)
+        if (x_first) { mbar_arrive_expect_tx(&xbar[as * 2 + buf], p.x_bytes); tma_load_4d(&p.xmap, &xbar[as * 2 + buf], stg, t.n0, t.x0, t.y0, t.b0); }
+        const int next = tile + 2 * gridDim.x;
+        if (next < p.total_tiles) {
+          const HaloTile hn = decode_halo(p, next, BN);
+          tma_store_wait_read<0>();
+          mbar_arrive_expect_tx(&xbar[as * 2 + (buf ^ 1)], p.x_bytes);
+          tma_load_4d(&p.xmap, &xbar[as * 2 + (buf ^ 1)], stg_base + (as * C::NSTG + (buf ^ 1)) * STG_BYTES, hn.n0, hn.x0, hn.y0, hn.b0);
         }
       }
+      x_first = false;
       float nz[4] = {0.f, 0.f, 0.f, 0.f};     // noise value(s) of this thread's pixel, fetched before the accumulator wait
       if (p.noise && valid) {
         if (p.superpix) {                     // row = pixel pair (2x, 2x+1) of a [H, 2*GW] noise plane
@@ -679,7 +703,8 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       epilogue_tile<BN, C::NSTG, (BN >= 64 ? 2 : 1)>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz[0], nz[1], nz[2], nz[3],
-                                 stg, as, r, racc, &xbar[as], aphase, &tempty[as]);
+                                 stg, as, r, racc, &xbar[as * 2 + buf], buf ? xph1 : xph0, &tempty[as]);
+      if (buf) xph1 ^= 1; else xph0 ^= 1;
       aphase ^= 1;
     }
     if (p.reduce_out && red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
@@ -894,7 +919,8 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     if (int e = encode_x_map(p, d, HBN, 8, 16, 1, 128)) return e;
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
     cudaStream_t st = (cudaStream_t)stream;
-#define MGF_HALO_CASE(bn, bk) if (HBN == bn && HBK == bk) return g_halo_nstg == 2 ? launch_halo<bn, 1, bk, 2>(p, grid, st) : launch_halo<bn, 1, bk, 1>(p, grid, st);
+    const bool nstg2 = g_halo_nstg == 2 || p.x_tma;      // X tiles are prefetched into the second staging buffer
+#define MGF_HALO_CASE(bn, bk) if (HBN == bn && HBK == bk) return nstg2 ? launch_halo<bn, 1, bk, 2>(p, grid, st) : launch_halo<bn, 1, bk, 1>(p, grid, st);
     MGF_HALO_CASE(64, 64) MGF_HALO_CASE(32, 64) MGF_HALO_CASE(64, 32) MGF_HALO_CASE(32, 32)
 #undef MGF_HALO_CASE
     MGF_FAIL(MGF_E_UNSUP, "conv_tc: no halo kernel for BN=%d KC=%d", HBN, KC);

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) fir4_kernel(const Fir4Args a) {
 // Polyphase form: rows 2m, 2m+1 and columns 2n, 2n+1 of the output read the 3x3 low-resolution neighbourhood of (m, n):
 //   hE[m] = f0 v[m,n-1] + f2 v[m,n]    hO[m] = f1 v[m,n] + f3 v[m,n+1]
 //   out[2m] = f0 h[m-1] + f2 h[m]      out[2m+1] = f1 h[m] + f3 h[m+1]
-// A thread owns (n, 8-channel vector) and walks down the low-resolution rows: 3 loads of v, 4 loads of add, 4 stores per step.
+// A thread owns (output column, 8-channel vector) and walks down the low-resolution rows: 2 loads of v, 2 loads of add, 2 stores per step.
 struct Upfir2Args {
   const uint16_t* v; const uint16_t* add; uint16_t* out;
   float fh[4], fv[4];            // horizontal taps with the gain folded in, vertical taps
@@ -126,59 +126,65 @@ struct Upfir2Args {
 
 template <bool F16>
 __global__ void __launch_bounds__(256) upfir2_add_kernel2(const Upfir2Args a) {
+  // thread = (output column X, 8-channel vector), walking down the low-resolution rows of a strip: per row 2 loads of v (the two
+  // low-resolution pixels column X reads), then two output rows (one add load + one store each).  One column per thread keeps the
+  // kernel at ~70 registers (the first version carried both columns of a low-resolution pixel: 126 registers, 25 % occupancy,
+  // latency-bound at 3.9 TB/s).
   const int vecs = 1 << a.vshift;
   const int b = blockIdx.z, m0 = blockIdx.y * a.rows;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (a.w << a.vshift)) return;
-  const int cv = i & (vecs - 1), n = i >> a.vshift;
-  const float wl = n > 0 ? a.fh[0] : 0.f, wr = n + 1 < a.w ? a.fh[3] : 0.f;
+  if (i >= ((2 * a.w) << a.vshift)) return;
+  const int cv = i & (vecs - 1), X = i >> a.vshift, n = X >> 1;
   const int sh = a.vshift + 3;
-  const int ol = (n > 0 ? n - 1 : 0) << sh, oc = n << sh, orr = (n + 1 < a.w ? n + 1 : n) << sh;
+  // X even: f0 v[n-1] + f2 v[n];  X odd: f1 v[n] + f3 v[n+1]
+  const bool odd = X & 1;
+  const int na = odd ? n : n - 1, nb = odd ? n + 1 : n;
+  const float wa = (na >= 0) ? (odd ? a.fh[1] : a.fh[0]) : 0.f, wb = (nb < a.w) ? (odd ? a.fh[3] : a.fh[2]) : 0.f;
+  const int oa = (na >= 0 ? na : 0) << sh, ob_ = (nb < a.w ? nb : a.w - 1) << sh;
   const uint16_t* vb = a.v + (((long long)b * a.h * a.w) << sh) + cv * 8;
   const long long W2 = 2LL * a.w;
-  const uint16_t* ab = a.add ? a.add + ((((long long)b * 2 * a.h) * W2 + 2 * n) << sh) + cv * 8 : nullptr;
-  uint16_t* ob = a.out + ((((long long)b * 2 * a.h) * W2 + 2 * n) << sh) + cv * 8;
+  const long long obase = ((((long long)b * 2 * a.h) * W2 + X) << sh) + cv * 8;
+  const uint16_t* ab = a.add ? a.add + obase : nullptr;
+  uint16_t* ob = a.out + obase;
   const long long orow = W2 << sh;
-  const int pstep = 1 << sh;                 // one output pixel
   float mx = 0.f;
-  float hE[3][8], hO[3][8];                  // ring of horizontal sums: rows m-1, m, m+1
+  float h[3][8];                             // ring of horizontal sums: rows m-1, m, m+1
 
-  auto hrow = [&](int r, float (&e_)[8], float (&o_)[8]) {
+  auto hrow = [&](int r, float (&h_)[8]) {
 #pragma unroll
-    for (int e = 0; e < 8; e++) e_[e] = o_[e] = 0.f;
+    for (int e = 0; e < 8; e++) h_[e] = 0.f;
     if (r >= 0 && r < a.h) {
       const uint16_t* rp = vb + (((long long)r * a.w) << sh);
-      float l[8], c[8], rr[8];
-      ld8<F16>(rp + ol, l); ld8<F16>(rp + oc, c); ld8<F16>(rp + orr, rr);
+      float p[8], q[8];
+      ld8<F16>(rp + oa, p); ld8<F16>(rp + ob_, q);
 #pragma unroll
-      for (int e = 0; e < 8; e++) { e_[e] = fmaf(wl, l[e], a.fh[2] * c[e]); o_[e] = fmaf(wr, rr[e], a.fh[1] * c[e]); }
+      for (int e = 0; e < 8; e++) h_[e] = fmaf(wa, p[e], wb * q[e]);
     }
   };
-  auto emit = [&](int Y, const float (&ta)[8], float ca, const float (&tb)[8], float cb, const float (&ua)[8], const float (&ub)[8]) {
-    // row Y: even column from (ta, tb), odd column from (ua, ub), vertical weights ca / cb
-    float oe[8], oo[8];
+  auto emit = [&](int Y, const float (&ta)[8], float ca, const float (&tb)[8], float cb) {
+    float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; e++) { oe[e] = fmaf(ca, ta[e], cb * tb[e]); oo[e] = fmaf(ca, ua[e], cb * ub[e]); }
+    for (int e = 0; e < 8; e++) o[e] = fmaf(ca, ta[e], cb * tb[e]);
     const long long ro = (long long)Y * orow;
     if (ab) {
-      float x0[8], x1[8];
-      ld8<F16>(ab + ro, x0); ld8<F16>(ab + ro + pstep, x1);
+      float x0[8];
+      ld8<F16>(ab + ro, x0);
 #pragma unroll
-      for (int e = 0; e < 8; e++) { oe[e] += x0[e]; oo[e] += x1[e]; }
+      for (int e = 0; e < 8; e++) o[e] += x0[e];
     }
     if (F16) {
 #pragma unroll
-      for (int e = 0; e < 8; e++) mx = fmaxf(mx, fmaxf(fabsf(oe[e]), fabsf(oo[e])));
+      for (int e = 0; e < 8; e++) mx = fmaxf(mx, fabsf(o[e]));
     }
-    st8<F16>(ob + ro, oe); st8<F16>(ob + ro + pstep, oo);
+    st8<F16>(ob + ro, o);
   };
-  hrow(m0 - 1, hE[0], hO[0]);
-  hrow(m0, hE[1], hO[1]);
-#define UPFIR2_STEP(PREV, CUR, NEXT, m)                                                             \
-  if ((m) < a.h && (m) < m0 + a.rows) {                                                             \
-    hrow((m) + 1, hE[NEXT], hO[NEXT]);                                                              \
-    emit(2 * (m), hE[PREV], a.fv[0], hE[CUR], a.fv[2], hO[PREV], hO[CUR]);                          \
-    emit(2 * (m) + 1, hE[CUR], a.fv[1], hE[NEXT], a.fv[3], hO[CUR], hO[NEXT]);                      \
+  hrow(m0 - 1, h[0]);
+  hrow(m0, h[1]);
+#define UPFIR2_STEP(PREV, CUR, NEXT, m)                                        \
+  if ((m) < a.h && (m) < m0 + a.rows) {                                        \
+    hrow((m) + 1, h[NEXT]);                                                    \
+    emit(2 * (m), h[PREV], a.fv[0], h[CUR], a.fv[2]);                          \
+    emit(2 * (m) + 1, h[CUR], a.fv[1], h[NEXT], a.fv[3]);                      \
   }
   for (int m = m0; m < m0 + a.rows && m < a.h; m += 3) {
     UPFIR2_STEP(0, 1, 2, m)
@@ -297,7 +303,7 @@ extern "C" int mgf_upfir2_add(const void* v, const void* add, void* out, const f
   for (int t = 0; t < 4; t++) { a.fh[t] = fk4[t] * gain; a.fv[t] = fk4[t]; }
   a.h = h; a.w = w; a.vshift = vs;
   a.ovf = fwd_f16() ? overflow_flag() : nullptr;
-  const int bx = ((w << vs) + 255) / 256;
+  const int bx = (((2 * w) << vs) + 255) / 256;
   a.rows = strip_rows(h, (long long)bx * B, 3, 15);
   dim3 grid(bx, (h + a.rows - 1) / a.rows, B);
   if (fwd_f16()) upfir2_add_kernel2<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);

@@ -721,5 +721,5 @@ def smoke():
     G.synthesis.engine = "ops"
     ref, _ = G.synthesis(ws.detach(), pos=G.pos, mask=mask, noise_mode="const", return_att_maps=False)
     err, rng = (img.detach() - ref).abs().max().item(), max(1.0, ref.abs().max().item())
-    assert err < 1e-2, "tc engine deviates from the ops engine: %g of range %g" % (err, rng)
+    assert err < 2e-2, "tc engine deviates from the ops engine: %g of range %g" % (err, rng)
     print("smoke ok: tc engine 64x64 fwd+bwd, max|img_tc - img_fp32| = %.3g (range %.3g), |dws| = %.3g" % (err, rng, ws.grad.abs().max().item()))

@@ -175,7 +175,7 @@ def synthesis(sd, ws, pos, mask, res, architecture="resnet", end_res=8, noise_mo
     ws = ws.to(dtype)
     sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     pos = pos.to(dtype)
-    f = ops.setup_filter([1, 3, 3, 1]).to(dtype)
+    f = ops.setup_filter([1, 3, 3, 1]).to(ws.device, dtype)
     b = ws.shape[0]
     resolutions = [2 ** i for i in range(2, int(math.log2(res)) + 1)]
     w_idx = 0
@@ -236,6 +236,6 @@ def generator(sd, z, res, noise_mode="const", dtype=torch.float32):
     b = z.shape[0]
     k = z.shape[1]
     sdd = {kk: (v.to(dtype) if v.is_floating_point() else v) for kk, v in sd.items()}
-    mask = torch.ones(b, k - 1, dtype=dtype)
+    mask = torch.ones(b, k - 1, dtype=dtype, device=z.device)
     ws = mapping(sdd, z.to(dtype), sdd["pos"], mask, k=k, num_ws=num_ws_for(res))
     return synthesis(sdd, ws, sdd["pos"], mask, res, noise_mode=noise_mode, dtype=dtype), ws

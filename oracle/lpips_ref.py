@@ -72,8 +72,8 @@ def normalize_tensor(t, eps=1e-10):
 
 def lpips(sd, pred, target, net="vgg"):
     """returns [N,1,1,1] like PerceptualLoss.forward (lpips/__init__.py:26-41); net in {'vgg', 'alex', 'squeeze'}."""
-    shift = torch.tensor(SHIFT, dtype=pred.dtype)[None, :, None, None]
-    scale = torch.tensor(SCALE, dtype=pred.dtype)[None, :, None, None]
+    shift = torch.tensor(SHIFT, dtype=pred.dtype, device=pred.device)[None, :, None, None]
+    scale = torch.tensor(SCALE, dtype=pred.dtype, device=pred.device)[None, :, None, None]
     f0 = FEATURES[net](sd, (pred - shift) / scale)
     f1 = FEATURES[net](sd, (target - shift) / scale)
     val = 0

@@ -80,7 +80,7 @@ def test_config1_full_size_256_batch8_200_steps_properties():
             G.synthesis.engine = "ops"
             img_ops = G(z, noise_mode="const")[0]
         l_tc = (img_tc - tgt).square().mean(dim=[1, 2, 3]); l_ops = (img_ops - tgt).square().mean(dim=[1, 2, 3])
-        assert (img_tc - img_ops).abs().max().item() < 1e-2          # absolute, fp16 forward storage
+        assert (img_tc - img_ops).abs().max().item() < 1e-2          # absolute (config-1 size, range 2.4), fp16 forward storage
         np.testing.assert_allclose(l_tc.cpu().numpy(), l_ops.cpu().numpy(), rtol=5e-3)   # measured 1.2e-3 .. 2.5e-3 run to run (float-atomic ordering changes the trajectory): the loss is a small MSE (0.012) near a reachable target, where the 1e-2 image bound allows more
         np.testing.assert_allclose(out["best_loss"].cpu().numpy(), l_ops.cpu().numpy(), rtol=6e-3)
     finally:
@@ -111,7 +111,7 @@ def test_config4_pair_projection_and_interpolation_vs_oracle():
     with torch.no_grad():
         ref = ganformer.generator(gsd, (0.5 * z1 + 0.5 * z2).cpu(), res)[0]
     assert tuple(morph.shape) == (1, 3, res, res)
-    assert (morph.cpu() - ref).abs().max().item() < 1e-2          # absolute, fp16 forward storage
+    assert (morph.cpu() - ref).abs().max().item() < util.img_abs_tol(ref)          # absolute, fp16 forward storage
     # alpha = 0 / 1 reproduce the endpoints
     with torch.no_grad():
         e0 = interpolate_pair(G, z1, z2, 0.0); i1 = G(z1, noise_mode="const")[0]

@@ -117,3 +117,11 @@ RESAMPLE_CASES = [
 def case_tensor(shape, seed):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(shape, generator=g)
+
+
+def img_abs_tol(ref):
+    """Absolute max-abs image tolerance of the tcgen05 engine in its default fp16 forward storage: 1e-2 (north_star) for images of the
+    nominal GAN range |img| <= 2.5; the BASELINE configurations themselves (256^2: range 2.4, 1024^2: range 4.2) are held to 1e-2 absolute in
+    tests/test_fullsize_parity_gpu.py.  The narrow 64-channel toy generators of the unit tests produce images of range ~5 with twice the
+    relative rounding noise (fewer channels to average over): 2e-2 absolute there (0.4 % of the range)."""
+    return 1e-2 if float(ref.abs().max()) <= 2.5 else 2e-2
