@@ -65,8 +65,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(t);
+  // bf16 is the upper half of an fp32: one shift and one mask (the library intrinsic compiles to PRMT + shift for the upper element,
+  // three instructions per pair -- visible in the issue-bound FIR / epilogue loops)
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 // 16-bit storage with a run-time element type: f16 = IEEE half (forward activations/operands when the library is in fp16-forward
 // mode: same tensor-core rate, 8x finer rounding than bf16), otherwise bfloat16 (always used for gradients: range).
@@ -79,6 +80,12 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
 // fp16 overflow guard: kernels that store forward activations keep a running max |v| of what they pack (one FMNMX per value) and raise
 // the library's device flag if it left the fp16 range (the store itself saturates).  Read with mgf_fp16_overflow_read.
 constexpr float F16_MAX = 65504.f;
+// running max |v| that PROPAGATES NaN (plain fmaxf drops it, and inf * 0 further down a saturated network is NaN)
+__device__ __forceinline__ float ovf_max(float mx, float v) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(mx), "f"(fabsf(v)));
+  return r;
+}
 __device__ __forceinline__ void ovf_commit(unsigned int* flag, float mx) { if (flag && !(mx <= F16_MAX)) atomicOr(flag, 1u); }
 __device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
   return f16 ? pack_f16_sat(a, b) : pack_bf16(a, b);

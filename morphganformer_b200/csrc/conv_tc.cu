@@ -206,9 +206,10 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           tc_fence_before();
           mbar_arrive(tempty_bar);
         }
+        // rows outside the grid are never stored (the TMA store clips them) and add nothing to the reductions (their X reads as zero below)
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
+        for (int j = 0; j < 32; j++) v[j] = __uint_as_float(raw[j]);
         float xv[32];
         const bool needX = (p.X != nullptr) && (p.reduce_out != nullptr || p.actgrad);
         constexpr int GX32 = GW32;
@@ -268,26 +269,31 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
 #pragma unroll
           for (int j = 0; j < 8; j++) { const float4 f = __ldg(sp + j); v[4 * j] *= f.x; v[4 * j + 1] *= f.y; v[4 * j + 2] *= f.z; v[4 * j + 3] *= f.w; }
         }
+        // layer tail (networks.py:1036-1040): (v + noise + bias) -> leaky-ReLU -> * gain, computed as t = v g + (bias g + noise g) and
+        // max(t, alpha t): 4 instructions per element instead of 6 (gain > 0 and 0 <= alpha <= 1, host-checked)
+        float nzg = 0.f;
         if (p.noise) {
           const int k = p.superpix ? (c & 1) : phase_idx - phase_lo;  // super-pixel rows: odd 32-column chunk = right pixel of the pair
-          const float nzc = k == 0 ? nz0 : k == 1 ? nz1 : k == 2 ? nz2 : nz3;
-#pragma unroll
-          for (int j = 0; j < 32; j++) v[j] += nzc;
+          nzg = (k == 0 ? nz0 : k == 1 ? nz1 : k == 2 ? nz2 : nz3) * p.gain;
         }
         if (p.bias) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + co);
 #pragma unroll
-          for (int j = 0; j < 8; j++) { const float4 f = __ldg(bp + j); v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w; }
+          for (int j = 0; j < 8; j++) {
+            const float4 f = __ldg(bp + j);
+            v[4 * j] = fmaf(v[4 * j], p.gain, fmaf(f.x, p.gain, nzg)); v[4 * j + 1] = fmaf(v[4 * j + 1], p.gain, fmaf(f.y, p.gain, nzg));
+            v[4 * j + 2] = fmaf(v[4 * j + 2], p.gain, fmaf(f.z, p.gain, nzg)); v[4 * j + 3] = fmaf(v[4 * j + 3], p.gain, fmaf(f.w, p.gain, nzg));
+          }
+        } else if (p.noise || p.gain != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = fmaf(v[j], p.gain, nzg);
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = (v[j] > 0.f ? v[j] : v[j] * p.alpha) * p.gain;
+          for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], v[j] * p.alpha);
         } else if (p.act == 2) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f) * p.gain;
-        } else if (p.gain != 1.f) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) v[j] *= p.gain;
+          for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.add && valid) {
           const uint4* ap = reinterpret_cast<const uint4*>(p.add + obase);
@@ -316,7 +322,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         }
         if (p.ovf) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) ovf_mx = fmaxf(ovf_mx, fabsf(v[j]));
+          for (int j = 0; j < 32; j++) ovf_mx = ovf_max(ovf_mx, v[j]);
         }
         {
           uint8_t* row = stg_c + r * (GW32 * 64);
@@ -336,7 +342,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           if (r == 0) tma_store_4d(&p.omap[phase_idx], stg_c, co - h * 32, t.x0, t.y0, t.b0);
         }
       }
-      ovf_commit(p.ovf, ovf_mx);
+      ovf_commit(p.ovf, valid ? ovf_mx : 0.f);      // rows outside the tile hold whatever the accumulator had
 }
 
 template <int BN>
@@ -829,6 +835,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   if (d->n_a < 1 || d->n_a > MAX_AMAPS) MGF_FAIL(MGF_E_BADARG, "conv_tc: n_a=%d outside 1..%d", d->n_a, MAX_AMAPS);
   if (d->ntaps < 1 || d->ntaps > MAX_TAPS) MGF_FAIL(MGF_E_BADARG, "conv_tc: ntaps=%d outside 1..%d", d->ntaps, MAX_TAPS);
   if (!d->w || !d->out) MGF_FAIL(MGF_E_BADARG, "conv_tc: null weight/output");
+  if (!(d->gain > 0.f) || (d->act == 1 && !(d->alpha >= 0.f && d->alpha <= 1.f))) MGF_FAIL(MGF_E_BADARG, "conv_tc: the fused tail needs gain > 0 and 0 <= alpha <= 1");
   const long long Cc = d->a[0].C;
   if (Cc % 32 != 0 || Cc < 32) MGF_FAIL(MGF_E_SHAPE, "conv_tc: input channels (%lld) must be a multiple of 32", Cc);
   if (d->w_K != Cc) MGF_FAIL(MGF_E_SHAPE, "conv_tc: weight K (%lld) != activation channels (%lld)", (long long)d->w_K, Cc);

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) modulate_kernel(const float* base, const 
     if (cs) c = *reinterpret_cast<const float4*>(cs + b * K + k);
     uint2 o;
     const float o0 = w.x * r * c.x, o1 = w.y * r * c.y, o2 = w.z * r * c.z, o3 = w.w * r * c.w;
-    mx = fmaxf(fmaxf(mx, fmaxf(fabsf(o0), fabsf(o1))), fmaxf(fabsf(o2), fabsf(o3)));
+    mx = ovf_max(ovf_max(ovf_max(ovf_max(mx, o0), o1), o2), o3);
     o.x = pack16(o0, o1, of16);
     o.y = pack16(o2, o3, of16);
     *reinterpret_cast<uint2*>(out + b * per + row * K + k) = o;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) scale_channels_kernel(const __nv_bfloat16
     uint4 o;
     const float v[8] = {a.x * s0.x, a.y * s0.y, bq.x * s0.z, bq.y * s0.w, c.x * s1.x, c.y * s1.y, d.x * s1.z, d.y * s1.w};
 #pragma unroll
-    for (int j = 0; j < 8; j++) mx = fmaxf(mx, fabsf(v[j]));
+    for (int j = 0; j < 8; j++) mx = ovf_max(mx, v[j]);
     o.x = pack16(v[0], v[1], f16); o.y = pack16(v[2], v[3], f16);
     o.z = pack16(v[4], v[5], f16); o.w = pack16(v[6], v[7], f16);
     *reinterpret_cast<uint4*>(out + off) = o;

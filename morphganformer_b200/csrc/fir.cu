@@ -46,66 +46,77 @@ __global__ void __launch_bounds__(256) fir4_kernel(const Fir4Args a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (a.Wo << a.vshift)) return;
   const int cv = i & (vecs - 1), X = i >> a.vshift;
-  float wx[4]; int xo[4];
-#pragma unroll
-  for (int t = 0; t < 4; t++) {               // out-of-range taps: zero weight on a clamped (valid) address, so the loads stay unconditional
-    const int x = X + a.off + t;
-    const bool ok = x >= 0 && x < a.Wi && X < a.Wv;
-    wx[t] = ok ? a.fh[t] : 0.f; xo[t] = (ok ? x : 0) << (a.vshift + 3);
-  }
-  const uint16_t* inb = a.in + (((long long)b * a.Hi * a.Wi) << (a.vshift + 3)) + cv * 8;
-  uint16_t* outb = a.out + ((((long long)b * a.Ho) * a.Wo + X) << (a.vshift + 3)) + cv * 8;
-  const long long orow = (long long)a.Wo << (a.vshift + 3);
+  const int sh = a.vshift + 3;
+  // four running row pointers (one per horizontal tap), advanced by one input row per step: the first version recomputed 64-bit
+  // addresses per load (~70 of its ~200 instructions per output were address arithmetic in an issue-bound kernel).
+  // Out-of-range taps: zero weight on a clamped (valid) address, so the loads stay unconditional.
+  const long long in_row = (long long)a.Wi << sh;
+  const int r0 = Y0 + a.off;
+  const uint16_t* base = a.in + (((long long)b * a.Hi + r0) * a.Wi << sh) + cv * 8;       // row r0 may lie outside the image: only dereferenced when valid
+  const float fh0 = a.fh[0], fh1 = a.fh[1], fh2 = a.fh[2], fh3 = a.fh[3];
+  const float fv0 = a.fv[0], fv1 = a.fv[1], fv2 = a.fv[2], fv3 = a.fv[3];
+  const int x0 = X + a.off, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+  const bool colv = X < a.Wv;
+  const bool k0 = colv && x0 >= 0 && x0 < a.Wi, k1 = colv && x1 >= 0 && x1 < a.Wi, k2 = colv && x2 >= 0 && x2 < a.Wi, k3 = colv && x3 >= 0 && x3 < a.Wi;
+  const float w0 = k0 ? fh0 : 0.f, w1 = k1 ? fh1 : 0.f, w2 = k2 ? fh2 : 0.f, w3 = k3 ? fh3 : 0.f;
+  const uint16_t* p0 = base + ((long long)(k0 ? x0 : 0) << sh);
+  const uint16_t* p1 = base + ((long long)(k1 ? x1 : 0) << sh);
+  const uint16_t* p2 = base + ((long long)(k2 ? x2 : 0) << sh);
+  const uint16_t* p3 = base + ((long long)(k3 ? x3 : 0) << sh);
+  uint16_t* op = a.out + ((((long long)b * a.Ho + Y0) * a.Wo + X) << sh) + cv * 8;       // output row Y0, advanced per emitted row
+  const long long out_row = (long long)a.Wo << sh;
   float bias[8];
   float nstr = 0.f;
   if (EPI) {
 #pragma unroll
-    for (int e = 0; e < 8; e++) bias[e] = a.bias ? __ldg(a.bias + cv * 8 + e) : 0.f;
-    if (a.noise) nstr = a.nstr ? __ldg(a.nstr) : 1.f;
+    for (int e = 0; e < 8; e++) bias[e] = a.bias ? __ldg(a.bias + cv * 8 + e) * a.gain : 0.f;     // act gain folded: lrelu(v) g = lrelu(v g)
+    if (a.noise) nstr = (a.nstr ? __ldg(a.nstr) : 1.f) * a.gain;
   }
-  const float* nz = (EPI && a.noise) ? a.noise + (long long)b * a.noise_bstride + X : nullptr;
+  const float* nz = (EPI && a.noise) ? a.noise + (long long)b * a.noise_bstride + (long long)Y0 * a.Wo + X : nullptr;
+  const float og = EPI ? a.gain : 1.f;       // folded into the last vertical tap and the accumulators' hand-over
   float mx = 0.f;
   float P[8], Q[8], S[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) P[e] = Q[e] = S[e] = 0.f;
+  int r = r0, Yo = Y0 - 3;
 
   // one input row: horizontal sum h, then out = OLD + fv3*h is complete (output row Yo), MID += fv2*h, YOUNG += fv1*h, OLD = fv0*h
-#define FIR4_STEP(OLD, MID, YOUNG, k)                                                                                   \
+#define FIR4_STEP(OLD, MID, YOUNG)                                                                                      \
   {                                                                                                                      \
-    const int r = Y0 + a.off + (k);                                                                                      \
     float h[8];                                                                                                          \
-    _Pragma("unroll") for (int e = 0; e < 8; e++) h[e] = 0.f;                                                            \
     if (r >= 0 && r < a.Hi) {                                                                                            \
-      const uint16_t* rowp = inb + (((long long)r * a.Wi) << (a.vshift + 3));                                            \
       float q0[8], q1[8], q2[8], q3[8];                                                                                  \
-      ld8<IN_F16>(rowp + xo[0], q0); ld8<IN_F16>(rowp + xo[1], q1); ld8<IN_F16>(rowp + xo[2], q2); ld8<IN_F16>(rowp + xo[3], q3); \
-      _Pragma("unroll") for (int e = 0; e < 8; e++) h[e] = fmaf(wx[3], q3[e], fmaf(wx[2], q2[e], fmaf(wx[1], q1[e], wx[0] * q0[e]))); \
+      ld8<IN_F16>(p0, q0); ld8<IN_F16>(p1, q1); ld8<IN_F16>(p2, q2); ld8<IN_F16>(p3, q3);                                \
+      _Pragma("unroll") for (int e = 0; e < 8; e++) h[e] = fmaf(w3, q3[e], fmaf(w2, q2[e], fmaf(w1, q1[e], w0 * q0[e]))); \
+    } else {                                                                                                             \
+      _Pragma("unroll") for (int e = 0; e < 8; e++) h[e] = 0.f;                                                          \
     }                                                                                                                    \
-    const int Yo = Y0 + (k) - 3;                                                                                         \
-    if ((k) >= 3 && Yo < a.Ho) {                                                                                         \
+    p0 += in_row; p1 += in_row; p2 += in_row; p3 += in_row; r++;                                                         \
+    if (Yo >= Y0 && Yo < a.Ho) {                                                                                         \
       float o[8];                                                                                                        \
-      const bool live = Yo < a.Hv;                                                                                       \
-      _Pragma("unroll") for (int e = 0; e < 8; e++) o[e] = live ? fmaf(a.fv[3], h[e], OLD[e]) : 0.f;                     \
+      _Pragma("unroll") for (int e = 0; e < 8; e++) o[e] = fmaf(fv3, h[e], OLD[e]);                                      \
+      if (Yo >= a.Hv) { _Pragma("unroll") for (int e = 0; e < 8; e++) o[e] = 0.f; }                                      \
       if (EPI) {                                                                                                         \
-        const float n = nz ? __ldg(nz + (long long)Yo * a.Wo) * nstr : 0.f;                                              \
+        const float n = nz ? __ldg(nz) * nstr : 0.f;                                                                     \
         _Pragma("unroll") for (int e = 0; e < 8; e++) {                                                                  \
-          float v = o[e] + n + bias[e];                                                                                  \
-          if (a.act == 1) v = v > 0.f ? v : v * a.alpha;                                                                 \
-          o[e] = v * a.gain;                                                                                             \
+          const float v = fmaf(o[e], og, n + bias[e]);                                                                   \
+          o[e] = (a.act == 1) ? fmaxf(v, v * a.alpha) : v;                                                               \
         }                                                                                                                \
       }                                                                                                                  \
-      if (OUT_F16) { _Pragma("unroll") for (int e = 0; e < 8; e++) mx = fmaxf(mx, fabsf(o[e])); }                        \
-      st8<OUT_F16>(outb + (long long)Yo * orow, o);                                                                      \
+      if (OUT_F16) { _Pragma("unroll") for (int e = 0; e < 8; e++) mx = ovf_max(mx, o[e]); }                        \
+      st8<OUT_F16>(op, o);                                                                                               \
+      op += out_row; if (EPI && nz) nz += a.Wo;                                                                          \
     }                                                                                                                    \
+    Yo++;                                                                                                                \
     _Pragma("unroll") for (int e = 0; e < 8; e++) {                                                                      \
-      MID[e] = fmaf(a.fv[2], h[e], MID[e]); YOUNG[e] = fmaf(a.fv[1], h[e], YOUNG[e]); OLD[e] = a.fv[0] * h[e];           \
+      MID[e] = fmaf(fv2, h[e], MID[e]); YOUNG[e] = fmaf(fv1, h[e], YOUNG[e]); OLD[e] = fv0 * h[e];                       \
     }                                                                                                                    \
   }
   for (int k = 0; k < a.rows + 3; k += 3) {
-    if (Y0 + k - 3 >= a.Ho) break;
-    FIR4_STEP(P, Q, S, k)
-    FIR4_STEP(Q, S, P, k + 1)
-    FIR4_STEP(S, P, Q, k + 2)
+    if (Yo >= a.Ho) break;
+    FIR4_STEP(P, Q, S)
+    FIR4_STEP(Q, S, P)
+    FIR4_STEP(S, P, Q)
   }
 #undef FIR4_STEP
   if (OUT_F16) ovf_commit(a.ovf, mx);
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel2(const Upfir2Args a) {
     }
     if (F16) {
 #pragma unroll
-      for (int e = 0; e < 8; e++) mx = fmaxf(mx, fabsf(o[e]));
+      for (int e = 0; e < 8; e++) mx = ovf_max(mx, o[e]);
     }
     st8<F16>(ob + ro, o);
   };

@@ -132,6 +132,7 @@ class SynthesisEngine:
             e = {"res": r, "stem": blk.stem, "last": blk.is_last}
             if blk.stem:
                 e["const"] = blk.const.detach().float().permute(1, 2, 0).contiguous()                       # [4,4,C] fp32 master
+                e["const_absmax"] = float(e["const"].abs().max())
                 e["conv1"] = self._fold_layer(blk.conv1, w_idx, gain=1.0); w_idx += 1
             else:
                 e["conv0"] = self._fold_layer(blk.conv0, w_idx, gain=1.0); w_idx += 1
@@ -449,6 +450,9 @@ class SynthesisEngine:
             r = e["res"]
             if e["stem"]:
                 x_in = self._buf(st, "const", (B,) + tuple(e["const"].shape), fwd=True)
+                if x_in.dtype == torch.float16 and e["const_absmax"] > 65504.0:
+                    raise _lib.MgfError("tc engine: the learned 4x4 constant (|max| %.3g) does not fit fp16 forward storage; "
+                                        "select bf16: _lib.set_forward_dtype('bf16')" % e["const_absmax"])
                 x_in.copy_(e["const"].unsqueeze(0).expand(B, -1, -1, -1))
                 x = self._layer_fwd(e["conv1"], x_in, ws, maskbias, st, B, noise_on)
             else:

@@ -93,10 +93,7 @@ def test_fp16_overflow_guard_raises_instead_of_clipping_silently():
     from morphganformer_b200 import _lib
     G = util.build_G(64, 0, 2048, 64).cuda()
     with torch.no_grad():
-        G.synthesis.b4.const.mul_(3e5)
-        for r in (8, 16, 32, 64):
-            blk = getattr(G.synthesis, f"b{r}")
-            blk.skip.weight.mul_(40.0)                      # the un-normalised resnet branch carries the blow-up to the output
+        G.synthesis.b16.skip.weight.mul_(3e6)     # the resnet skip branch is not normalised: its 1x1 convolution output leaves the fp16 range
     ws = util.case_tensor((1, 17, G.num_ws, 32), 5).cuda()
     G.synthesis.engine = "tc"
     assert not _lib.fp16_overflow()
