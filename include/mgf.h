@@ -205,10 +205,12 @@ int mgf_lpips_head(int mode, const void* f, const void* n1, const float* lin, co
                    int relu_mask, int B, int64_t HW, int C, void* stream);
 /* fused forward of an LPIPS tap followed by a 2x2 max-pool: val[b] += head distance of x [B,H,W,C] vs n1 (as mgf_lpips_head mode 1) and
  * y [B,H/2,W/2,C] = maxpool2(x), one pass over x */
-int mgf_lpips_tap_pool_fwd(const void* x, const void* n1, const float* lin, void* y, float* val, int B, int H, int W, int C, void* stream);
+/* stats (optional, [B,H,W] float2): per-pixel (|f|, g . f) written by the forward kernel and consumed by the backward kernel below, which then
+ * skips its own channel-reduction pass */
+int mgf_lpips_tap_pool_fwd(const void* x, const void* n1, const float* lin, void* y, float* val, void* stats, int B, int H, int W, int C, void* stream);
 /* fused backward of an LPIPS tap followed by a 2x2 max-pool: dx = (route(dy) + d(head)/dx) * (x > 0); x, n1 forward tensors, dy/dx bf16 */
 int mgf_lpips_tap_pool_bwd(const void* x, const void* n1, const float* lin, const float* coef, const void* dy, void* dx,
-                           int B, int H, int W, int C, void* stream);
+                           const void* stats, int B, int H, int W, int C, void* stream);
 int mgf_adam_noise_step(float* latent, const float* grad, float* m, float* v, const float* noise_all, int noise_rows, float* latent_n,
                         const float* sched, int* step_ptr, float beta1, float beta2, float eps, float weight_decay, int64_t n, void* stream);
 

@@ -55,8 +55,8 @@ SIGNATURES = {
     "mgf_maxpool2_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_maxpool2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_lpips_head": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
-    "mgf_lpips_tap_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "mgf_lpips_tap_pool_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_lpips_tap_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_lpips_tap_pool_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_adam_noise_step": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_int64, c_void_p]),
     "mgf_fma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
 }

@@ -206,10 +206,15 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           tc_fence_before();
           mbar_arrive(tempty_bar);
         }
-        // rows outside the grid are never stored (the TMA store clips them) and add nothing to the reductions (their X reads as zero below)
+        // rows outside the grid are never stored (the TMA store clips them); their accumulators may hold anything (NaN included), so they are
+        // zeroed before they can reach the column reductions -- a rarely taken branch instead of 32 selects per chunk for every thread
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = __uint_as_float(raw[j]);
+        if (!valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = 0.f;
+        }
         float xv[32];
         const bool needX = (p.X != nullptr) && (p.reduce_out != nullptr || p.actgrad);
         constexpr int GX32 = GW32;

@@ -152,34 +152,39 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel2(const Upfir2Args a) {
   const int na = odd ? n : n - 1, nb = odd ? n + 1 : n;
   const float wa = (na >= 0) ? (odd ? a.fh[1] : a.fh[0]) : 0.f, wb = (nb < a.w) ? (odd ? a.fh[3] : a.fh[2]) : 0.f;
   const int oa = (na >= 0 ? na : 0) << sh, ob_ = (nb < a.w ? nb : a.w - 1) << sh;
-  const uint16_t* vb = a.v + (((long long)b * a.h * a.w) << sh) + cv * 8;
+  // running pointers (one add per row instead of 64-bit index arithmetic per access)
+  const long long vrow = (long long)a.w << sh;
+  const uint16_t* pa = a.v + ((((long long)b * a.h + (m0 - 1)) * a.w) << sh) + cv * 8 + oa;      // row m0 - 1 may lie outside: dereferenced only when valid
+  const uint16_t* pb = pa - oa + ob_;
   const long long W2 = 2LL * a.w;
-  const long long obase = ((((long long)b * 2 * a.h) * W2 + X) << sh) + cv * 8;
+  const long long obase = ((((long long)b * 2 * a.h + 2 * m0) * W2 + X) << sh) + cv * 8;
   const uint16_t* ab = a.add ? a.add + obase : nullptr;
   uint16_t* ob = a.out + obase;
   const long long orow = W2 << sh;
   float mx = 0.f;
   float h[3][8];                             // ring of horizontal sums: rows m-1, m, m+1
+  int rin = m0 - 1;                          // low-resolution row the pointers stand on
 
-  auto hrow = [&](int r, float (&h_)[8]) {
-#pragma unroll
-    for (int e = 0; e < 8; e++) h_[e] = 0.f;
-    if (r >= 0 && r < a.h) {
-      const uint16_t* rp = vb + (((long long)r * a.w) << sh);
+  auto hrow = [&](float (&h_)[8]) {          // horizontal sum of row `rin`, then step down
+    if (rin >= 0 && rin < a.h) {
       float p[8], q[8];
-      ld8<F16>(rp + oa, p); ld8<F16>(rp + ob_, q);
+      ld8<F16>(pa, p); ld8<F16>(pb, q);
 #pragma unroll
       for (int e = 0; e < 8; e++) h_[e] = fmaf(wa, p[e], wb * q[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) h_[e] = 0.f;
     }
+    pa += vrow; pb += vrow; rin++;
   };
-  auto emit = [&](int Y, const float (&ta)[8], float ca, const float (&tb)[8], float cb) {
+  auto emit = [&](const float (&ta)[8], float ca, const float (&tb)[8], float cb) {      // next output row
     float o[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) o[e] = fmaf(ca, ta[e], cb * tb[e]);
-    const long long ro = (long long)Y * orow;
     if (ab) {
       float x0[8];
-      ld8<F16>(ab + ro, x0);
+      ld8<F16>(ab, x0);
+      ab += orow;
 #pragma unroll
       for (int e = 0; e < 8; e++) o[e] += x0[e];
     }
@@ -187,15 +192,17 @@ __global__ void __launch_bounds__(256) upfir2_add_kernel2(const Upfir2Args a) {
 #pragma unroll
       for (int e = 0; e < 8; e++) mx = ovf_max(mx, o[e]);
     }
-    st8<F16>(ob + ro, o);
+    st8<F16>(ob, o);
+    ob += orow;
   };
-  hrow(m0 - 1, h[0]);
-  hrow(m0, h[1]);
+  const float fv0 = a.fv[0], fv1 = a.fv[1], fv2 = a.fv[2], fv3 = a.fv[3];
+  hrow(h[0]);
+  hrow(h[1]);
 #define UPFIR2_STEP(PREV, CUR, NEXT, m)                                        \
   if ((m) < a.h && (m) < m0 + a.rows) {                                        \
-    hrow((m) + 1, h[NEXT]);                                                    \
-    emit(2 * (m), h[PREV], a.fv[0], h[CUR], a.fv[2]);                          \
-    emit(2 * (m) + 1, h[CUR], a.fv[1], h[NEXT], a.fv[3]);                      \
+    hrow(h[NEXT]);                                                             \
+    emit(h[PREV], fv0, h[CUR], fv2);                                           \
+    emit(h[CUR], fv1, h[NEXT], fv3);                                           \
   }
   for (int m = m0; m < m0 + a.rows && m < a.h; m += 3) {
     UPFIR2_STEP(0, 1, 2, m)
@@ -229,32 +236,51 @@ __global__ void __launch_bounds__(256) upfir2_bwd_kernel2(const Upfir2BwdArgs a)
     const bool ok = X >= 0 && X < W2;
     wx[fx] = ok ? a.fh[fx] : 0.f; xo[fx] = (ok ? X : 0) << sh;
   }
-  const uint16_t* db = a.dout + (((long long)b * H2 * W2) << sh) + cv * 8;
-  uint16_t* ob = a.dv + ((((long long)b * a.h) * a.w + n) << sh) + cv * 8;
+  const long long drow = (long long)W2 << sh;
+  int Yin = 2 * m0 - 1;                      // dout row the pointers stand on (may start at -1: dereferenced only when valid)
+  const uint16_t* base = a.dout + ((((long long)b * H2 + Yin) * W2) << sh) + cv * 8;
+  const uint16_t* p0 = base + xo[0];
+  const uint16_t* p1 = base + xo[1];
+  const uint16_t* p2 = base + xo[2];
+  const uint16_t* p3 = base + xo[3];
+  uint16_t* op = a.dv + ((((long long)b * a.h + m0) * a.w + n) << sh) + cv * 8;
   const long long orow = (long long)a.w << sh;
+  const float fv0 = a.fv[0], fv1 = a.fv[1], fv2 = a.fv[2], fv3 = a.fv[3];
   float Ha[8], Hb[8], Hc[8], Hd[8];          // H[2m-1], H[2m], H[2m+1], H[2m+2]
-  auto hrow = [&](int Y, float (&h_)[8]) {
-#pragma unroll
-    for (int e = 0; e < 8; e++) h_[e] = 0.f;
-    if (Y >= 0 && Y < H2) {
-      const uint16_t* rp = db + (((long long)Y * W2) << sh);
+  auto hrow = [&](float (&h_)[8]) {          // horizontal sum of dout row Yin, then step down
+    if (Yin >= 0 && Yin < H2) {
       float q0[8], q1[8], q2[8], q3[8];
-      ld8<false>(rp + xo[0], q0); ld8<false>(rp + xo[1], q1); ld8<false>(rp + xo[2], q2); ld8<false>(rp + xo[3], q3);
+      ld8<false>(p0, q0); ld8<false>(p1, q1); ld8<false>(p2, q2); ld8<false>(p3, q3);
 #pragma unroll
       for (int e = 0; e < 8; e++) h_[e] = fmaf(wx[3], q3[e], fmaf(wx[2], q2[e], fmaf(wx[1], q1[e], wx[0] * q0[e])));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) h_[e] = 0.f;
     }
+    p0 += drow; p1 += drow; p2 += drow; p3 += drow; Yin++;
   };
-  hrow(2 * m0 - 1, Ha);
-  hrow(2 * m0, Hb);
-  for (int m = m0; m < m0 + a.rows && m < a.h; m++) {
-    hrow(2 * m + 1, Hc);
-    hrow(2 * m + 2, Hd);
-    float o[8];
+  hrow(Ha);
+  hrow(Hb);
+  // two steps per iteration so that the ring is renamed instead of moved: (Ha, Hb, Hc, Hd) -> (Hc, Hd, Ha, Hb)
+  for (int m = m0; m < m0 + a.rows && m < a.h; m += 2) {
+    hrow(Hc);
+    hrow(Hd);
+    {
+      float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; e++) o[e] = fmaf(a.fv[3], Ha[e], fmaf(a.fv[2], Hb[e], fmaf(a.fv[1], Hc[e], a.fv[0] * Hd[e])));
-    st8<false>(ob + (long long)m * orow, o);
+      for (int e = 0; e < 8; e++) o[e] = fmaf(fv3, Ha[e], fmaf(fv2, Hb[e], fmaf(fv1, Hc[e], fv0 * Hd[e])));
+      st8<false>(op, o);
+      op += orow;
+    }
+    if (m + 1 < m0 + a.rows && m + 1 < a.h) {
+      hrow(Ha);
+      hrow(Hb);
+      float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; e++) { Ha[e] = Hc[e]; Hb[e] = Hd[e]; }
+      for (int e = 0; e < 8; e++) o[e] = fmaf(fv3, Hc[e], fmaf(fv2, Hd[e], fmaf(fv1, Ha[e], fv0 * Hb[e])));
+      st8<false>(op, o);
+      op += orow;
+    }
   }
 }
 

@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* __
 // Same lane-group-per-window layout as the backward kernel below.
 template <int VPL, bool f16>
 __global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1, const float* __restrict__ lin,
-                                                                 __nv_bfloat16* __restrict__ y, float* val, int H, int W, int C) {
+                                                                 __nv_bfloat16* __restrict__ y, float* val, float2* __restrict__ stats, int H, int W, int C) {
+  // stats (optional) [B,H,W] = (|f|, g . f) per pixel with g = 2 lin (f inv - n1): the two channel reductions the backward kernel needs; they cost
+  // this pass one FFMA per element and 8 bytes per pixel, and take the whole first pass (3 FMAs per element + shuffles) out of the backward kernel
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpp = (C / 8) / VPL, wpw = 32 / lpp;
   const int sub = lane / lpp, ll = lane % lpp;
@@ -297,7 +299,9 @@ __global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bflo
         }
       }
       for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float inv = 1.f / (sqrtf(ss) + eps);
+      const float rr = sqrtf(ss);
+      const float inv = 1.f / (rr + eps);
+      float dsum = 0.f;                      // sum_c lin (f inv - n1) f  =  inv sa - sb
 #pragma unroll
       for (int q = 0; q < VPL; q++) {
         const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w}, n4[4] = {nr[k][q].x, nr[k][q].y, nr[k][q].z, nr[k][q].w};
@@ -305,8 +309,14 @@ __global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bflo
         for (int e = 0; e < 4; e++) {
           const float2 v = unpack16(w4[e], f16), t = unpack16(n4[e], f16);
           const float d0 = fmaf(v.x, inv, -t.x), d1 = fmaf(v.y, inv, -t.y);
-          wsum = fmaf(lw[q][e * 2] * d0, d0, wsum); wsum = fmaf(lw[q][e * 2 + 1] * d1, d1, wsum);
+          const float l0 = lw[q][e * 2] * d0, l1 = lw[q][e * 2 + 1] * d1;
+          wsum = fmaf(l0, d0, wsum); wsum = fmaf(l1, d1, wsum);
+          dsum = fmaf(l0, v.x, dsum); dsum = fmaf(l1, v.y, dsum);
         }
+      }
+      if (stats) {
+        for (int o = lpp >> 1; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        if (ok && ll == 0) stats[((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)] = make_float2(rr, 2.f * dsum);
       }
     }
     if (ok) {
@@ -338,7 +348,8 @@ __global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bflo
 template <int VPL, bool f16>      // f16: compile-time forward dtype (the run-time flag cost a select per unpacked pair in an issue-bound kernel)
 __global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1,
                                                                  const float* __restrict__ lin, const float* __restrict__ coef,
-                                                                 const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int H, int W, int C) {
+                                                                 const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
+                                                                 const float2* __restrict__ stats, int H, int W, int C) {
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lpp = (C / 8) / VPL, wpw = 32 / lpp;                // lanes per window, windows per warp
   const int sub = lane / lpp, ll = lane % lpp;
@@ -365,8 +376,17 @@ __global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kern
         nr[k][q] = __ldg(reinterpret_cast<const uint4*>(n1 + row) + q * lpp + ll);
       }
     }
-    // one pass: |f|^2, sum lin f^2, sum lin f n1 per pixel -> one shuffle round of 3 values -> inv and k2
+    // per pixel: inv = 1 / (|f| + eps) and k2 = (g . f) inv^2 / |f| with g = 2 lin (f inv - n1).  The two channel reductions come from the
+    // forward kernel (stats) when it ran; otherwise one pass over the packed registers: |f|^2, sum lin f^2, sum lin f n1 and one shuffle round
     float inv[4], k2[4];
+    if (stats) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 st = __ldg(stats + ((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1));
+        inv[k] = 1.f / (st.x + eps);
+        k2[k] = (st.x > 0.f) ? st.y * inv[k] * inv[k] / st.x : 0.f;
+      }
+    } else {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       float ss = 0.f, sa = 0.f, sb = 0.f;
@@ -388,6 +408,7 @@ __global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kern
       inv[k] = 1.f / (r + eps);
       const float dot = 2.f * (inv[k] * sa - sb);                // g . f  with g = 2 lin (f inv - n1)
       k2[k] = (r > 0.f) ? dot * inv[k] * inv[k] / r : 0.f;
+    }
     }
     if (!ok) continue;
 #pragma unroll
@@ -523,7 +544,7 @@ extern "C" int mgf_lpips_head(int mode, const void* f, const void* n1, const flo
   MGF_CHECK_LAUNCH("lpips_head");
   return 0;
 }
-extern "C" int mgf_lpips_tap_pool_fwd(const void* x, const void* n1, const float* lin, void* y, float* val, int B, int H, int W, int C, void* stream) {
+extern "C" int mgf_lpips_tap_pool_fwd(const void* x, const void* n1, const float* lin, void* y, float* val, void* stats, int B, int H, int W, int C, void* stream) {
   if (!x || !n1 || !lin || !y || !val) MGF_FAIL(MGF_E_BADARG, "lpips_tap_pool_fwd: null tensor");
   if (!(C == 64 || C == 128 || C == 256 || C == 512) || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "lpips_tap_pool_fwd: C in {64,128,256,512}, even H/W");
   const int vpl = C == 512 ? 2 : 1, lpp = (C / 8) / vpl, wpw = 32 / lpp;
@@ -531,7 +552,7 @@ extern "C" int mgf_lpips_tap_pool_fwd(const void* x, const void* n1, const float
   long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, B);
   cudaStream_t st = (cudaStream_t)stream;
-#define MGF_TPF(V, F) lpips_tap_pool_fwd_kernel<V, F><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, (__nv_bfloat16*)y, val, H, W, C)
+#define MGF_TPF(V, F) lpips_tap_pool_fwd_kernel<V, F><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, (__nv_bfloat16*)y, val, (float2*)stats, H, W, C)
   if (fwd_f16()) { if (vpl == 1) MGF_TPF(1, true); else MGF_TPF(2, true); }
   else { if (vpl == 1) MGF_TPF(1, false); else MGF_TPF(2, false); }
 #undef MGF_TPF
@@ -539,7 +560,7 @@ extern "C" int mgf_lpips_tap_pool_fwd(const void* x, const void* n1, const float
   return 0;
 }
 extern "C" int mgf_lpips_tap_pool_bwd(const void* x, const void* n1, const float* lin, const float* coef, const void* dy, void* dx,
-                                      int B, int H, int W, int C, void* stream) {
+                                      const void* stats, int B, int H, int W, int C, void* stream) {
   if (!x || !n1 || !lin || !coef || !dy || !dx) MGF_FAIL(MGF_E_BADARG, "lpips_tap_pool_bwd: null tensor");
   if (!(C == 64 || C == 128 || C == 256 || C == 512) || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "lpips_tap_pool_bwd: C in {64,128,256,512}, even H/W");
   const int vpl = C == 512 ? 2 : 1, lpp = (C / 8) / vpl, wpw = 32 / lpp;
@@ -547,7 +568,7 @@ extern "C" int mgf_lpips_tap_pool_bwd(const void* x, const void* n1, const float
   long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, B);
   cudaStream_t st = (cudaStream_t)stream;
-#define MGF_TPB(V, F) lpips_tap_pool_bwd_kernel<V, F><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, H, W, C)
+#define MGF_TPB(V, F) lpips_tap_pool_bwd_kernel<V, F><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, (const float2*)stats, H, W, C)
   if (fwd_f16()) { if (vpl == 1) MGF_TPB(1, true); else MGF_TPB(2, true); }
   else { if (vpl == 1) MGF_TPB(1, false); else MGF_TPB(2, false); }
 #undef MGF_TPB

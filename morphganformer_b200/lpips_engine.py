@@ -88,7 +88,8 @@ class LpipsEngine:
                 y = self._buf(f"{tag}p{ci}", (B, res // 2, res // 2, x.shape[3]), fwd=True)
                 if head_val is not None and (ci - 1) in TAP_AFTER:
                     k = TAP_AFTER[ci - 1]
-                    _lib.check(_L().mgf_lpips_tap_pool_fwd(_p(x), _p(self.n1[k]), _p(self.lin[k]), _p(y), _p(head_val), B, res, res, x.shape[3], s),
+                    stats = self._buf(f"{tag}stats{k}", (B, res, res, 2), torch.float32)      # per-pixel (|f|, g . f) for the backward kernel
+                    _lib.check(_L().mgf_lpips_tap_pool_fwd(_p(x), _p(self.n1[k]), _p(self.lin[k]), _p(y), _p(head_val), _p(stats), B, res, res, x.shape[3], s),
                                "mgf_lpips_tap_pool_fwd")
                 else:
                     _lib.check(_L().mgf_maxpool2_fwd(_p(x), _p(y), B, res, res, x.shape[3], s), "mgf_maxpool2_fwd")
@@ -182,7 +183,7 @@ class LpipsEngine:
                 g2 = self._buf(f"dpre{ci - 1}", tuple(src.shape))
                 if (ci - 1) in TAP_AFTER:      # tap + pool: one fused kernel (head gradient + pool routing + ReLU mask)
                     k = TAP_AFTER[ci - 1]
-                    _lib.check(_L().mgf_lpips_tap_pool_bwd(_p(src), _p(self.n1[k]), _p(self.lin[k]), _p(coef), _p(dp), _p(g2), B,
+                    _lib.check(_L().mgf_lpips_tap_pool_bwd(_p(src), _p(self.n1[k]), _p(self.lin[k]), _p(coef), _p(dp), _p(g2), _p(self._st.get(f"gstats{k}")), B,
                                                            src.shape[1], src.shape[2], src.shape[3], s), "mgf_lpips_tap_pool_bwd")
                 else:
                     _lib.check(_L().mgf_maxpool2_bwd(_p(src), _p(dp), None, _p(g2), B, src.shape[1], src.shape[2], src.shape[3], s), "mgf_maxpool2_bwd")

@@ -20,7 +20,7 @@ for (H, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
     out = torch.empty_like(f); n = f.numel() * 2
     run("lpips_head fwd %dx%d C%d" % (H, H, C), lambda: L.mgf_lpips_head(1, p(f), p(n1), p(lin), None, None, p(val), 0, B, H * H, C, s), 2 * n)
     dy = bf(B, H // 2, H // 2, C)
-    run("lpips_tap_pool_bwd %dx%d C%d" % (H, H, C), lambda: L.mgf_lpips_tap_pool_bwd(p(f), p(n1), p(lin), p(coef), p(dy), p(out), B, H, H, C, s), 3.25 * n)
+    run("lpips_tap_pool_bwd %dx%d C%d" % (H, H, C), lambda: L.mgf_lpips_tap_pool_bwd(p(f), p(n1), p(lin), p(coef), p(dy), p(out), None, B, H, H, C, s), 3.25 * n)
     y = torch.empty(B, H // 2, H // 2, C, dtype=torch.bfloat16, device="cuda")
     run("maxpool2_fwd %dx%d C%d" % (H, H, C), lambda: L.mgf_maxpool2_fwd(p(f), p(y), B, H, H, C, s), 1.25 * n)
 for (H, C) in [(1024, 32), (512, 64), (256, 128)]:
