@@ -173,13 +173,15 @@ int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int
 
 /* ---- fused duplex attention layer (attention.cu): TransformerLayer.forward (networks.py:748-822, default GANformer config)
  * + noise + bias_act tail (:1036-1040) in one pass over X [B,HW,C] bf16; Kf [16,C], Sc [HW,16], maskbias [B,16], VM [B,16,C],
- * bm [C] are the host-folded constants described in attention.cu.  bwd writes dX, accumulates dVM [B,16,C] and R [B,C]. */
+ * bm [C] are the host-folded constants described in attention.cu.  bwd writes dX, accumulates dVM [B,16,C] and R [B,C].
+ * dmask (optional, [B,HW,16] fp32): attention dropout of training mode (networks.py:505-513) = keep-masks of the cell and column dropouts
+ * times their 1/(1-p) scales; multiplies the probabilities after the softmax (probs, when requested, are the dropped ones, as in the reference). */
 int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                  const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                 void* out, float* probs, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
+                 void* out, float* probs, const float* dmask, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
 int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                  const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                 void* dX, float* dVM, float* R, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
+                 void* dX, float* dVM, float* R, const float* dmask, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
 
 /* ---- mapping network z -> ws and its backward wrt z (mapping.cu): training/networks.py MappingNetwork.forward :894-942 with the
  * GANformer-default configuration (16 local + 1 global latents x 32, 4 resnet blocks, latent self-attention, positional maps).

@@ -54,6 +54,7 @@ struct AttnMP {
   const float* noise; const float* nstr; const float* bias; float gain, alpha;
   void* out; float* probs;
   const __nv_bfloat16* dz; __nv_bfloat16* dX; float* dVM; float* R;
+  const float* dmask;          // attention dropout (training mode): [B,HW,16] fp32 keep-mask * scale, multiplies the probabilities after the softmax (nullptr: eval)
   long long HW; int C; int pix_per_cta; long long nbs;      // nbs: elements between per-sample noise planes (0 = shared plane)
 };
 
@@ -137,6 +138,14 @@ __device__ __forceinline__ void tile_probs(const uint4* __restrict__ x0, const u
   P[0] *= i0; P[1] *= i0; P[4] *= i0; P[5] *= i0; P[2] *= i1; P[3] *= i1; P[6] *= i1; P[7] *= i1;
 }
 
+// attention dropout (reference networks.py:505-513: probs = dropout(probs) over cells, then over whole 'to' columns; both masks and their
+// 1/(1-p) scales arrive pre-multiplied in dmask): values of the two rows in the layout of P
+__device__ __forceinline__ void load_dmask(const float* dm0, const float* dm1, int t, float (&M)[8]) {
+  const float2 a0 = *reinterpret_cast<const float2*>(dm0 + 2 * t), a1 = *reinterpret_cast<const float2*>(dm0 + 8 + 2 * t);
+  const float2 b0 = *reinterpret_cast<const float2*>(dm1 + 2 * t), b1 = *reinterpret_cast<const float2*>(dm1 + 8 + 2 * t);
+  M[0] = a0.x; M[1] = a0.y; M[4] = a1.x; M[5] = a1.y; M[2] = b0.x; M[3] = b0.y; M[6] = b1.x; M[7] = b1.y;
+}
+
 // Forward shared memory: sKhi, sKlo [16][C+32] 16-bit | sVp uint2 [C/8][32] (fp16) | sm1 [C] fp32 (1 + bm) | sb [C] fp32 (bias)
 static int fwd_smem(int C) { return 2 * NT * krow(C) * 2 + (C / 8) * 32 * 8 + 2 * C * 4; }
 
@@ -166,6 +175,12 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(AttnMP p) {
     const uint4* x1 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.X) + ((long long)b * p.HW + q1) * C);
     float P[8], rn0, rn1;
     tile_probs<F16, C32>(x0, x1, sKhi, sKlo, C, g, t, p.Sc + q0 * NT, p.Sc + q1 * NT, mbr, P, rn0, rn1);
+    if (p.dmask) {
+      float M[8];
+      load_dmask(p.dmask + ((long long)b * p.HW + q0) * NT, p.dmask + ((long long)b * p.HW + q1) * NT, t, M);
+#pragma unroll
+      for (int i = 0; i < 8; i++) P[i] *= M[i];
+    }
     if (p.probs) {
       float* pr0 = p.probs + ((long long)b * p.HW + q0) * NT; float* pr1 = p.probs + ((long long)b * p.HW + q1) * NT;
       if (v0) { *reinterpret_cast<float2*>(pr0 + 2 * t) = make_float2(P[0], P[1]); *reinterpret_cast<float2*>(pr0 + 8 + 2 * t) = make_float2(P[4], P[5]); }
@@ -269,7 +284,9 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
     const uint4* x1 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.X) + ((long long)b * p.HW + q1) * C);
     const uint4* g0 = reinterpret_cast<const uint4*>(p.dz + ((long long)b * p.HW + q0) * C);
     const uint4* g1 = reinterpret_cast<const uint4*>(p.dz + ((long long)b * p.HW + q1) * C);
-    float P[8], rn0 = 0.f, rn1 = 0.f;
+    float P[8], M[8], rn0 = 0.f, rn1 = 0.f;      // P: softmax probabilities; M: dropout mask * scale (ones in eval mode); A = P * M feeds ctl and dVM
+#pragma unroll
+    for (int i = 0; i < 8; i++) M[i] = 1.f;
     uint32_t pa0 = 0, pa1 = 0, pa2 = 0, pa3 = 0;
     float nz0 = 0.f, nz1 = 0.f;
     const float gm0 = v0 ? p.gain : 0.f, gm1 = v1 ? p.gain : 0.f;
@@ -277,11 +294,15 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
     float sd0 = 0.f, sd1 = 0.f;
     if (active) {
       tile_probs<F16, C32>(x0, x1, sKhi, sKlo, C, g, t, p.Sc + q0 * NT, p.Sc + q1 * NT, mbr, P, rn0, rn1);
-      pa0 = pk<true>(P[0], P[1]); pa1 = pk<true>(P[2], P[3]); pa2 = pk<true>(P[4], P[5]); pa3 = pk<true>(P[6], P[7]);
+      if (p.dmask) load_dmask(p.dmask + ((long long)b * p.HW + q0) * NT, p.dmask + ((long long)b * p.HW + q1) * NT, t, M);
+      float A[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) A[i] = P[i] * M[i];
+      pa0 = pk<true>(A[0], A[1]); pa1 = pk<true>(A[2], A[3]); pa2 = pk<true>(A[4], A[5]); pa3 = pk<true>(A[6], A[7]);
       if (p.noise) { nz0 = p.noise[b * p.nbs + q0] * ns; nz1 = p.noise[b * p.nbs + q1] * ns; }
-      // probabilities of the tile (bf16) for the dVM phase
-      *reinterpret_cast<uint32_t*>(myP + g * SPS + 2 * t) = pack_bf16(P[0], P[1]); *reinterpret_cast<uint32_t*>(myP + g * SPS + 8 + 2 * t) = pack_bf16(P[4], P[5]);
-      *reinterpret_cast<uint32_t*>(myP + (g + 8) * SPS + 2 * t) = pack_bf16(P[2], P[3]); *reinterpret_cast<uint32_t*>(myP + (g + 8) * SPS + 8 + 2 * t) = pack_bf16(P[6], P[7]);
+      // (dropped) probabilities of the tile (bf16) for the dVM phase
+      *reinterpret_cast<uint32_t*>(myP + g * SPS + 2 * t) = pack_bf16(A[0], A[1]); *reinterpret_cast<uint32_t*>(myP + g * SPS + 8 + 2 * t) = pack_bf16(A[4], A[5]);
+      *reinterpret_cast<uint32_t*>(myP + (g + 8) * SPS + 2 * t) = pack_bf16(A[2], A[3]); *reinterpret_cast<uint32_t*>(myP + (g + 8) * SPS + 8 + 2 * t) = pack_bf16(A[6], A[7]);
     }
 #pragma unroll
     for (int h = 0; h < NH; h++) {
@@ -351,7 +372,9 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
     }
     if (active) {
       sd0 = quad_sum(sd0); sd1 = quad_sum(sd1);
-      // dS = A * (dA - sum_t A dA);  the accumulator layout of dA equals the layout of P
+      // dA is the gradient wrt the dropped probabilities: dP = dA * M, then the softmax backward dS = P * (dP - sum_t P dP);
+      // the accumulator layout of dA equals the layout of P
+      dA0[0] *= M[0]; dA0[1] *= M[1]; dA0[2] *= M[2]; dA0[3] *= M[3]; dA1[0] *= M[4]; dA1[1] *= M[5]; dA1[2] *= M[6]; dA1[3] *= M[7];
       const float ad0 = quad_sum(P[0] * dA0[0] + P[1] * dA0[1] + P[4] * dA1[0] + P[5] * dA1[1]);
       const float ad1 = quad_sum(P[2] * dA0[2] + P[3] * dA0[3] + P[6] * dA1[2] + P[7] * dA1[3]);
       const uint32_t sa0 = pack_bf16(P[0] * (dA0[0] - ad0), P[1] * (dA0[1] - ad0)), sa1 = pack_bf16(P[2] * (dA0[2] - ad1), P[3] * (dA0[3] - ad1));
@@ -484,12 +507,12 @@ using namespace mgf;
 
 extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                             const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                            void* out, float* probs, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
+                            void* out, float* probs, const float* dmask, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
   if (!X || !Kf || !Sc || !maskbias || !VM || !bm || !out) MGF_FAIL(MGF_E_BADARG, "attn_fwd: null tensor");
   if (B <= 0 || HW <= 0) MGF_FAIL(MGF_E_SHAPE, "attn_fwd: empty batch or grid");
   if (int e = check_c(C, "attn_fwd")) return e;
   AttnMP p{}; p.X = X; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm; p.noise = noise; p.nstr = nstr; p.bias = bias;
-  p.gain = gain; p.alpha = alpha; p.out = out; p.probs = probs; p.HW = HW; p.C = C; p.nbs = noise_bstride;
+  p.gain = gain; p.alpha = alpha; p.out = out; p.probs = probs; p.dmask = dmask; p.HW = HW; p.C = C; p.nbs = noise_bstride;
   p.pix_per_cta = pix_per_cta(HW, B, 2);      // one wave of 2 CTAs per SM
   dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
   const int rc = fwd_f16() ? launch_fwd<true>(p, grid, fwd_smem(C), (cudaStream_t)stream) : launch_fwd<false>(p, grid, fwd_smem(C), (cudaStream_t)stream);
@@ -500,12 +523,12 @@ extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, con
 
 extern "C" int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                             const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                            void* dX, float* dVM, float* R, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
+                            void* dX, float* dVM, float* R, const float* dmask, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
   if (!X || !dz || !Kf || !Sc || !maskbias || !VM || !bm || !dX || !dVM) MGF_FAIL(MGF_E_BADARG, "attn_bwd: null tensor");
   if (B <= 0 || HW <= 0) MGF_FAIL(MGF_E_SHAPE, "attn_bwd: empty batch or grid");
   if (int e = check_c(C, "attn_bwd")) return e;
   AttnMP p{}; p.X = X; p.dz = (const __nv_bfloat16*)dz; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm;
-  p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.HW = HW; p.C = C; p.nbs = noise_bstride;
+  p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.dmask = dmask; p.HW = HW; p.C = C; p.nbs = noise_bstride;
   p.pix_per_cta = pix_per_cta(HW, B, 1);      // one wave of 1 CTA per SM
   dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
   const int rc = fwd_f16() ? launch_bwd<true>(p, grid, bwd_smem(C), (cudaStream_t)stream) : launch_bwd<false>(p, grid, bwd_smem(C), (cudaStream_t)stream);

@@ -260,6 +260,7 @@ class SynthesisEngine:
             L.bVM = (Wm @ bv).contiguous()
             L.WVMt = L.WVM.t().contiguous()                                               # [32, C]
             L.bm = (t.modulation.bias.detach().float() * float(t.modulation.b_gain)).contiguous()
+            L.att_dp = float(t.att_dp.p)
         return L
 
     # -------------------------------------------------------------------------------------------- buffers
@@ -285,7 +286,8 @@ class SynthesisEngine:
             off = st.get("zpool_used", 0)
             pool = st.get("zpool")
             if pool is None:
-                pool = st["zpool"] = torch.zeros(1 << 20, dtype=torch.float32, device=self.dev)      # 4 MB: ~20x what a 1024^2 generator needs at B = 8
+                # 4 MB per 8 samples: ~4x what a 1024^2 generator needs (every target is [B, channels] or [B, 16, channels])
+                pool = st["zpool"] = torch.zeros((1 << 20) * max(1, (st.get("batch", 8) + 7) // 8), dtype=torch.float32, device=self.dev)
             if off + n > pool.numel():
                 raise _lib.MgfError("engine: reduction arena exhausted (%d + %d floats)" % (off, n))
             t = st[key] = pool[off:off + n].view(*shape)
@@ -386,12 +388,23 @@ class SynthesisEngine:
             if not L.two_stage_fwd:
                 tc.conv_tc([a_in], Wf, L.taps_f, (B, h, w), L.phases, L.O, y, scale_n=scale_n, alg_scale=1.0 / L.phases, tag="g.fwd", **kw)
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
+            dmask = None
+            if st.get("train"):
+                # attention dropout of training mode (reference networks.py:505-513, :374-376): cell mask [B,1,HW,16] then column mask
+                # [B,1,1,16], both torch dropouts of rate attention_dropout / 2 drawn right after the layer's noise plane -- the same draws,
+                # in the same order, as the ops engine makes, so one torch seed gives both engines identical masks
+                pdrop = float(L.att_dp)
+                if pdrop > 0:
+                    m1 = torch.nn.functional.dropout(torch.ones([B, 1, H * Wd, 16], device=self.dev), pdrop, True)
+                    m2 = torch.nn.functional.dropout(torch.ones([B, 1, 1, 16], device=self.dev), pdrop, True)
+                    dmask = (m1 * m2).reshape(B, H * Wd, 16).contiguous()
+            st[f"dmask{L.idx}"] = dmask
             probs = None
             if st.get("want_probs"):                            # attention maps requested: [B, HW, 16] fp32 per attention layer, in layer order
                 probs = torch.empty(B, H * Wd, 16, device=self.dev)
                 st["probs"].append(probs)
             _lib.check(_L().mgf_attn_fwd(_p(y), _p(L.Kf), _p(L.Sc), _p(maskbias), _p(VM), _p(L.bm), _p(noise), _p(nstr), _p(L.bias),
-                                         L.gain, LRELU_ALPHA, _p(z), _p(probs), B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_fwd")
+                                         L.gain, LRELU_ALPHA, _p(z), _p(probs), _p(dmask), B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_fwd")
         elif L.superpix:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             bias2 = L.bias.repeat(2).contiguous() if L.bias is not None else None
@@ -419,13 +432,16 @@ class SynthesisEngine:
             st[key] = torch.randn([B, 1, H, Wd], device=self.dev)
         return st[key], H * Wd
 
-    def forward_raw(self, ws, mask=None, noise_mode="const", want_probs=False):
-        """want_probs: also keep every attention layer's probabilities [B, HW, 16] (fp32) in self.last_probs (attention maps)."""
+    def forward_raw(self, ws, mask=None, noise_mode="const", want_probs=False, train=False):
+        """want_probs: also keep every attention layer's probabilities [B, HW, 16] (fp32) in self.last_probs (attention maps).
+        train: training-mode forward (attention dropout masks drawn per layer; the backward pass re-uses them)."""
         if noise_mode not in ("const", "none", "random"):
             raise ValueError("noise_mode must be 'random', 'const' or 'none'")
         B = ws.shape[0]
         st = self._state(B)
+        st["batch"] = B
         st["want_probs"], st["probs"] = bool(want_probs), []
+        st["train"] = bool(train)
         self.last_probs = st["probs"]
         ws = ws.detach().to(torch.float32).contiguous()
         st["ws"] = ws
@@ -569,7 +585,8 @@ class SynthesisEngine:
         dVM = self._zbuf(st, f"dVM{L.idx}", (B, 16, L.O))
         R = self._zbuf(st, f"R{L.idx}", (B, L.O))
         _lib.check(_L().mgf_attn_bwd(_p(y), _p(dz), _p(L.Kf), _p(L.Sc), _p(st["maskbias"]), _p(st[f"VM{L.idx}"]), _p(L.bm), _p(noise), _p(nstr),
-                                     _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_bwd")
+                                     _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), _p(st.get(f"dmask{L.idx}")), B, H * Wd, L.O, nbs, _s(self.dev)),
+                   "mgf_attn_bwd")
         dcomp = dws[:, :-1, L.idx]                                 # [B,16,32] strided, accumulate
         self._on_side(lambda: _lib.check(_L().mgf_small_gemm(_p(dVM), 16 * L.O, L.O, _p(L.WVMt), None, _p(dcomp), dcomp.stride(0), dcomp.stride(1),
                                                              B, 16, dcomp.shape[2], L.O, 1, _s(self.dev)), "mgf_small_gemm"))
@@ -681,12 +698,20 @@ class SynthesisEngine:
         return dws
 
     # -------------------------------------------------------------------------------------------- autograd entry
+    def _param_state(self):
+        return tuple((id(p), p._version) for p in list(self.net.parameters()) + list(self.net.buffers()))
+
     def __call__(self, ws, pos=None, mask=None, noise_mode="const", fused_modconv=None, want_probs=False, **_ignored):
-        if self.net.training:
-            # train mode means attention dropout and w_avg tracking in the reference (networks.py:505-513, :928-929); this engine folds frozen
-            # weights and is an inference / projection engine -- use engine="ops" for training-mode graphs
-            raise NotImplementedError("tc engine: the synthesis network is in training mode; call G.eval() (or use engine='ops')")
-        img = _SynthesisFn.apply(ws, self, mask, noise_mode, want_probs)
+        """Public entry (G.synthesis with engine='tc').  Training mode (reference networks.py:505-513, :1010-1017): attention dropout and,
+        with noise_mode='random', fresh noise planes per call; gradients flow to ws only (the engine folds the weights: it serves projection,
+        path-length style regularisers and evaluation, not weight updates -- use engine='ops' to train the weights).  The folded weights are
+        rebuilt automatically when a parameter changed in place since the last call (optimizer steps, load_state_dict)."""
+        state = self._param_state()
+        if state != getattr(self, "_folded_state", None):
+            if getattr(self, "_folded_state", None) is not None:
+                self.refresh()
+            self._folded_state = state
+        img = _SynthesisFn.apply(ws, self, mask, noise_mode, want_probs, bool(self.net.training))
         if _lib.forward_torch_dtype() == torch.float16 and not torch.cuda.is_current_stream_capturing():
             _lib.check_fp16_overflow(self.dev, "G.synthesis (tc engine)")     # public entry: a clipped image must not pass silently
         return img
@@ -694,14 +719,14 @@ class SynthesisEngine:
 
 class _SynthesisFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ws, eng, mask, noise_mode, want_probs):
+    def forward(ctx, ws, eng, mask, noise_mode, want_probs, train):
         ctx.eng = eng
         ctx.B = ws.shape[0]
-        return eng.forward_raw(ws, mask=mask, noise_mode=noise_mode, want_probs=want_probs)
+        return eng.forward_raw(ws, mask=mask, noise_mode=noise_mode, want_probs=want_probs, train=train)
 
     @staticmethod
     def backward(ctx, dimg):
-        return ctx.eng.backward_raw(dimg), None, None, None, None
+        return ctx.eng.backward_raw(dimg), None, None, None, None, None
 
 
 def smoke():

@@ -43,7 +43,7 @@ def _normalize(x, eps=1e-8):
 
 
 def transformer_layer(sd, pre, from_tensor, to_tensor, from_pos, to_pos, att_mask, from_len, to_len,
-                      integration="mul", norm="layer", kmeans=True, lrmul=1.0):
+                      integration="mul", norm="layer", kmeans=True, lrmul=1.0, dmask=None):
     """TransformerLayer.forward, networks.py:748-822, for num_heads=1, kmeans_iters=1, eval mode
     (dropout = multiply by ones, :374-376), parametric centroids (:715-717), no gates (:546-547).
     from_tensor [B*F or B,F, C]; to_tensor [B,T,Dt]; from_pos [F, P] or None; to_pos [T,P] or None.
@@ -73,6 +73,8 @@ def transformer_layer(sd, pre, from_tensor, to_tensor, from_pos, to_pos, att_mas
     if att_mask is not None:
         scores = scores + (1 - att_mask.unsqueeze(1).to(ft.dtype)) * -10000.0   # :799, :379-380
     probs = F.softmax(scores, dim=-1)                                  # :507
+    if dmask is not None:            # training mode, :510-512: probs = dropout(probs) over cells, then over whole 'to' columns; the two
+        probs = probs * dmask        # torch.nn.Dropout masks (keep / (1 - p)) are injected pre-multiplied, broadcastable to [B,1,F,T]
     control = probs.matmul(v).permute(0, 2, 1, 3).reshape(-1, dim)     # :812-814
     # integrate(), :657-672, with att_norm :341-358
     x = ft
@@ -140,7 +142,7 @@ def modulated_conv2d(x, weight, styles, up=1, padding=0, f=None, demodulate=True
 
 
 def synthesis_layer(sd, pre, x, w, pos, mask, out_res, up=1, gain=1.0, attention=True, bias=True, noise=True,
-                    noise_mode="const", f=None, rand_noise=None):
+                    noise_mode="const", f=None, rand_noise=None, dmask=None):
     """SynthesisLayer.forward, networks.py:1010-1042."""
     nz = None
     if noise and noise_mode != "none":
@@ -158,7 +160,7 @@ def synthesis_layer(sd, pre, x, w, pos, mask, out_res, up=1, gain=1.0, attention
         shape = x.shape
         xt = x.reshape(shape[0], shape[1], -1).permute(0, 2, 1)
         xt, att = transformer_layer(sd, pre + ".transformer", xt, w[:, :-1], sd[pre + ".grid_pos"].to(x.dtype), pos,
-                                    mask.unsqueeze(1), out_res * out_res, w.shape[1] - 1)
+                                    mask.unsqueeze(1), out_res * out_res, w.shape[1] - 1, dmask=dmask)
         x = xt.permute(0, 2, 1).reshape(shape)
     if nz is not None:
         x = x + nz
@@ -168,10 +170,13 @@ def synthesis_layer(sd, pre, x, w, pos, mask, out_res, up=1, gain=1.0, attention
 
 
 def synthesis(sd, ws, pos, mask, res, architecture="resnet", end_res=8, noise_mode="const", return_att=False,
-              dtype=torch.float32, trace=None):
+              dtype=torch.float32, trace=None, inject=None):
     """SynthesisNetwork.forward networks.py:1244-1264 + SynthesisBlock.forward :1132-1174 (resnet architecture,
     const stem, ToRGB only on the last block).  ws [B,k,num_ws,w_dim]."""
     assert architecture == "resnet"
+    # inject (training-mode runs): {"noise": {ws index: [B,1,r,r] plane of noise_mode='random'}, "dmask": {ws index: [B,1,r*r,16] dropout mask}}
+    inj_n = (inject or {}).get("noise", {})
+    inj_d = (inject or {}).get("dmask", {})
     ws = ws.to(dtype)
     sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     pos = pos.to(dtype)
@@ -189,7 +194,7 @@ def synthesis(sd, ws, pos, mask, res, architecture="resnet", end_res=8, noise_mo
         if r == 4:
             x = sd[pre + ".const"].unsqueeze(0).repeat(b, 1, 1, 1)
             x, a = synthesis_layer(sd, pre + ".conv1", x, ws[:, :, w_idx], pos, mask, r, attention=attn,
-                                   noise_mode=noise_mode, f=f)
+                                   noise_mode=noise_mode, f=f, rand_noise=inj_n.get(w_idx), dmask=inj_d.get(w_idx))
             atts.append(a)
             if trace is not None:
                 trace[f"z{w_idx}"] = x
@@ -200,11 +205,11 @@ def synthesis(sd, ws, pos, mask, res, architecture="resnet", end_res=8, noise_mo
             y = ops.conv2d_resample(x, wsk, f=f, up=2, padding=0, flip_weight=False)
             y = ops.bias_act(y, None, act="linear", gain=math.sqrt(0.5))
             x, a0 = synthesis_layer(sd, pre + ".conv0", x, ws[:, :, w_idx], pos, mask, r, up=2, attention=attn,
-                                    noise_mode=noise_mode, f=f)
+                                    noise_mode=noise_mode, f=f, rand_noise=inj_n.get(w_idx), dmask=inj_d.get(w_idx))
             if trace is not None:
                 trace[f"z{w_idx}"] = x
             x, a1 = synthesis_layer(sd, pre + ".conv1", x, ws[:, :, w_idx + 1], pos, mask, r, gain=math.sqrt(0.5),
-                                    attention=attn, noise_mode=noise_mode, f=f)
+                                    attention=attn, noise_mode=noise_mode, f=f, rand_noise=inj_n.get(w_idx + 1), dmask=inj_d.get(w_idx + 1))
             atts += [a0, a1]
             if trace is not None:
                 trace[f"z{w_idx + 1}"] = x

@@ -9,9 +9,11 @@ from morphganformer_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 
-def _ref(X, Kf, Sc, mb, VM, bm, noise, ns, bias, gain, alpha):
+def _ref(X, Kf, Sc, mb, VM, bm, noise, ns, bias, gain, alpha, dmask=None):
     S = X @ Kf.t() + Sc[None] + mb[:, None, :]
     A = torch.softmax(S, -1)
+    if dmask is not None:          # attention dropout (reference networks.py:505-513): applied after the softmax, no renormalisation
+        A = A * dmask
     ctl = A @ VM + bm
     xn = X * torch.rsqrt(X.square().mean(-1, keepdim=True) + 1e-8)
     u = xn * (1 + ctl) + noise[None, :, None] * ns + bias
@@ -23,8 +25,9 @@ def _p(t):
 
 
 @pytest.mark.parametrize("fwd", ["fp16", "bf16"])
+@pytest.mark.parametrize("dropout", [False, True])
 @pytest.mark.parametrize("B,HW,C", [(2, 16, 32), (2, 100, 64), (3, 1032, 128), (2, 4096, 256), (1, 500, 384), (2, 1000, 512), (8, 16, 512)])
-def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd):
+def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd, dropout):
     L = _lib.lib()
     _lib.set_forward_dtype(fwd)
     try:
@@ -36,14 +39,18 @@ def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd):
         VM, bm, noise, ns, bias = r(B, 16, C) * 0.3, r(C) * 0.1, r(HW), torch.tensor([0.2], device="cuda"), r(C) * 0.1
         dz16 = r(B, HW, C).to(torch.bfloat16)
         gain, alpha = 1.4142135, 0.2
+        dmask = None
+        if dropout:                # cell mask x column mask, each scaled by 1/(1-p), p = 0.06 (attention_dropout / 2)
+            keep = lambda *sh: (torch.rand(*sh, device="cuda", generator=g) >= 0.06).float() / 0.94
+            dmask = (keep(B, HW, 16) * keep(B, 1, 16)).contiguous()
         s = torch.cuda.current_stream().cuda_stream
         out = torch.empty_like(X16); probs = torch.empty(B, HW, 16, device="cuda")
-        _lib.check(L.mgf_attn_fwd(_p(X16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(out), _p(probs), B, HW, C, 0, s), "fwd")
+        _lib.check(L.mgf_attn_fwd(_p(X16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(out), _p(probs), _p(dmask), B, HW, C, 0, s), "fwd")
         dX = torch.empty(B, HW, C, device="cuda", dtype=torch.bfloat16); dVM = torch.zeros(B, 16, C, device="cuda"); R = torch.zeros(B, C, device="cuda")
-        _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(dX), _p(dVM), _p(R), B, HW, C, 0, s), "bwd")
+        _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(dX), _p(dVM), _p(R), _p(dmask), B, HW, C, 0, s), "bwd")
         torch.cuda.synchronize()
         Xr = X16.float().requires_grad_(True); VMr = VM.clone().requires_grad_(True)
-        ref, A = _ref(Xr, Kf, Sc, mb, VMr, bm, noise, ns, bias, gain, alpha)
+        ref, A = _ref(Xr, Kf, Sc, mb, VMr, bm, noise, ns, bias, gain, alpha, dmask)
         gX, gVM = torch.autograd.grad(ref, [Xr, VMr], grad_outputs=dz16.float())
         Rr = (gX * Xr.detach()).sum(1)
         eps = 2.0 ** -10 if fwd == "fp16" else 2.0 ** -7
@@ -64,5 +71,49 @@ def test_attn_rejects_bad_shapes():
     L = _lib.lib()
     x = torch.zeros(1, 16, 48, device="cuda", dtype=torch.bfloat16)
     f = torch.zeros(16, 48, device="cuda")
-    rc = L.mgf_attn_fwd(_p(x), _p(f), _p(f), _p(f), _p(f), _p(f), None, None, None, 1.0, 0.2, _p(x), None, 1, 16, 48, 0, 0)
+    rc = L.mgf_attn_fwd(_p(x), _p(f), _p(f), _p(f), _p(f), _p(f), None, None, None, 1.0, 0.2, _p(x), None, None, 1, 16, 48, 0, 0)
     assert rc != 0 and b"C=48" in L.mgf_last_error()
+
+
+@pytest.mark.parametrize("res,C,B", [(8, 32, 2), (16, 64, 3)])
+def test_attn_kernel_vs_oracle_transformer_layer(res, C, B):
+    """The kernel against the ORACLE's restatement of the reference layer (oracle/ganformer.py transformer_layer = networks.py:748-822 with
+    its separate Q / positional / centroid / value / modulation projections), not against the builder's own folded formula: the folding of
+    engine.SynthesisEngine._fold_layer (Kf, Sc, VM, bm) is applied to a real layer's parameters, the kernel runs on the folded constants, and
+    output + d(X) must match the oracle layer evaluated on the un-folded parameters (fp32 autograd on the CPU)."""
+    import math
+    import util
+    from oracle import ganformer
+    G = util.build_G(res, 0, 64 * res, C)             # last block: res x res with C channels
+    sd = util.state_dict_cpu(G)
+    pre = f"synthesis.b{res}.conv1.transformer"
+    HW = res * res
+    g = torch.Generator().manual_seed(res)
+    X = torch.randn(B, HW, C, generator=g) * 1.3
+    Y = torch.randn(B, 16, 32, generator=g)
+    mask = torch.ones(B, 16); mask[0, 3] = 0
+    Xr = X.half().float().requires_grad_(True)
+    ref, probs_ref = ganformer.transformer_layer(sd, pre, Xr, Y, sd[f"synthesis.b{res}.conv1.grid_pos"], sd["pos"], mask.unsqueeze(1), HW, 16)
+    dz = torch.randn(B, HW, C, generator=g)
+    gX, = torch.autograd.grad(ref, [Xr], dz.bfloat16().float())
+    # fold exactly as the engine does
+    from morphganformer_b200 import engine as E
+    Gc = G.cuda(); Gc.synthesis.engine = "tc"
+    eng = E.SynthesisEngine(Gc.synthesis)
+    Lr = [e for e in eng.blocks if e["res"] == res][0]["conv1"]
+    assert Lr.attn
+    VM = (Y.cuda() @ Lr.WVM.t() + Lr.bVM).contiguous()
+    mb = ((1.0 - mask.cuda()) * -10000.0).contiguous()
+    L, s = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    X16 = X.half().cuda()
+    out = torch.empty_like(X16); probs = torch.empty(B, HW, 16, device="cuda")
+    # no noise, no bias, linear tail (alpha = 1, gain = 1): the pure attention layer
+    _lib.check(L.mgf_attn_fwd(_p(X16), _p(Lr.Kf), _p(Lr.Sc), _p(mb), _p(VM), _p(Lr.bm), None, None, None, 1.0, 1.0, _p(out), _p(probs), None, B, HW, C, 0, s), "fwd")
+    dX = torch.empty(B, HW, C, device="cuda", dtype=torch.bfloat16); dVM = torch.zeros(B, 16, C, device="cuda"); R = torch.zeros(B, C, device="cuda")
+    dz16 = dz.bfloat16().cuda()
+    _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Lr.Kf), _p(Lr.Sc), _p(mb), _p(VM), _p(Lr.bm), None, None, None, 1.0, 1.0, _p(dX), _p(dVM), _p(R), None, B, HW, C, 0, s), "bwd")
+    torch.cuda.synchronize()
+    assert (probs.cpu() - probs_ref.detach().reshape(B, HW, 16)).abs().max().item() < 2e-3
+    scale = ref.detach().abs().max().item()
+    assert (out.float().cpu() - ref.detach()).abs().max().item() < 4 * 2.0 ** -10 * scale
+    assert ((dX.float().cpu() - gX).norm() / gX.norm()).item() < 1.5e-2

@@ -240,3 +240,52 @@ def test_tc_engine_refuses_training_mode():
     G.train()
     with pytest.raises(NotImplementedError):
         G.synthesis(util.case_tensor((1, 17, G.num_ws, 32), 1).cuda(), pos=G.pos, mask=torch.ones(1, 16, device="cuda"), noise_mode="const")
+
+
+def test_training_mode_on_both_engines_vs_oracle_with_injected_masks():
+    """G.train() -> attention dropout (two torch dropouts of rate attention_dropout / 2 per attention layer: cells, then whole
+    'to' columns; reference networks.py:505-513) and noise_mode='random' planes (:1015-1017).  Both engines draw, per layer and in layer order,
+    randn([B,1,r,r]) then dropout(ones([B,1,r*r,16])) then dropout(ones([B,1,1,16])): the test replays exactly these draws from the same seed,
+    injects the planes and masks into the oracle, and compares image and d(ws): exact-fp32 ops engine 1e-4, tcgen05 engine at its 16-bit bound."""
+    res, B = 32, 2
+    G = util.build_G(res, 0, 1024, 32)
+    sd = util.state_dict_cpu(G)
+    ws = util.case_tensor((B, 17, G.num_ws, 32), 31)
+    tgt = torch.tanh(util.case_tensor((B, 3, res, res), 32))
+    pdrop = G.synthesis.b4.conv1.transformer.att_dp.p
+    assert pdrop > 0
+    seed = 1234
+    # replay of the engines' draws (on the GPU generator they use)
+    torch.manual_seed(seed)
+    inject = {"noise": {}, "dmask": {}}
+    idx = 0
+    for r in G.synthesis.block_resolutions:
+        for _ in range(1 if r == 4 else 2):
+            inject["noise"][idx] = torch.randn([B, 1, r, r], device="cuda").cpu()
+            m1 = torch.nn.functional.dropout(torch.ones([B, 1, r * r, 16], device="cuda"), pdrop, True)
+            m2 = torch.nn.functional.dropout(torch.ones([B, 1, 1, 16], device="cuda"), pdrop, True)
+            inject["dmask"][idx] = (m1 * m2).cpu()
+            idx += 1
+    assert any((m == 0).any() for m in inject["dmask"].values()), "the masks must really drop something"
+    wr = ws.clone().requires_grad_(True)
+    ref = ganformer.synthesis(sd, wr, sd["pos"], torch.ones(B, 16), res, noise_mode="random", inject=inject)
+    gref, = torch.autograd.grad((ref - tgt).square().mean(), [wr])
+    Gc = G.cuda().train()
+    try:
+        for engine, img_tol, g_tol in (("ops", 1e-4, 1e-3), ("tc", None, 2e-2)):
+            Gc.synthesis.engine = engine
+            w = ws.cuda().requires_grad_(True)
+            torch.manual_seed(seed)
+            img = Gc.synthesis(w, pos=Gc.pos, mask=torch.ones(B, 16, device="cuda"), noise_mode="random", return_att_maps=False)[0]
+            g, = torch.autograd.grad((img - tgt.cuda()).square().mean(), [w])
+            err = (img.detach().cpu() - ref.detach()).abs().max().item()
+            grel = ((g.cpu() - gref).norm() / gref.norm()).item()
+            print("train mode, engine %s: image max-abs %.3g (range %.3g), d(ws) rel-L2 %.3g" % (engine, err, ref.abs().max().item(), grel))
+            assert err < (img_tol if img_tol is not None else util.img_abs_tol(ref)) and grel < g_tol, (engine, err, grel)
+        # eval mode gives a different image (no dropout) -- the flag really reaches the kernels
+        Gc.eval()
+        torch.manual_seed(seed)
+        img_eval = Gc.synthesis(ws.cuda(), pos=Gc.pos, mask=torch.ones(B, 16, device="cuda"), noise_mode="random", return_att_maps=False)[0]
+        assert (img_eval.cpu() - ref.detach()).abs().max().item() > 1e-2
+    finally:
+        Gc.eval()
