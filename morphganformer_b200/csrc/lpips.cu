@@ -283,11 +283,13 @@ __global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bflo
 #pragma unroll
       for (int e = 0; e < 8; e++) mx[q][e] = -3.0e38f;
     float wsum = 0.f;
+    // pass 1 over the packed registers: |f|^2 of the four pixels and the running max; the four shuffle chains are interleaved (in-order issue:
+    // one pixel at a time left each chain's latency exposed).  Pass 2: the distance in its direct form (f inv - n1)^2, which stays accurate
+    // when the projection converges and the two terms nearly cancel, and g . f for the backward kernel.
+    float ss[4], inv[4], ds[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      // pass 1 over the packed registers: |f|^2 and the running max; pass 2: the distance in its direct form (f inv - n1)^2, which
-      // stays accurate when the projection converges and the two terms nearly cancel
-      float ss = 0.f;
+      ss[k] = 0.f;
 #pragma unroll
       for (int q = 0; q < VPL; q++) {
         const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w};
@@ -295,28 +297,41 @@ __global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bflo
         for (int e = 0; e < 4; e++) {
           const float2 v = unpack16(w4[e], f16);
           mx[q][e * 2] = fmaxf(mx[q][e * 2], v.x); mx[q][e * 2 + 1] = fmaxf(mx[q][e * 2 + 1], v.y);
-          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss);
+          ss[k] = fmaf(v.x, v.x, ss[k]); ss[k] = fmaf(v.y, v.y, ss[k]);
         }
       }
-      for (int o = lpp >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float rr = sqrtf(ss);
-      const float inv = 1.f / (rr + eps);
-      float dsum = 0.f;                      // sum_c lin (f inv - n1) f  =  inv sa - sb
+    }
+    for (int o = lpp >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      ss[k] = sqrtf(ss[k]);
+      inv[k] = 1.f / (ss[k] + eps);
+      ds[k] = 0.f;                          // sum_c lin (f inv - n1) f  =  inv sa - sb
 #pragma unroll
       for (int q = 0; q < VPL; q++) {
         const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w}, n4[4] = {nr[k][q].x, nr[k][q].y, nr[k][q].z, nr[k][q].w};
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const float2 v = unpack16(w4[e], f16), t = unpack16(n4[e], f16);
-          const float d0 = fmaf(v.x, inv, -t.x), d1 = fmaf(v.y, inv, -t.y);
+          const float d0 = fmaf(v.x, inv[k], -t.x), d1 = fmaf(v.y, inv[k], -t.y);
           const float l0 = lw[q][e * 2] * d0, l1 = lw[q][e * 2 + 1] * d1;
           wsum = fmaf(l0, d0, wsum); wsum = fmaf(l1, d1, wsum);
-          dsum = fmaf(l0, v.x, dsum); dsum = fmaf(l1, v.y, dsum);
+          ds[k] = fmaf(l0, v.x, ds[k]); ds[k] = fmaf(l1, v.y, ds[k]);
         }
       }
-      if (stats) {
-        for (int o = lpp >> 1; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-        if (ok && ll == 0) stats[((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)] = make_float2(rr, 2.f * dsum);
+    }
+    if (stats) {
+      for (int o = lpp >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) ds[k] += __shfl_xor_sync(0xffffffffu, ds[k], o);
+      }
+      if (ok && ll < 4) {                   // lane k of the group writes pixel k (select, not a dynamic index: keeps ss / ds in registers)
+        const float r_ = ll == 0 ? ss[0] : ll == 1 ? ss[1] : ll == 2 ? ss[2] : ss[3];
+        const float d_ = ll == 0 ? ds[0] : ll == 1 ? ds[1] : ll == 2 ? ds[2] : ds[3];
+        stats[((long long)b * H + 2 * yo + (ll >> 1)) * W + 2 * xo + (ll & 1)] = make_float2(r_, 2.f * d_);
       }
     }
     if (ok) {
@@ -341,11 +356,25 @@ __global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bflo
   }
 }
 
+// packed 16-bit pair helpers (storage type chosen at compile time): element-wise max, equality mask and "> 0" mask (0xFFFF per half)
+template <bool F16> __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+  if (F16) { const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b)); return *reinterpret_cast<const uint32_t*>(&r); }
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b)); return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <bool F16> __device__ __forceinline__ uint32_t eqmask2(uint32_t a, uint32_t b) {
+  if (F16) return __heq2_mask(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return __heq2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+template <bool F16> __device__ __forceinline__ uint32_t gtzmask2(uint32_t a) {
+  if (F16) return __hgt2_mask(*reinterpret_cast<__half2*>(&a), __float2half2_rn(0.f));
+  return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), __float2bfloat162_rn(0.f));
+}
+
 // Fused backward of an LPIPS tap that is followed by a max-pool (relu1_2, relu2_2, relu3_3, relu4_3):
 //   dx = ( route(dy through the 2x2 max-pool) + d(head)/dx ) * (x > 0)
 // replaces lpips_head<2> + maxpool2_bwd for those taps: x and n1 are read once, the head gradient never touches HBM
 // (7 tensor passes -> 3.25).  A group of LPP lanes owns one 2x2 window (4 pixels), channel vectors stay in registers.
-template <int VPL, bool f16>      // f16: compile-time forward dtype (the run-time flag cost a select per unpacked pair in an issue-bound kernel)
+template <int VPL, bool f16, bool STATS>      // f16: compile-time forward dtype (the run-time flag cost a select per unpacked pair in an issue-bound kernel)
 __global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1,
                                                                  const float* __restrict__ lin, const float* __restrict__ coef,
                                                                  const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
@@ -379,7 +408,7 @@ __global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kern
     // per pixel: inv = 1 / (|f| + eps) and k2 = (g . f) inv^2 / |f| with g = 2 lin (f inv - n1).  The two channel reductions come from the
     // forward kernel (stats) when it ran; otherwise one pass over the packed registers: |f|^2, sum lin f^2, sum lin f n1 and one shuffle round
     float inv[4], k2[4];
-    if (stats) {
+    if (STATS) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const float2 st = __ldg(stats + ((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1));
@@ -413,47 +442,40 @@ __global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_bwd_kern
     if (!ok) continue;
 #pragma unroll
     for (int q = 0; q < VPL; q++) {
-      float g[8];
+      // max-pool routing and ReLU masks on the PACKED 16-bit pairs (comparisons are exact in the storage type): sel[k][e] = 0xFFFF per half
+      // where pixel k is the FIRST maximum of the 2x2 window (torch's max_pool2d backward), pos[k][e] = 0xFFFF where x > 0.  Two elements per
+      // instruction and no fp32 copy of the four pixels (the scalar version spent 9 compare/select instructions per element on the arg-max
+      // alone and kept 32 more registers live)
+      uint32_t sel[4][4], pos[4][4], gsel[4];
       {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)b * Ho + yo) * Wo + xo) * C) + q * lpp + ll);
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; e++) { const float2 v = unpack_bf16(w4[e]); g[e * 2] = v.x; g[e * 2 + 1] = v.y; }
+        gsel[0] = u.x; gsel[1] = u.y; gsel[2] = u.z; gsel[3] = u.w;
       }
-      float xv[4][8];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w};
-#pragma unroll
-        for (int e = 0; e < 4; e++) { const float2 v = unpack16(w4[e], f16); xv[k][e * 2] = v.x; xv[k][e * 2 + 1] = v.y; }
-      }
-      int arg[8];
-#pragma unroll
-      for (int e = 0; e < 8; e++) {
-        int a = 0; float m = xv[0][e];
-#pragma unroll
-        for (int k = 1; k < 4; k++) if (xv[k][e] > m) { m = xv[k][e]; a = k; }
-        arg[e] = a;
+      for (int e = 0; e < 4; e++) {
+        const uint32_t w0 = (&xr[0][q].x)[e], w1 = (&xr[1][q].x)[e], w2 = (&xr[2][q].x)[e], w3 = (&xr[3][q].x)[e];
+        const uint32_t m = max2<f16>(max2<f16>(w0, w1), max2<f16>(w2, w3));
+        const uint32_t e0 = eqmask2<f16>(w0, m), e1 = eqmask2<f16>(w1, m), e2 = eqmask2<f16>(w2, m);
+        sel[0][e] = e0; sel[1][e] = e1 & ~e0; sel[2][e] = e2 & ~(e0 | e1); sel[3][e] = ~(e0 | e1 | e2);
+        pos[0][e] = gtzmask2<f16>(w0); pos[1][e] = gtzmask2<f16>(w1); pos[2][e] = gtzmask2<f16>(w2); pos[3][e] = gtzmask2<f16>(w3);
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const uint32_t n4[4] = {nr[k][q].x, nr[k][q].y, nr[k][q].z, nr[k][q].w};
-        float o[8];
+        const uint32_t w4[4] = {xr[k][q].x, xr[k][q].y, xr[k][q].z, xr[k][q].w}, n4[4] = {nr[k][q].x, nr[k][q].y, nr[k][q].z, nr[k][q].w};
+        uint32_t ow[4];
         // head gradient h = cf (2 lin (x inv - t) inv - k2 x) = x * (ca lin - ck) - t * (cb lin): two FMAs per element
         const float ca = 2.f * cf * inv[k] * inv[k], cb = 2.f * cf * inv[k], ck = cf * k2[k];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const float2 t = unpack16(n4[e], f16);
+          const float2 xx = unpack16(w4[e], f16), t = unpack16(n4[e], f16);
+          const float2 gr = unpack_bf16(gsel[e] & sel[k][e]);          // routed pooled gradient (bf16 pair) or zero
           const float l0 = lw[q][e * 2], l1 = lw[q][e * 2 + 1];
-          const float h0 = fmaf(xv[k][e * 2], fmaf(ca, l0, -ck), -(cb * l0) * t.x);
-          const float h1 = fmaf(xv[k][e * 2 + 1], fmaf(ca, l1, -ck), -(cb * l1) * t.y);
-          const float v0 = ((arg[e * 2] == k) ? g[e * 2] : 0.f) + h0, v1 = ((arg[e * 2 + 1] == k) ? g[e * 2 + 1] : 0.f) + h1;
-          o[e * 2] = xv[k][e * 2] > 0.f ? v0 : 0.f; o[e * 2 + 1] = xv[k][e * 2 + 1] > 0.f ? v1 : 0.f;
+          const float v0 = fmaf(xx.x, fmaf(ca, l0, -ck), fmaf(-(cb * l0), t.x, gr.x));
+          const float v1 = fmaf(xx.y, fmaf(ca, l1, -ck), fmaf(-(cb * l1), t.y, gr.y));
+          ow[e] = pack_bf16(v0, v1) & pos[k][e];                       // ReLU mask of the tapped activation
         }
-        uint4 u;
-        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
         const long long row = (((long long)b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C;
-        reinterpret_cast<uint4*>(dx + row)[q * lpp + ll] = u;
+        reinterpret_cast<uint4*>(dx + row)[q * lpp + ll] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
   }
@@ -568,7 +590,8 @@ extern "C" int mgf_lpips_tap_pool_bwd(const void* x, const void* n1, const float
   long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, B);
   cudaStream_t st = (cudaStream_t)stream;
-#define MGF_TPB(V, F) lpips_tap_pool_bwd_kernel<V, F><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, (const float2*)stats, H, W, C)
+#define MGF_TPB(V, F) do { if (stats) lpips_tap_pool_bwd_kernel<V, F, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, (const float2*)stats, H, W, C); \
+    else lpips_tap_pool_bwd_kernel<V, F, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, nullptr, H, W, C); } while (0)
   if (fwd_f16()) { if (vpl == 1) MGF_TPB(1, true); else MGF_TPB(2, true); }
   else { if (vpl == 1) MGF_TPB(1, false); else MGF_TPB(2, false); }
 #undef MGF_TPB

@@ -19,6 +19,7 @@ ap.add_argument("--res", type=int, default=1024)
 ap.add_argument("--halo-modes", default="1")
 ap.add_argument("--dump-conv", action="store_true")
 ap.add_argument("--top", type=int, default=45)
+ap.add_argument("--detail", default="", help="substring: also list every launch of the kernels whose name contains it, in launch order")
 args = ap.parse_args()
 
 B, R = args.batch, args.res
@@ -52,6 +53,9 @@ for mode in [int(m) for m in args.halo_modes.split(",")]:
         if ev.device_type == torch.autograd.DeviceType.CUDA:
             d = agg.setdefault(short(ev.name), [0, 0.0])
             d[0] += 1; d[1] += ev.device_time / 1000.0 if hasattr(ev, "device_time") else ev.cuda_time / 1000.0
+    if args.detail:
+        for ev in sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and args.detail in e.name), key=lambda e: e.time_range.start):
+            print("   launch %-60s %8.1f us" % (short(ev.name), ev.device_time if hasattr(ev, "device_time") else ev.cuda_time))
     tot = sum(v[1] for v in agg.values())
     print("=== halo mode %d: %d kernels, %.3f ms summed kernel time" % (mode, sum(v[0] for v in agg.values()), tot))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:args.top]:

@@ -234,12 +234,22 @@ def test_tc_engine_skip_and_orig_architectures(arch):
     assert torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item() > 0.998
 
 
-def test_tc_engine_refuses_training_mode():
+def test_tc_engine_refolds_weights_after_an_in_place_parameter_update():
+    """The engine folds the weights once; its public entry re-folds them when any parameter changed in place since the last call (an optimizer
+    step, load_state_dict), so G.synthesis(engine='tc') never serves stale weights."""
     G = util.build_G(32, 0, 1024, 32).cuda()
     G.synthesis.engine = "tc"
-    G.train()
-    with pytest.raises(NotImplementedError):
-        G.synthesis(util.case_tensor((1, 17, G.num_ws, 32), 1).cuda(), pos=G.pos, mask=torch.ones(1, 16, device="cuda"), noise_mode="const")
+    ws = util.case_tensor((1, 17, G.num_ws, 32), 1).cuda()
+    mask = torch.ones(1, 16, device="cuda")
+    a = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const")[0].clone()
+    with torch.no_grad():
+        G.synthesis.b16.conv1.weight.mul_(1.5)
+        G.synthesis.b32.torgb.biasAct.bias.add_(0.25)
+    b = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const")[0].clone()
+    G.synthesis.engine = "ops"
+    ref = G.synthesis(ws, pos=G.pos, mask=mask, noise_mode="const", return_att_maps=False)[0]
+    assert (a - b).abs().max().item() > 0.1
+    assert (b - ref).abs().max().item() < util.img_abs_tol(ref)
 
 
 def test_training_mode_on_both_engines_vs_oracle_with_injected_masks():
