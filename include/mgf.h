@@ -178,10 +178,17 @@ int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int
  * times their 1/(1-p) scales; multiplies the probabilities after the softmax (probs, when requested, are the dropped ones, as in the reference). */
 int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                  const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                 void* out, float* probs, const float* dmask, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
+                 void* out, float* probs, const float* dmask, const void* tabK, const void* tabV,
+                 int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
 int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                  const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                 void* dX, float* dVM, float* R, const float* dmask, int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
+                 void* dX, float* dVM, float* R, const float* dmask, const void* tabK, const void* tabV,
+                 int B, int64_t HW, int C, int64_t noise_bstride, void* stream);
+/* tabK / tabV (optional): the 16-bit coefficient tables of Kf / VM in the kernels' shared-memory layout, built once by mgf_attn_tables
+ * (Kf: when the weights are folded; VM [B,16,C]: per step) instead of by every CTA of every launch.  mgf_attn_table_bytes(0 | 1, C) = bytes
+ * of tabK / of tabV per sample.  The tables depend on the forward dtype in effect when they were built. */
+int64_t mgf_attn_table_bytes(int which, int C);
+int mgf_attn_tables(const float* Kf, const float* VM, void* tabK, void* tabV, int B, int C, void* stream);
 
 /* ---- mapping network z -> ws and its backward wrt z (mapping.cu): training/networks.py MappingNetwork.forward :894-942 with the
  * GANformer-default configuration (16 local + 1 global latents x 32, 4 resnet blocks, latent self-attention, positional maps).

@@ -54,6 +54,7 @@ struct AttnMP {
   const float* noise; const float* nstr; const float* bias; float gain, alpha;
   void* out; float* probs;
   const __nv_bfloat16* dz; __nv_bfloat16* dX; float* dVM; float* R;
+  const void* tabK; const void* tabV;   // pre-built coefficient tables (mgf_attn_tables): shared-memory images, copied instead of rebuilt per CTA
   const float* dmask;          // attention dropout (training mode): [B,HW,16] fp32 keep-mask * scale, multiplies the probabilities after the softmax (nullptr: eval)
   long long HW; int C; int pix_per_cta; long long nbs;      // nbs: elements between per-sample noise planes (0 = shared plane)
 };
@@ -93,6 +94,35 @@ __device__ __forceinline__ void fill_permtable(uint2* dst, const float* __restri
     u.x = pk<F16>(a, b);
     u.y = pk<F16>(c, d);
     dst[i] = u;
+  }
+}
+
+// ---- pre-built tables.  Building the 16-bit coefficient tables from the fp32 constants cost every CTA of every launch ~40 us (strided
+// scalar loads + conversions: the whole run time of the 4^2 .. 16^2 layers and a third of the 64^2 ones).  mgf_attn_tables writes the
+// same shared-memory images to global memory once -- Kf tables when the weights are folded, VM tables per step on the side stream --
+// and the kernels copy them with 16-byte vectors.
+//   tabK: [Khi rows][Klo rows][Kp perm (bf16)]      tabV (per sample): [Vr rows (bf16)][Vp perm (fp16)]
+__host__ __device__ inline size_t rows_bytes(int C) { return (size_t)NT * krow(C) * 2; }
+__host__ __device__ inline size_t perm_bytes(int C) { return (size_t)(C / 8) * 32 * 8; }
+__host__ __device__ inline size_t tabk_bytes(int C) { return 2 * rows_bytes(C) + perm_bytes(C); }
+__host__ __device__ inline size_t tabv_bytes(int C) { return rows_bytes(C) + perm_bytes(C); }
+__device__ __forceinline__ void copy_table(void* dst, const void* src, size_t bytes) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int i = threadIdx.x; i < (int)(bytes >> 4); i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(256) attn_tables_kernel(const float* __restrict__ Kf, const float* __restrict__ VM, unsigned char* tabK, unsigned char* tabV, int C) {
+  // block 0 .. B-1: the VM tables of sample blockIdx.x (if VM); the last block: the Kf tables (if Kf).  The fill_* helpers index their
+  // destination exactly as they index shared memory, so the images are identical to what the kernels used to build in place.
+  if (VM && (int)blockIdx.x < (int)gridDim.x - (Kf ? 1 : 0)) {
+    unsigned char* tv = tabV + (size_t)blockIdx.x * tabv_bytes(C);
+    const float* vm = VM + (size_t)blockIdx.x * NT * C;
+    fill_rowtable<false>(reinterpret_cast<uint16_t*>(tv), nullptr, vm, C);
+    fill_permtable<true>(reinterpret_cast<uint2*>(tv + rows_bytes(C)), vm, C);
+  } else if (Kf) {
+    fill_rowtable<F16>(reinterpret_cast<uint16_t*>(tabK), reinterpret_cast<uint16_t*>(tabK + rows_bytes(C)), Kf, C);
+    fill_permtable<false>(reinterpret_cast<uint2*>(tabK + 2 * rows_bytes(C)), Kf, C);
   }
 }
 
@@ -159,8 +189,9 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(AttnMP p) {
   float* sm1 = reinterpret_cast<float*>(sVp + (C / 8) * 32);
   float* sb = sm1 + C;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  fill_rowtable<F16>(sKhi, sKlo, p.Kf, C);
-  fill_permtable<true>(sVp, p.VM + (long long)b * NT * C, C);
+  if (p.tabK) copy_table(sKhi, p.tabK, 2 * rows_bytes(C)); else fill_rowtable<F16>(sKhi, sKlo, p.Kf, C);
+  if (p.tabV) copy_table(sVp, reinterpret_cast<const unsigned char*>(p.tabV) + (size_t)b * tabv_bytes(C) + rows_bytes(C), perm_bytes(C));
+  else fill_permtable<true>(sVp, p.VM + (long long)b * NT * C, C);
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sb[i] = p.bias ? p.bias[i] : 0.f; sm1[i] = 1.f + p.bm[i]; }
   __syncthreads();
   const float ns = (p.noise && p.nstr) ? *p.nstr : 0.f;
@@ -253,10 +284,18 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
   uint16_t* sD = sP + 128 * SPS;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const float* VMb = p.VM + (long long)b * NT * C;
-  fill_rowtable<F16>(sKhi, sKlo, p.Kf, C);
-  fill_rowtable<false>(sVr, nullptr, VMb, C);
-  fill_permtable<true>(sVp, VMb, C);
-  fill_permtable<false>(sKp, p.Kf, C);
+  if (p.tabK) {
+    copy_table(sKhi, p.tabK, 2 * rows_bytes(C));
+    copy_table(sKp, reinterpret_cast<const unsigned char*>(p.tabK) + 2 * rows_bytes(C), perm_bytes(C));
+  } else {
+    fill_rowtable<F16>(sKhi, sKlo, p.Kf, C);
+    fill_permtable<false>(sKp, p.Kf, C);
+  }
+  if (p.tabV) copy_table(sVr, reinterpret_cast<const unsigned char*>(p.tabV) + (size_t)b * tabv_bytes(C), tabv_bytes(C));      // sVr | sVp are contiguous, like the image
+  else {
+    fill_rowtable<false>(sVr, nullptr, VMb, C);
+    fill_permtable<true>(sVp, VMb, C);
+  }
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sb[i] = p.bias ? p.bias[i] : 0.f; sm1[i] = 1.f + p.bm[i]; sR[i] = 0.f; }
   __syncthreads();
   const float ns = (p.noise && p.nstr) ? *p.nstr : 0.f;
@@ -507,12 +546,13 @@ using namespace mgf;
 
 extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                             const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                            void* out, float* probs, const float* dmask, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
+                            void* out, float* probs, const float* dmask, const void* tabK, const void* tabV,
+                            int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
   if (!X || !Kf || !Sc || !maskbias || !VM || !bm || !out) MGF_FAIL(MGF_E_BADARG, "attn_fwd: null tensor");
   if (B <= 0 || HW <= 0) MGF_FAIL(MGF_E_SHAPE, "attn_fwd: empty batch or grid");
   if (int e = check_c(C, "attn_fwd")) return e;
   AttnMP p{}; p.X = X; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm; p.noise = noise; p.nstr = nstr; p.bias = bias;
-  p.gain = gain; p.alpha = alpha; p.out = out; p.probs = probs; p.dmask = dmask; p.HW = HW; p.C = C; p.nbs = noise_bstride;
+  p.gain = gain; p.alpha = alpha; p.out = out; p.probs = probs; p.dmask = dmask; p.tabK = tabK; p.tabV = tabV; p.HW = HW; p.C = C; p.nbs = noise_bstride;
   p.pix_per_cta = pix_per_cta(HW, B, 2);      // one wave of 2 CTAs per SM
   dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
   const int rc = fwd_f16() ? launch_fwd<true>(p, grid, fwd_smem(C), (cudaStream_t)stream) : launch_fwd<false>(p, grid, fwd_smem(C), (cudaStream_t)stream);
@@ -523,16 +563,34 @@ extern "C" int mgf_attn_fwd(const void* X, const float* Kf, const float* Sc, con
 
 extern "C" int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc, const float* maskbias, const float* VM, const float* bm,
                             const float* noise, const float* nstr, const float* bias, float gain, float alpha,
-                            void* dX, float* dVM, float* R, const float* dmask, int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
+                            void* dX, float* dVM, float* R, const float* dmask, const void* tabK, const void* tabV,
+                            int B, int64_t HW, int C, int64_t noise_bstride, void* stream) {
   if (!X || !dz || !Kf || !Sc || !maskbias || !VM || !bm || !dX || !dVM) MGF_FAIL(MGF_E_BADARG, "attn_bwd: null tensor");
   if (B <= 0 || HW <= 0) MGF_FAIL(MGF_E_SHAPE, "attn_bwd: empty batch or grid");
   if (int e = check_c(C, "attn_bwd")) return e;
   AttnMP p{}; p.X = X; p.dz = (const __nv_bfloat16*)dz; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm;
-  p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.dmask = dmask; p.HW = HW; p.C = C; p.nbs = noise_bstride;
+  p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.dmask = dmask; p.tabK = tabK; p.tabV = tabV; p.HW = HW; p.C = C; p.nbs = noise_bstride;
   p.pix_per_cta = pix_per_cta(HW, B, 1);      // one wave of 1 CTA per SM
   dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
   const int rc = fwd_f16() ? launch_bwd<true>(p, grid, bwd_smem(C), (cudaStream_t)stream) : launch_bwd<false>(p, grid, bwd_smem(C), (cudaStream_t)stream);
   if (rc) MGF_FAIL(MGF_E_SHAPE, "attn_bwd: unsupported C=%d", C);
   MGF_CHECK_LAUNCH("attn_bwd");
+  return 0;
+}
+
+extern "C" int64_t mgf_attn_table_bytes(int which, int C) {
+  if (C < 32 || C % 32) return -1;
+  return (int64_t)(which == 0 ? mgf::tabk_bytes(C) : mgf::tabv_bytes(C));
+}
+
+extern "C" int mgf_attn_tables(const float* Kf, const float* VM, void* tabK, void* tabV, int B, int C, void* stream) {
+  if ((!Kf && !VM) || (Kf && !tabK) || (VM && !tabV)) MGF_FAIL(MGF_E_BADARG, "attn_tables: null tensor");
+  if (int e = check_c(C, "attn_tables")) return e;
+  if (VM && B <= 0) MGF_FAIL(MGF_E_SHAPE, "attn_tables: empty batch");
+  if (((uintptr_t)tabK | (uintptr_t)tabV) & 15) MGF_FAIL(MGF_E_ALIGN, "attn_tables: tables must be 16-byte aligned");
+  const unsigned grid = (VM ? B : 0) + (Kf ? 1 : 0);
+  if (fwd_f16()) attn_tables_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(Kf, VM, (unsigned char*)tabK, (unsigned char*)tabV, C);
+  else attn_tables_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(Kf, VM, (unsigned char*)tabK, (unsigned char*)tabV, C);
+  MGF_CHECK_LAUNCH("attn_tables");
   return 0;
 }

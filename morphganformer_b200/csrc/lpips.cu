@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* __
 // pixels of every 2x2 window AND y = max over the window, in one pass over f (the separate head + pool kernels read f twice).
 // Same lane-group-per-window layout as the backward kernel below.
 template <int VPL, bool f16>
-__global__ void __launch_bounds__(256) lpips_tap_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1, const float* __restrict__ lin,
+__global__ void __launch_bounds__(256, VPL == 1 ? 3 : 1) lpips_tap_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1, const float* __restrict__ lin,
                                                                  __nv_bfloat16* __restrict__ y, float* val, float2* __restrict__ stats, int H, int W, int C) {
   // stats (optional) [B,H,W] = (|f|, g . f) per pixel with g = 2 lin (f inv - n1): the two channel reductions the backward kernel needs; they cost
   // this pass one FFMA per element and 8 bytes per pixel, and take the whole first pass (3 FMAs per element + shuffles) out of the backward kernel

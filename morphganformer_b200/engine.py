@@ -261,6 +261,7 @@ class SynthesisEngine:
             L.WVMt = L.WVM.t().contiguous()                                               # [32, C]
             L.bm = (t.modulation.bias.detach().float() * float(t.modulation.b_gain)).contiguous()
             L.att_dp = float(t.att_dp.p)
+            L.tabK, L.tabK_dtype = None, None
         return L
 
     # -------------------------------------------------------------------------------------------- buffers
@@ -345,6 +346,16 @@ class SynthesisEngine:
             comps = ws[:, :-1, L.idx]                           # [B,16,32] strided
             _lib.check(_L().mgf_small_gemm(_p(comps), comps.stride(0), comps.stride(1), _p(L.WVM), _p(L.bVM), _p(VM),
                                            16 * L.O, L.O, B, 16, L.O, comps.shape[2], 0, _s(self.dev)), "mgf_small_gemm")
+            # 16-bit coefficient tables of VM (per step, here on the side stream) and of Kf (once per fold and forward dtype) in the attention
+            # kernels' shared-memory layout: every CTA copies them instead of rebuilding them from the fp32 constants
+            fdt = _lib.forward_torch_dtype()
+            tabV = self._buf(st, f"tabV{L.idx}", (B * int(_L().mgf_attn_table_bytes(1, L.O)),), torch.uint8)
+            need_k = L.tabK is None or L.tabK_dtype != fdt
+            if need_k:
+                L.tabK = torch.empty(int(_L().mgf_attn_table_bytes(0, L.O)), dtype=torch.uint8, device=self.dev)
+                L.tabK_dtype = fdt
+            _lib.check(_L().mgf_attn_tables(_p(L.Kf) if need_k else None, _p(VM), _p(L.tabK) if need_k else None, _p(tabV), B, L.O, _s(self.dev)),
+                       "mgf_attn_tables")
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
         st[f"prep{L.idx}"] = (s, d, Wf, VM, ev)
@@ -404,7 +415,8 @@ class SynthesisEngine:
                 probs = torch.empty(B, H * Wd, 16, device=self.dev)
                 st["probs"].append(probs)
             _lib.check(_L().mgf_attn_fwd(_p(y), _p(L.Kf), _p(L.Sc), _p(maskbias), _p(VM), _p(L.bm), _p(noise), _p(nstr), _p(L.bias),
-                                         L.gain, LRELU_ALPHA, _p(z), _p(probs), _p(dmask), B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_fwd")
+                                         L.gain, LRELU_ALPHA, _p(z), _p(probs), _p(dmask), _p(L.tabK), _p(st[f"tabV{L.idx}"]),
+                                         B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_fwd")
         elif L.superpix:
             z = self._buf(st, f"z{L.idx}", (B, H, Wd, L.O), fwd=True)
             bias2 = L.bias.repeat(2).contiguous() if L.bias is not None else None
@@ -585,8 +597,8 @@ class SynthesisEngine:
         dVM = self._zbuf(st, f"dVM{L.idx}", (B, 16, L.O))
         R = self._zbuf(st, f"R{L.idx}", (B, L.O))
         _lib.check(_L().mgf_attn_bwd(_p(y), _p(dz), _p(L.Kf), _p(L.Sc), _p(st["maskbias"]), _p(st[f"VM{L.idx}"]), _p(L.bm), _p(noise), _p(nstr),
-                                     _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), _p(st.get(f"dmask{L.idx}")), B, H * Wd, L.O, nbs, _s(self.dev)),
-                   "mgf_attn_bwd")
+                                     _p(L.bias), L.gain, LRELU_ALPHA, _p(dy), _p(dVM), _p(R), _p(st.get(f"dmask{L.idx}")), _p(L.tabK), _p(st[f"tabV{L.idx}"]),
+                                     B, H * Wd, L.O, nbs, _s(self.dev)), "mgf_attn_bwd")
         dcomp = dws[:, :-1, L.idx]                                 # [B,16,32] strided, accumulate
         self._on_side(lambda: _lib.check(_L().mgf_small_gemm(_p(dVM), 16 * L.O, L.O, _p(L.WVMt), None, _p(dcomp), dcomp.stride(0), dcomp.stride(1),
                                                              B, 16, dcomp.shape[2], L.O, 1, _s(self.dev)), "mgf_small_gemm"))

@@ -11,8 +11,8 @@ for (B, HW, C) in [(8, 16384, 256), (8, 4096, 512), (8, 1024, 512)]:
     VM = torch.randn(B, 16, C, device="cuda") * 0.1; bm = torch.zeros(C, device="cuda"); noise = torch.randn(HW, device="cuda"); ns = torch.tensor([0.1], device="cuda")
     bias = torch.zeros(C, device="cuda"); out = torch.empty_like(X); dX = torch.empty_like(X); dVM = torch.zeros_like(VM); R = torch.zeros(B, C, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
-    def fwd(): _lib.check(L.mgf_attn_fwd(p(X), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(out), None, None, B, HW, C, 0, s))
-    def bwd(): _lib.check(L.mgf_attn_bwd(p(X), p(dz), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(dX), p(dVM), p(R), None, B, HW, C, 0, s))
+    def fwd(): _lib.check(L.mgf_attn_fwd(p(X), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(out), None, None, None, None, B, HW, C, 0, s))
+    def bwd(): _lib.check(L.mgf_attn_bwd(p(X), p(dz), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(dX), p(dVM), p(R), None, None, None, B, HW, C, 0, s))
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         ts = []
         for i in range(7):

@@ -60,9 +60,9 @@ def test_entry_points_reject_bad_arguments_on_the_host():
         ("mgf_mapping_fwd", (None, None, None, None, 1, 11, None), -1, b"null"),
         ("mgf_mapping_fwd", (P, P, P, P, 0, 11, None), -3, b"empty"),
         ("mgf_mapping_bwd", (P, P, P, None, P, 1, 11, None), -1, b"null"),
-        ("mgf_attn_fwd", (None,) * 9 + (1.0, 0.2, None, None, None, 1, 16, 32, 0, None), -1, b"null"),
-        ("mgf_attn_fwd", (P,) * 9 + (1.0, 0.2, P, None, None, 1, 16, 48, 0, None), -3, b"C=48"),
-        ("mgf_attn_bwd", (P,) * 10 + (1.0, 0.2, P, P, P, None, 0, 16, 32, 0, None), -3, b"empty"),
+        ("mgf_attn_fwd", (None,) * 9 + (1.0, 0.2, None, None, None, None, None, 1, 16, 32, 0, None), -1, b"null"),
+        ("mgf_attn_fwd", (P,) * 9 + (1.0, 0.2, P, None, None, None, None, 1, 16, 48, 0, None), -3, b"C=48"),
+        ("mgf_attn_bwd", (P,) * 10 + (1.0, 0.2, P, P, P, None, None, None, 0, 16, 32, 0, None), -3, b"empty"),
         ("mgf_lpips_head", (1, None, None, None, None, None, None, 0, 1, 16, 64, None), -1, b"null"),
         ("mgf_lpips_head", (1, P, P, P, None, None, P, 0, 1, 16, 96, None), -3, b"C=96"),
         ("mgf_upfir2_add", (P, None, P, (ctypes.c_float * 4)(1, 3, 3, 1), 1.0, 1, 4, 4, 24, None), -3, b"power of two"),

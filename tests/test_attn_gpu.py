@@ -25,9 +25,9 @@ def _p(t):
 
 
 @pytest.mark.parametrize("fwd", ["fp16", "bf16"])
-@pytest.mark.parametrize("dropout", [False, True])
+@pytest.mark.parametrize("dropout,tables", [(False, False), (True, False), (False, True), (True, True)])
 @pytest.mark.parametrize("B,HW,C", [(2, 16, 32), (2, 100, 64), (3, 1032, 128), (2, 4096, 256), (1, 500, 384), (2, 1000, 512), (8, 16, 512)])
-def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd, dropout):
+def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd, dropout, tables):
     L = _lib.lib()
     _lib.set_forward_dtype(fwd)
     try:
@@ -44,10 +44,15 @@ def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd, dropout):
             keep = lambda *sh: (torch.rand(*sh, device="cuda", generator=g) >= 0.06).float() / 0.94
             dmask = (keep(B, HW, 16) * keep(B, 1, 16)).contiguous()
         s = torch.cuda.current_stream().cuda_stream
+        tabK = tabV = None
+        if tables:                 # pre-built shared-memory images of the coefficient tables (what the engine passes)
+            tabK = torch.empty(L.mgf_attn_table_bytes(0, C), dtype=torch.uint8, device="cuda")
+            tabV = torch.empty(B * L.mgf_attn_table_bytes(1, C), dtype=torch.uint8, device="cuda")
+            _lib.check(L.mgf_attn_tables(_p(Kf), _p(VM), _p(tabK), _p(tabV), B, C, s), "tables")
         out = torch.empty_like(X16); probs = torch.empty(B, HW, 16, device="cuda")
-        _lib.check(L.mgf_attn_fwd(_p(X16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(out), _p(probs), _p(dmask), B, HW, C, 0, s), "fwd")
+        _lib.check(L.mgf_attn_fwd(_p(X16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(out), _p(probs), _p(dmask), _p(tabK), _p(tabV), B, HW, C, 0, s), "fwd")
         dX = torch.empty(B, HW, C, device="cuda", dtype=torch.bfloat16); dVM = torch.zeros(B, 16, C, device="cuda"); R = torch.zeros(B, C, device="cuda")
-        _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(dX), _p(dVM), _p(R), _p(dmask), B, HW, C, 0, s), "bwd")
+        _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), gain, alpha, _p(dX), _p(dVM), _p(R), _p(dmask), _p(tabK), _p(tabV), B, HW, C, 0, s), "bwd")
         torch.cuda.synchronize()
         Xr = X16.float().requires_grad_(True); VMr = VM.clone().requires_grad_(True)
         ref, A = _ref(Xr, Kf, Sc, mb, VMr, bm, noise, ns, bias, gain, alpha, dmask)
@@ -71,7 +76,7 @@ def test_attn_rejects_bad_shapes():
     L = _lib.lib()
     x = torch.zeros(1, 16, 48, device="cuda", dtype=torch.bfloat16)
     f = torch.zeros(16, 48, device="cuda")
-    rc = L.mgf_attn_fwd(_p(x), _p(f), _p(f), _p(f), _p(f), _p(f), None, None, None, 1.0, 0.2, _p(x), None, None, 1, 16, 48, 0, 0)
+    rc = L.mgf_attn_fwd(_p(x), _p(f), _p(f), _p(f), _p(f), _p(f), None, None, None, 1.0, 0.2, _p(x), None, None, None, None, 1, 16, 48, 0, 0)
     assert rc != 0 and b"C=48" in L.mgf_last_error()
 
 
@@ -108,10 +113,10 @@ def test_attn_kernel_vs_oracle_transformer_layer(res, C, B):
     X16 = X.half().cuda()
     out = torch.empty_like(X16); probs = torch.empty(B, HW, 16, device="cuda")
     # no noise, no bias, linear tail (alpha = 1, gain = 1): the pure attention layer
-    _lib.check(L.mgf_attn_fwd(_p(X16), _p(Lr.Kf), _p(Lr.Sc), _p(mb), _p(VM), _p(Lr.bm), None, None, None, 1.0, 1.0, _p(out), _p(probs), None, B, HW, C, 0, s), "fwd")
+    _lib.check(L.mgf_attn_fwd(_p(X16), _p(Lr.Kf), _p(Lr.Sc), _p(mb), _p(VM), _p(Lr.bm), None, None, None, 1.0, 1.0, _p(out), _p(probs), None, None, None, B, HW, C, 0, s), "fwd")
     dX = torch.empty(B, HW, C, device="cuda", dtype=torch.bfloat16); dVM = torch.zeros(B, 16, C, device="cuda"); R = torch.zeros(B, C, device="cuda")
     dz16 = dz.bfloat16().cuda()
-    _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Lr.Kf), _p(Lr.Sc), _p(mb), _p(VM), _p(Lr.bm), None, None, None, 1.0, 1.0, _p(dX), _p(dVM), _p(R), None, B, HW, C, 0, s), "bwd")
+    _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Lr.Kf), _p(Lr.Sc), _p(mb), _p(VM), _p(Lr.bm), None, None, None, 1.0, 1.0, _p(dX), _p(dVM), _p(R), None, None, None, B, HW, C, 0, s), "bwd")
     torch.cuda.synchronize()
     assert (probs.cpu() - probs_ref.detach().reshape(B, HW, 16)).abs().max().item() < 2e-3
     scale = ref.detach().abs().max().item()
