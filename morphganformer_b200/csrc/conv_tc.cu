@@ -127,6 +127,40 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- CTA-pair (cta_group::2) wrappers: two SMs of one TPC execute one M = 256 MMA, each supplying its own 128 rows of A and HALF of B
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address: "the same location in CTA 0 of the pair"
+__device__ __forceinline__ void tma_load_4d_2cta(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  // executed by both CTAs: the data lands in the issuing CTA's shared memory, the transaction bytes are counted on CTA 0's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs once the MMAs issued so far have completed
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {    // arrive on the barrier at the same offset in CTA 0 of the pair
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -187,7 +221,8 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile, int 
 template <int BN, int NSTG, int GW32>
 __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& t, int x, int y, int b, bool valid, uint32_t tacc, int lane,
                                               float nz0, float nz1, float nz2, float nz3,
-                                              uint8_t* stg, int group, int r, float* racc, uint64_t* xbar, uint32_t xphase, uint64_t* tempty_bar) {
+                                              uint8_t* stg, int group, int r, float* racc, uint64_t* xbar, uint32_t xphase, uint64_t* tempty_bar,
+                                              bool tempty_on_cta0 = false) {
       // A tile may span several output phases (BN > Cout, e.g. the four parities of an up-convolution in one 128- or 256-column tile, so
       // the activation tiles are fetched once for all of them): phase and channel offset are per 32-column chunk; a staged group of
       // GW32 * 32 columns never straddles two phases (host check).  nz0..nz3: noise of this thread's pixel in the tile's phases
@@ -204,7 +239,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         tmem_ld32(tacc + (uint32_t)(c * 32), raw);
         if (c == BN / 32 - 1) {          // the accumulator now lives in registers: hand the TMEM stage back to the MMA issuer at once
           tc_fence_before();
-          mbar_arrive(tempty_bar);
+          if (tempty_on_cta0) mbar_arrive_cta0(tempty_bar); else mbar_arrive(tempty_bar);
         }
         // rows outside the grid are never stored (the TMA store clips them); their accumulators may hold anything (NaN included), so they are
         // zeroed before they can reach the column reductions -- a rarely taken branch instead of 32 selects per chunk for every thread
@@ -519,6 +554,168 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 
 
 // ================================================================================================================
+// CTA-pair variant (tcgen05.mma.cta_group::2) for the wide tiles (BN = 128 / 256).  Two CTAs of a cluster -- two SMs of one TPC -- work on
+// two neighbouring 128-pixel tiles of the same N block: one M = 256 MMA per k-step, issued by CTA 0, reads each CTA's own A tile and HALF
+// of the weight tile from each CTA's shared memory, and writes each CTA's 128 accumulator rows into its own TMEM.  Per SM the weight tile
+// is filled and read at half the rate: with the 128 B/clk shared-memory port model of DESIGN.md section 4, BN = 128 goes from 174 to
+// 130 B/clk per MMA-cycle (port limit 74 % -> ~98 %) and BN = 256 from 130 to 87.
+// Protocol: every CTA's TMA producer fills its own stage and counts the bytes on CTA 0's `full` barrier (cta_group::2 loads); CTA 0's MMA warp
+// frees a stage / publishes an accumulator in BOTH CTAs with multicast commits; the epilogue groups of both CTAs drain their own TMEM
+// and arrive on CTA 0's `tempty` barrier (256 arrivals).
+template <int BN, int BK>
+struct Cfg2 {
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the weight tile
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NSTG = 1;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
+  static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
+  static constexpr int SMEM = STAGES * STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + BAR_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ TileCoord decode_pair(const Params& p, int pt, int rank, int BN) {
+  // pair tiles are ordered like tiles (N block fastest); a pair = M tiles 2 mp and 2 mp + 1 of one N block.  An M index past the end decodes to a
+  // sample index >= NB: TMA zero-fills its loads and clips its stores, and every row is invalid
+  TileCoord t;
+  const int nb = pt % p.n_tiles; int m = 2 * (pt / p.n_tiles) + rank;
+  t.n0 = nb * BN;
+  t.x0 = (m % p.tilesW) * p.TW; m /= p.tilesW;
+  t.y0 = (m % p.tilesH) * p.TH; m /= p.tilesH;
+  t.b0 = m * p.TB;
+  return t;
+}
+
+template <int BN, int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant__ Params p) {
+  using C = Cfg2<BN, BK>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stg_base = smem + C::STAGES * C::STAGE;
+  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * C::NSTG * STG_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(racc_base + 2 * RACC);     // used in CTA 0 only
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;                                            // used in CTA 0 only
+  uint64_t* xbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync();                              // barriers of both CTAs initialised and visible before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = p.kchunks * p.ntaps;
+  const int pair_tiles = p.total_tiles;        // host: number of PAIR tiles
+
+  if (warp == 8) {     // ------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0; uint32_t phase = 0;
+    for (int pt = cid; pt < pair_tiles; pt += nclusters) {
+      const TileCoord t = decode_pair(p, pt, rank, BN);
+      const TileCoord t0 = decode_pair(p, pt, 0, BN);
+      const int wbase = p.per_sample ? t0.b0 * p.w_T : 0;      // both tiles of a pair read the weights of CTA 0's tile (host: same sample)
+      for (int kc = 0; kc < p.kchunks; kc++) {
+        for (int tp = 0; tp < p.ntaps; tp++) {
+          const Tap tap = p.taps[tp];
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * p.tx_bytes);
+            uint8_t* sa = smem + stage * C::STAGE;
+            tma_load_4d_2cta(&p.amap[tap.amap], &full[stage], sa, kc * BK, t.x0 + tap.dx, t.y0 + tap.dy, t.b0);
+            tma_load_3d_2cta(&p.bmap, &full[stage], sa + C::A_BYTES, kc * BK, t.n0 + rank * (BN / 2), wbase + tap.wz);
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {   // ------------------------------------------------- MMA issuer (CTA 0 only)
+    if (rank == 0) {
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      for (int pt = cid; pt < pair_tiles; pt += nclusters) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int it = 0; it < iters; it++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+            const uint64_t adesc = make_desc<BK>(sa), bdesc = make_desc<BK>(sa + C::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) tc_mma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+            tc_commit_2cta(&empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) tc_commit_2cta(&tfull[as]);
+        __syncwarp();
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {                 // ------------------------------------------------ epilogue (both CTAs): group g drains accumulator stage g
+    const int as = warp >> 2; uint32_t aphase = 0;
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const int tx = r % p.TW, ty = (r / p.TW) % p.TH, tb = r / (p.TW * p.TH);
+    const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
+    float* racc = racc_base + as * RACC;
+    int red_key = -1;
+    if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
+    for (int pt = cid + as * nclusters; pt < pair_tiles; pt += 2 * nclusters) {
+      const TileCoord t = decode_pair(p, pt, rank, BN);
+      const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
+      const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
+      if (p.reduce_out) {
+        const int key = t.b0 * p.n_tiles + t.n0 / BN;
+        if (key != red_key) {
+          if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
+          red_key = key;
+        }
+      }
+      uint8_t* stg = stg_base + as * C::NSTG * STG_BYTES;
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.noise && valid) {
+        const int ph0 = t.n0 / p.Cout;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int ph = ph0 + k;
+          if (k == 0 || (k * p.Cout < BN && ph < 4))
+            nz[k] = __ldg(p.noise + (long long)b * p.noise_bstride + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+        }
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      epilogue_tile<BN, C::NSTG, 2>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz[0], nz[1], nz[2], nz[3],
+                                    stg, as, r, racc, &xbar[0], 0u, &tempty[as], rank != 0);
+      aphase ^= 1;
+    }
+    if (p.reduce_out && red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
+    if (r == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync();                              // neither CTA may leave (or free its TMEM) while the pair's MMAs / remote arrivals are in flight
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ================================================================================================================
 // Halo variant for narrow layers (C = 64 or 128, 3x3 taps, large images).  The generic kernel above re-loads a shifted A tile
 // from L2 for each of the 9 taps and re-fetches the weight tile for every output tile; for C <= 128 that L2->shared-memory
 // traffic, not HBM or the tensor pipe, is the limiter (profiles/r01_conv_tc_ncu_full.md).  Here
@@ -803,6 +1000,20 @@ static int launch(const Params& p, int grid, cudaStream_t st) {
   return 0;
 }
 
+template <int BN, int BK>
+static int launch2(const Params& p, int grid, cudaStream_t st) {
+  using C = Cfg2<BN, BK>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc(2cta): cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  conv_tc2_kernel<BN, BK><<<grid, 320, C::SMEM, st>>>(p);      // __cluster_dims__(2,1,1): grid is even
+  MGF_CHECK_LAUNCH("conv_tc(2cta)");
+  return 0;
+}
+
 template <int BN, int KC, int BK, int NSTG_>
 static int launch_halo(const Params& p, int grid, cudaStream_t st) {
   using C = HaloCfg<BN, KC, BK, NSTG_>;
@@ -819,17 +1030,19 @@ static int launch_halo(const Params& p, int grid, cudaStream_t st) {
 
 static bool g_halo_enabled = true;
 static bool g_halo_phases = false;  // halo kernel also for multi-phase (up-convolution) launches; default: those run as one wide tile per pixel block
+static bool g_cg2_enabled = true;     // CTA-pair (cta_group::2) kernel for the wide tiles (A/B switch: mgf_conv_tc_set_halo bit 4 disables it)
 static int g_halo_nstg = 1;        // epilogue staging tiles per group in the halo kernel (A/B switch: mgf_conv_tc_set_halo(1 | 2 << 1))
 
 }  // namespace tc
 }  // namespace mgf
 
 extern "C" int mgf_conv_tc_set_halo(int mode) {
-  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2); bit 3: halo kernel for multi-phase launches too
+  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2); bit 3: halo kernel for multi-phase launches too; bit 4: disable the CTA-pair kernel
   mgf::tc::g_halo_enabled = (mode & 1) != 0;
   const int n = (mode >> 1) & 3;
   mgf::tc::g_halo_nstg = (n == 2) ? 2 : 1;
   mgf::tc::g_halo_phases = (mode & 8) != 0;
+  mgf::tc::g_cg2_enabled = (mode & 16) == 0;
   return 0;
 }
 
@@ -1005,6 +1218,26 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   if (int e = encode_x_map(p, d, BN, TW, TH, TB, p.rows)) return e;
   int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
+  // CTA-pair kernel: wide full tiles, both tiles of a pair under the same weights (shared weights, or an even number of tiles per sample)
+  const long long mtiles = (long long)p.tilesW * p.tilesH * p.tilesB;
+  if (g_cg2_enabled && BN >= 128 && !g32 && !ph_taps && p.rows == 128 && !p.x_tma && mtiles >= 2 &&
+      (!per_sample || ((long long)p.tilesW * p.tilesH) % 2 == 0)) {
+    Params q = p;
+    const long long pairs = ((mtiles + 1) / 2) * q.n_tiles;
+    q.total_tiles = (int)pairs;
+    q.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);
+    // each CTA loads half of the weight tile
+    cuuint64_t dims[3] = {(cuuint64_t)d->w_K, (cuuint64_t)d->w_NT, (cuuint64_t)(d->w_G * d->w_T)};
+    cuuint64_t strides[2] = {(cuuint64_t)d->w_K * 2, (cuuint64_t)d->w_K * d->w_NT * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BN / 2), 1};
+    if (int e = encode(&q.bmap, d->w, 3, dims, strides, box, BK)) return e;
+    q.tx_bytes = (uint32_t)((128 * BK + (BN / 2) * BK) * 2);
+    int g2 = (num_sms() / 2) * 2; if (g2 > 2 * pairs) g2 = (int)(2 * pairs);
+    if (BN == 256 && BK == 64) return launch2<256, 64>(q, g2, st);
+    if (BN == 128 && BK == 64) return launch2<128, 64>(q, g2, st);
+    if (BN == 256 && BK == 32) return launch2<256, 32>(q, g2, st);
+    if (BN == 128 && BK == 32) return launch2<128, 32>(q, g2, st);
+  }
   if (g32) {
     if (BN == 128 && BK == 64) return launch<128, 64, true>(p, grid, st);
     if (BN == 128 && BK == 32) return launch<128, 32, true>(p, grid, st);

@@ -202,3 +202,28 @@ def test_four_phase_upconv_form_in_one_tile_with_fused_tail(cfg, halo_mode):
         ref4[:, :, py::2, px::2] = y
     ref4 = F.leaky_relu(ref4 + noise * nstr + bias.reshape(1, co, 1, 1), 0.2) * 1.3
     _check(out4, ref4)
+
+
+@pytest.mark.parametrize("cfg", [(2, 32, 32, 64, 128), (1, 64, 48, 128, 256), (3, 16, 16, 256, 512), (2, 24, 40, 512, 256), (1, 16, 8, 64, 128)])
+def test_cta_pair_kernel_equals_single_cta_kernel(cfg):
+    """Wide tiles (BN = 128 / 256) run on the CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256 over two SMs, each CTA staging half of the weight
+    tile): same result as the one-CTA kernel (mode bit 4 switches the pair kernel off) and as the fp32 reference, including odd tile counts
+    (the last pair's second tile falls outside the tensor), the bias + ReLU tail and the shared-weight d(style)-free dgrad form."""
+    from morphganformer_b200 import tc, _lib
+    b, h, w, ci, co = cfg
+    x = _bf(util.case_tensor((b, h, w, ci), 21))
+    wt = _bf(util.case_tensor((co, ci, 3, 3), 22) * (1.0 / np.sqrt(9 * ci)))
+    bias = util.case_tensor((co,), 23) * 0.2
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1) + bias.reshape(1, co, 1, 1))
+    outs = []
+    try:
+        for mode in (1, 1 | 16):
+            _lib.lib().mgf_conv_tc_set_halo(mode)
+            out = torch.full((b, h, w, co), float("nan"), dtype=torch.bfloat16, device="cuda")
+            tc.conv_tc([x.cuda()], tc.pack_w3x3(wt).cuda(), tc.TAPS_3X3, (b, h, w), 1, co, out, bias=bias.cuda(), act=2, gain=1.0)
+            torch.cuda.synchronize()
+            outs.append(out.float().cpu())
+    finally:
+        _lib.lib().mgf_conv_tc_set_halo(1)
+    assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max()
+    _check(outs[0], ref)
