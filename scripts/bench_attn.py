@@ -5,14 +5,17 @@ import torch
 from morphganformer_b200 import _lib
 L = _lib.lib()
 def p(t): return t.data_ptr() if t is not None else None
-for (B, HW, C) in [(8, 16384, 256), (8, 4096, 512), (8, 1024, 512)]:
+for (B, HW, C) in [(8, 16384, 256), (8, 4096, 512), (8, 1024, 512), (8, 256, 512), (8, 64, 512), (8, 16, 512)]:
     X = torch.randn(B, HW, C, device="cuda").to(torch.bfloat16); dz = torch.randn_like(X)
     Kf = torch.randn(16, C, device="cuda") * 0.05; Sc = torch.randn(HW, 16, device="cuda"); mb = torch.zeros(B, 16, device="cuda")
     VM = torch.randn(B, 16, C, device="cuda") * 0.1; bm = torch.zeros(C, device="cuda"); noise = torch.randn(HW, device="cuda"); ns = torch.tensor([0.1], device="cuda")
     bias = torch.zeros(C, device="cuda"); out = torch.empty_like(X); dX = torch.empty_like(X); dVM = torch.zeros_like(VM); R = torch.zeros(B, C, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
-    def fwd(): _lib.check(L.mgf_attn_fwd(p(X), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(out), None, None, None, None, B, HW, C, 0, s))
-    def bwd(): _lib.check(L.mgf_attn_bwd(p(X), p(dz), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(dX), p(dVM), p(R), None, None, None, B, HW, C, 0, s))
+    # pre-built coefficient tables, as the engine passes them
+    tabK = torch.empty(int(L.mgf_attn_table_bytes(0, C)), dtype=torch.uint8, device="cuda"); tabV = torch.empty(B * int(L.mgf_attn_table_bytes(1, C)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.mgf_attn_tables(p(Kf), p(VM), p(tabK), p(tabV), B, C, s))
+    def fwd(): _lib.check(L.mgf_attn_fwd(p(X), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(out), None, None, p(tabK), p(tabV), B, HW, C, 0, s))
+    def bwd(): _lib.check(L.mgf_attn_bwd(p(X), p(dz), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(dX), p(dVM), p(R), None, p(tabK), p(tabV), B, HW, C, 0, s))
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         ts = []
         for i in range(7):
