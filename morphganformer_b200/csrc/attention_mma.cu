@@ -106,9 +106,30 @@ __host__ __device__ inline size_t rows_bytes(int C) { return (size_t)NT * krow(C
 __host__ __device__ inline size_t perm_bytes(int C) { return (size_t)(C / 8) * 32 * 8; }
 __host__ __device__ inline size_t tabk_bytes(int C) { return 2 * rows_bytes(C) + perm_bytes(C); }
 __host__ __device__ inline size_t tabv_bytes(int C) { return rows_bytes(C) + perm_bytes(C); }
-__device__ __forceinline__ void copy_table(void* dst, const void* src, size_t bytes) {
-  const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(dst);
-  for (int i = threadIdx.x; i < (int)(bytes >> 4); i += blockDim.x) d4[i] = __ldg(s4 + i);
+// Table copies are asynchronous bulk copies (cp.async.bulk global -> shared, completion counted on an mbarrier): one thread posts them all,
+// they run beside the rest of the CTA prologue, and every thread then waits on the barrier.  (A per-thread 16-byte copy loop cost ~1 us
+// of L2 latency per 4 KB trip -- 13 trips for the forward tables, 21 for the backward ones: most of the run time of the 4^2 .. 32^2 layers.)
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sm_u32(dst)), "l"(src), "r"(bytes), "r"(sm_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tbar_wait(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(sm_u32(bar)) : "memory");
 }
 
 template <bool F16>
@@ -135,7 +156,8 @@ __device__ __forceinline__ void tile_probs(const uint4* __restrict__ x0, const u
   const int KS = krow(C);
   float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
   float ss0 = 0.f, ss1 = 0.f;
-#pragma unroll
+  constexpr int UP = C32 < 4 ? C32 : 4;      // partial unrolling: four independent vector-load pairs in flight, a loop body the instruction cache keeps
+#pragma unroll (UP)
   for (int j = 0; j < C32; j++) {
     const uint4 a = __ldg(x0 + j * 4 + t), b = __ldg(x1 + j * 4 + t);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
@@ -189,11 +211,21 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(AttnMP p) {
   float* sm1 = reinterpret_cast<float*>(sVp + (C / 8) * 32);
   float* sb = sm1 + C;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  if (p.tabK) copy_table(sKhi, p.tabK, 2 * rows_bytes(C)); else fill_rowtable<F16>(sKhi, sKlo, p.Kf, C);
-  if (p.tabV) copy_table(sVp, reinterpret_cast<const unsigned char*>(p.tabV) + (size_t)b * tabv_bytes(C) + rows_bytes(C), perm_bytes(C));
-  else fill_permtable<true>(sVp, p.VM + (long long)b * NT * C, C);
+  __shared__ __align__(8) uint64_t tbar;
+  const bool bulk = p.tabK || p.tabV;
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      tbar_init(&tbar);
+      tbar_expect(&tbar, (uint32_t)((p.tabK ? 2 * rows_bytes(C) : 0) + (p.tabV ? perm_bytes(C) : 0)));
+      if (p.tabK) bulk_copy(sKhi, p.tabK, (uint32_t)(2 * rows_bytes(C)), &tbar);
+      if (p.tabV) bulk_copy(sVp, reinterpret_cast<const unsigned char*>(p.tabV) + (size_t)b * tabv_bytes(C) + rows_bytes(C), (uint32_t)perm_bytes(C), &tbar);
+    }
+  }
+  if (!p.tabK) fill_rowtable<F16>(sKhi, sKlo, p.Kf, C);
+  if (!p.tabV) fill_permtable<true>(sVp, p.VM + (long long)b * NT * C, C);
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sb[i] = p.bias ? p.bias[i] : 0.f; sm1[i] = 1.f + p.bm[i]; }
-  __syncthreads();
+  __syncthreads();                     // the barrier word is initialised (and the fill_* / sb / sm1 writes are visible) past this point
+  if (bulk) tbar_wait(&tbar);
   const float ns = (p.noise && p.nstr) ? *p.nstr : 0.f;
   const long long p0 = (long long)blockIdx.x * p.pix_per_cta;
   long long pend = p0 + p.pix_per_cta; if (pend > p.HW) pend = p.HW;
@@ -284,20 +316,28 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
   uint16_t* sD = sP + 128 * SPS;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const float* VMb = p.VM + (long long)b * NT * C;
-  if (p.tabK) {
-    copy_table(sKhi, p.tabK, 2 * rows_bytes(C));
-    copy_table(sKp, reinterpret_cast<const unsigned char*>(p.tabK) + 2 * rows_bytes(C), perm_bytes(C));
-  } else {
+  __shared__ __align__(8) uint64_t tbar;
+  const bool bulk = p.tabK || p.tabV;
+  if (bulk && threadIdx.x == 0) {
+    tbar_init(&tbar);
+    tbar_expect(&tbar, (uint32_t)((p.tabK ? tabk_bytes(C) : 0) + (p.tabV ? tabv_bytes(C) : 0)));
+    if (p.tabK) {
+      bulk_copy(sKhi, p.tabK, (uint32_t)(2 * rows_bytes(C)), &tbar);
+      bulk_copy(sKp, reinterpret_cast<const unsigned char*>(p.tabK) + 2 * rows_bytes(C), (uint32_t)perm_bytes(C), &tbar);
+    }
+    if (p.tabV) bulk_copy(sVr, reinterpret_cast<const unsigned char*>(p.tabV) + (size_t)b * tabv_bytes(C), (uint32_t)tabv_bytes(C), &tbar);   // sVr | sVp are contiguous, like the image
+  }
+  if (!p.tabK) {
     fill_rowtable<F16>(sKhi, sKlo, p.Kf, C);
     fill_permtable<false>(sKp, p.Kf, C);
   }
-  if (p.tabV) copy_table(sVr, reinterpret_cast<const unsigned char*>(p.tabV) + (size_t)b * tabv_bytes(C), tabv_bytes(C));      // sVr | sVp are contiguous, like the image
-  else {
+  if (!p.tabV) {
     fill_rowtable<false>(sVr, nullptr, VMb, C);
     fill_permtable<true>(sVp, VMb, C);
   }
   for (int i = threadIdx.x; i < C; i += blockDim.x) { sb[i] = p.bias ? p.bias[i] : 0.f; sm1[i] = 1.f + p.bm[i]; sR[i] = 0.f; }
-  __syncthreads();
+  __syncthreads();                     // barrier word initialised; fill_* / sb / sm1 / sR visible
+  if (bulk) tbar_wait(&tbar);
   const float ns = (p.noise && p.nstr) ? *p.nstr : 0.f;
   const long long p0 = (long long)blockIdx.x * p.pix_per_cta;
   long long pend = p0 + p.pix_per_cta; if (pend > p.HW) pend = p.HW;
@@ -307,9 +347,9 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
   for (int h = 0; h < NH; h++)
 #pragma unroll
     for (int i = 0; i < NTW; i++) { dvm[h][i][0] = dvm[h][i][1] = dvm[h][i][2] = dvm[h][i][3] = 0.f; }
-  float racc[C32];                                        // R partial sums: racc[j] belongs to channel (j*4 + t)*8 + g
-#pragma unroll
-  for (int i = 0; i < C32; i++) racc[i] = 0.f;
+  // The channel loops below are unrolled by UJ only: fully unrolled, the C = 512 kernel was 12 K instructions (190 KB) of straight-line code
+  // that every round streamed through the instruction cache -- `no_instruction` was its top stall reason (profiles/r01 attention table).
+  constexpr int UJ = C32 < 2 ? C32 : 2;
 
   for (long long base = p0; base < pend; base += 128) {
     const long long f0 = base + warp * 16;
@@ -347,7 +387,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
     for (int h = 0; h < NH; h++) {
       if (active) {
         // ---- pass B: ctl, du, dctl -> dA (tensor cores), sdot = sum_c dxn * x; dctl staged for the dVM phase
-#pragma unroll
+#pragma unroll (UJ)
         for (int jj = 0; jj < JH; jj++) {
           const int j = h * JH + jj;
           const uint4 a = __ldg(x0 + j * 4 + t), bq = __ldg(x1 + j * 4 + t);
@@ -422,7 +462,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
       // ---- pass C: dX = dS Kf + rn * dxn - x * k3 ; R[c] += dX * x
       uint4* o0 = reinterpret_cast<uint4*>(p.dX + ((long long)b * p.HW + q0) * C);
       uint4* o1 = reinterpret_cast<uint4*>(p.dX + ((long long)b * p.HW + q1) * C);
-#pragma unroll
+#pragma unroll (UJ)
       for (int j = 0; j < C32; j++) {
         const uint4 a = __ldg(x0 + j * 4 + t), bq = __ldg(x1 + j * 4 + t);
         const uint4 ga = __ldg(g0 + j * 4 + t), gb = __ldg(g1 + j * 4 + t);
@@ -478,7 +518,8 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
         {
           const bool up = (g & 1) != 0;
           const float send = up ? h2[0] : h2[1], keep = up ? h2[1] : h2[0];
-          racc[j] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          // lane (g, t) now holds the 16-row sum of channel ch + g: one conflict-free shared-memory reduction per lane (bank = 8 t + g)
+          atomicAdd(&sR[ch + g], keep + __shfl_xor_sync(0xffffffffu, send, 4));
         }
       }
     }
@@ -495,8 +536,6 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
         atomicAdd(d + (g + 8) * C, dvm[h][i][2]); atomicAdd(d + (g + 8) * C + 1, dvm[h][i][3]);
       }
     }
-#pragma unroll
-  for (int j = 0; j < C32; j++) atomicAdd(&sR[(j * 4 + t) * 8 + g], racc[j]);
   __syncthreads();
   if (p.R) for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&p.R[(long long)b * C + i], sR[i]);
 }

@@ -65,6 +65,7 @@ struct alignas(64) Params {
   int ph_taps;                   // per-phase tap lists: phase ph owns taps [ph_tap0[ph], ph_tap0[ph+1]); weights are shared by the phases
   int ph_tap0[5]; int ph_tiles;  // ph_tiles = tiles of one phase (tile order is phase-major so the persistent CTAs stay balanced)
   int x_tma; uint32_t x_bytes;   // X tile arrives by TMA (one 64/32-channel group per tile) instead of per-thread strided loads
+  int dbg;                       // experiment switches (scripts/bench_halo.py; 0 in production): 1 = epilogue only drains TMEM, 2 = no MMAs, 4 = no activation loads
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -229,6 +230,14 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
       // (super-pixel rows: nz0 / nz1 = left / right pixel of the pair).
       const int phase_lo = t.n0 / p.Cout;
       float ovf_mx = 0.f;
+      if (p.dbg & 1) {                 // experiment: drain the accumulator and hand it back, nothing else (which stage bounds the tile rate?)
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c++) { uint32_t raw[32]; tmem_ld32(tacc + (uint32_t)(c * 32), raw); }
+        tc_fence_before();
+        if (tempty_on_cta0) mbar_arrive_cta0(tempty_bar); else mbar_arrive(tempty_bar);
+        if (p.X && (p.reduce_out || p.actgrad) && p.x_tma) mbar_wait(xbar, xphase);
+        return;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         const int col = t.n0 + c * 32;
@@ -818,8 +827,11 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       for (int kc = 0; kc < KC; kc++) {
         mbar_wait(&aempty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&afull[stage], (uint32_t)C::A_BOX);
-          tma_load_4d(&p.amap[0], &afull[stage], sA + stage * C::A_STAGE, kc * BK, t.x0 - 1, t.y0 - 1, t.b0);
+          if (p.dbg & 4) mbar_arrive(&afull[stage]);
+          else {
+            mbar_arrive_expect_tx(&afull[stage], (uint32_t)C::A_BOX);
+            tma_load_4d(&p.amap[0], &afull[stage], sA + stage * C::A_STAGE, kc * BK, t.x0 - 1, t.y0 - 1, t.b0);
+          }
         }
         __syncwarp();
         last_stage = stage; last_phase = phase;
@@ -844,6 +856,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(sA + stage * C::A_STAGE);
+          if (!(p.dbg & 2))
 #pragma unroll
           for (int tp = 0; tp < 9; tp++) {
             const uint64_t adesc = make_desc_halo<BK>(sa + tap_off[tp]);
@@ -1031,6 +1044,7 @@ static int launch_halo(const Params& p, int grid, cudaStream_t st) {
 static bool g_halo_enabled = true;
 static bool g_halo_phases = false;  // halo kernel also for multi-phase (up-convolution) launches; default: those run as one wide tile per pixel block
 static bool g_cg2_enabled = true;     // CTA-pair (cta_group::2) kernel for the wide tiles (A/B switch: mgf_conv_tc_set_halo bit 4 disables it)
+static int g_dbg = 0;             // experiment switches copied into Params::dbg (mgf_conv_tc_set_halo bits 8..10)
 static int g_halo_nstg = 1;        // epilogue staging tiles per group in the halo kernel (A/B switch: mgf_conv_tc_set_halo(1 | 2 << 1))
 
 }  // namespace tc
@@ -1043,6 +1057,7 @@ extern "C" int mgf_conv_tc_set_halo(int mode) {
   mgf::tc::g_halo_nstg = (n == 2) ? 2 : 1;
   mgf::tc::g_halo_phases = (mode & 8) != 0;
   mgf::tc::g_cg2_enabled = (mode & 16) == 0;
+  mgf::tc::g_dbg = (mode >> 8) & 7;
   return 0;
 }
 
@@ -1085,6 +1100,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
 
   Params p;
   memset(&p, 0, sizeof(p));
+  p.dbg = g_dbg;
   // ---- halo variant: 3x3 taps in {-1,0,1}^2 on one activation map, C = 64 or 128, images large enough that a CTA keeps the
   // resident weights for many tiles
   // (measured: a win for C = 64 -- 0.95 -> 0.68 ms on 64->64 @1024^2 x8 -- but not for C = 128, where the generic kernel's

@@ -219,24 +219,39 @@ __global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict_
     w0[e] = wrgb[o]; w1[e] = wrgb[C + o]; w2[e] = wrgb[2 * C + o]; sv[e] = s[(long long)b * C + o]; lds[e] = 0.f; lR[e] = 0.f;
   }
   const long long p0 = (long long)blockIdx.x * pix_per_cta;
-  for (long long p = p0 + pl; p < p0 + pix_per_cta && p < HW; p += tp) {
-    const float* ip = dimg + (long long)b * 3 * HW + p;
-    const float g0 = __ldg(ip), g1 = __ldg(ip + HW), g2 = __ldg(ip + 2 * HW);
-    const long long off = ((long long)b * HW + p) * C + cv * 8;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + off));
-    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o4[4];
+  long long pe = p0 + pix_per_cta; if (pe > HW) pe = HW;
+  // four pixels per trip, all their loads issued before the first use: one load round trip per pixel kept this kernel at 0.4 of the HBM
+  // roofline (long_scoreboard was its only stall reason)
+  constexpr int UP = 4;
+  for (long long p = p0 + pl; p < pe; p += (long long)UP * tp) {
+    float g0[UP], g1[UP], g2[UP]; uint4 u[UP];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const float2 f = unpack16(w4[e], yf16);
-      const float t0 = g0 * w0[e * 2] + g1 * w1[e * 2] + g2 * w2[e * 2];
-      const float t1 = g0 * w0[e * 2 + 1] + g1 * w1[e * 2 + 1] + g2 * w2[e * 2 + 1];
-      const float d0 = t0 * sv[e * 2], d1 = t1 * sv[e * 2 + 1];
-      lds[e * 2] += t0 * f.x; lds[e * 2 + 1] += t1 * f.y;
-      lR[e * 2] += d0 * f.x; lR[e * 2 + 1] += d1 * f.y;
-      o4[e] = pack_bf16(d0, d1);
+    for (int k = 0; k < UP; k++) {
+      const long long q = p + (long long)k * tp;
+      const bool ok = q < pe;
+      const float* ip = dimg + (long long)b * 3 * HW + (ok ? q : p);
+      g0[k] = __ldg(ip); g1[k] = __ldg(ip + HW); g2[k] = __ldg(ip + 2 * HW);
+      u[k] = __ldg(reinterpret_cast<const uint4*>(y + ((long long)b * HW + (ok ? q : p)) * C + cv * 8));
     }
-    *reinterpret_cast<uint4*>(dy + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+#pragma unroll
+    for (int k = 0; k < UP; k++) {
+      const long long q = p + (long long)k * tp;
+      if (q < pe) {
+        const uint32_t w4[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 f = unpack16(w4[e], yf16);
+          const float t0 = g0[k] * w0[e * 2] + g1[k] * w1[e * 2] + g2[k] * w2[e * 2];
+          const float t1 = g0[k] * w0[e * 2 + 1] + g1[k] * w1[e * 2 + 1] + g2[k] * w2[e * 2 + 1];
+          const float d0 = t0 * sv[e * 2], d1 = t1 * sv[e * 2 + 1];
+          lds[e * 2] += t0 * f.x; lds[e * 2 + 1] += t1 * f.y;
+          lR[e * 2] += d0 * f.x; lR[e * 2 + 1] += d1 * f.y;
+          o4[e] = pack_bf16(d0, d1);
+        }
+        *reinterpret_cast<uint4*>(dy + ((long long)b * HW + q) * C + cv * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
   }
 #pragma unroll
   for (int e = 0; e < 8; e++) { atomicAdd(&acc_ds[cv * 8 + e], lds[e]); atomicAdd(&acc_R[cv * 8 + e], lR[e]); }

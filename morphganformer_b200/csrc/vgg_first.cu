@@ -44,7 +44,7 @@ __device__ __forceinline__ int perm_chan(int nt, int g) { return ((nt >> 2) * 4 
 constexpr int FTH = 8, FTW = 64, FSW = FTW + 2 + 2, FPL = (FTH + 2) * FSW;     // tile 8 x 64 pixels, padded row 68, plane 680 floats
 
 template <bool F16>
-__global__ void __launch_bounds__(256, 3) vgg_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ target, float* mse,
+__global__ void __launch_bounds__(256, 2) vgg_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ target, float* mse,
                                                             const float* __restrict__ W, const float* __restrict__ bias, uint16_t* out, int R, int ntiles) {
   __shared__ float sx[3 * FPL + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -62,11 +62,8 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_fwd_kernel(const float* __re
       bw[s][nt][0] = pack16(k0 < 27 ? wr[k0] : 0.f, k0 + 1 < 27 ? wr[k0 + 1] : 0.f, F16);
       bw[s][nt][1] = pack16(k0 + 8 < 27 ? wr[k0 + 8] : 0.f, k0 + 9 < 27 ? wr[k0 + 9] : 0.f, F16);
     }
-  float bv[2][8];
-#pragma unroll
-  for (int jj = 0; jj < 2; jj++)
-#pragma unroll
-    for (int e = 0; e < 8; e++) bv[jj][e] = bias[(jj * 4 + t) * 8 + e];
+  __shared__ float sbias[64];            // bias stays in shared memory (the prefetch registers need the room)
+  if (threadIdx.x < 64) sbias[threadIdx.x] = bias[threadIdx.x];
   // patch offsets of this lane's 8 k indices: {2t, 2t+1, 2t+8, 2t+9} + 16 s
   int koff[8];
 #pragma unroll
@@ -77,45 +74,55 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_fwd_kernel(const float* __re
   }
   float mse_local = 0.f;
   int mse_b = -1;
+  // The haloed image tile (3 channels x 10 rows x 66 columns = 1980 floats, FPT per thread) and the target values of its interior are
+  // fetched into registers ONE TILE AHEAD: all of a thread's loads are in flight together and their HBM latency is covered by the MMA
+  // phase of the current tile.  (Fetching in place -- a row loop of dependent load -> store trips per warp, then a second loop for the MSE --
+  // serialised ~7 DRAM latencies per tile: the kernel ran at 0.3 of the HBM roofline, profiles/r01e_secondary_kernels_ncu.md.)
+  constexpr int FNE = 3 * (FTH + 2) * (FTW + 2), FPT = (FNE + 255) / 256;
+  float vi[FPT], vt[FPT];
+  auto fetch = [&](long long tile) {
+    const int b = (int)(tile / (tiles_x * tiles_y)), tr = (int)(tile % (tiles_x * tiles_y));
+    const int Y0 = (tr / tiles_x) * FTH, X0 = (tr % tiles_x) * FTW;
+    const float* ib = img + (long long)b * 3 * HW;
+    const float* tb = target ? target + (long long)b * 3 * HW : nullptr;
+#pragma unroll
+    for (int k = 0; k < FPT; k++) {
+      const int e = threadIdx.x + 256 * k;
+      const int c = e / ((FTH + 2) * (FTW + 2)), rem = e - c * ((FTH + 2) * (FTW + 2));
+      const int hy = rem / (FTW + 2), hx = rem - hy * (FTW + 2);
+      const int y = Y0 - 1 + hy, x = X0 - 1 + hx;
+      const bool in = e < FNE && y >= 0 && y < R && x >= 0 && x < R;
+      const bool interior = in && hy >= 1 && hy <= FTH && hx >= 1 && hx <= FTW;
+      const long long o = c * HW + (long long)y * R + x;
+      vi[k] = in ? __ldg(ib + o) : 0.f;
+      vt[k] = (interior && tb) ? __ldg(tb + o) : vi[k];          // outside the interior: a zero difference
+    }
+  };
+  if ((long long)blockIdx.x < (long long)ntiles) fetch(blockIdx.x);
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < (long long)ntiles; tile += gridDim.x) {
   const int b = (int)(tile / (tiles_x * tiles_y)), tr = (int)(tile % (tiles_x * tiles_y));
   const int Y0 = (tr / tiles_x) * FTH, X0 = (tr % tiles_x) * FTW;
-  const float* ib = img + (long long)b * 3 * HW;
   if (target && b != mse_b) {          // flush the MSE partial sum when the image changes (tiles of one image are contiguous)
     if (mse_b >= 0) { const float tot = warp_sum(mse_local); if (lane == 0 && tot != 0.f) atomicAdd(&mse[mse_b], tot); }
     mse_local = 0.f; mse_b = b;
   }
-  // ---- image tile with halo, scaled; zero outside the image (= the conv's zero padding of the SCALED input)
-  for (int row = warp; row < 3 * (FTH + 2); row += 8) {        // one warp per (channel, halo row): no per-element index arithmetic
-    const int c = row / (FTH + 2), hy = row - c * (FTH + 2);
-    const int y = Y0 - 1 + hy;
-    const bool yin = y >= 0 && y < R;
-    const float* src = ib + c * HW + (long long)(yin ? y : 0) * R;
-    const float sh = v_shift[c], inv = 1.f / v_scale[c];
-    float* dst = sx + c * FPL + hy * FSW;
+  // ---- registers -> scaled tile in shared memory (zero outside the image = the conv's zero padding of the SCALED input) + MSE partial sum
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
-      const int hx = q * 32 + lane, x = X0 - 1 + hx;
-      if (hx < FTW + 2) dst[hx] = (yin && x >= 0 && x < R) ? (__ldg(src + x) - sh) * inv : 0.f;
-    }
-  }
-  // ---- MSE partial sum over the interior of the tile
-  if (target) {
-    const float* tb = target + (long long)b * 3 * HW;
-    for (int row = warp; row < 3 * FTH; row += 8) {
-      const int c = row / FTH, y = Y0 + row - c * FTH;
-      if (y < R) {
-        const long long o = c * HW + (long long)y * R + X0;
-#pragma unroll
-        for (int q = 0; q < FTW / 32; q++) {
-          const int x = q * 32 + lane;
-          if (X0 + x < R) { const float d = __ldg(ib + o + x) - __ldg(tb + o + x); mse_local = fmaf(d, d, mse_local); }
-        }
-      }
+  for (int k = 0; k < FPT; k++) {
+    const int e = threadIdx.x + 256 * k;
+    const int c = e / ((FTH + 2) * (FTW + 2)), rem = e - c * ((FTH + 2) * (FTW + 2));
+    const int hy = rem / (FTW + 2), hx = rem - hy * (FTW + 2);
+    const int y = Y0 - 1 + hy, x = X0 - 1 + hx;
+    if (e < FNE) {
+      const bool in = y >= 0 && y < R && x >= 0 && x < R;
+      sx[c * FPL + hy * FSW + hx] = in ? (vi[k] - v_shift[c]) * (1.f / v_scale[c]) : 0.f;
+      const float d = vi[k] - vt[k];
+      mse_local = fmaf(d, d, mse_local);
     }
   }
   __syncthreads();
+  if (tile + gridDim.x < (long long)ntiles) fetch(tile + gridDim.x);      // in flight during the MMA phase below
   const int y = Y0 + warp;
 #pragma unroll 1
   for (int cg = 0; cg < FTW / 16; cg++) {
@@ -140,7 +147,8 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_fwd_kernel(const float* __re
       uint32_t w0[4], w1[4];
 #pragma unroll
       for (int m = 0; m < 4; m++) {
-        float acc[4] = {bv[jj][2 * m], bv[jj][2 * m + 1], bv[jj][2 * m], bv[jj][2 * m + 1]};
+        const float2 bq = *reinterpret_cast<const float2*>(sbias + (jj * 4 + t) * 8 + 2 * m);
+        float acc[4] = {bq.x, bq.y, bq.x, bq.y};
         mma16816<F16>(acc, a[0][0], a[0][1], a[0][2], a[0][3], bw[0][jj * 4 + m][0], bw[0][jj * 4 + m][1]);
         mma16816<F16>(acc, a[1][0], a[1][1], a[1][2], a[1][3], bw[1][jj * 4 + m][0], bw[1][jj * 4 + m][1]);
         w0[m] = pk_relu<F16>(acc[0], acc[1]); w1[m] = pk_relu<F16>(acc[2], acc[3]);
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_fwd_kernel(const float* __re
 constexpr int BTH = 8, BTW = 32, BHW = BTW + 2, BNP = (BTH + 2) * BHW;       // 8 x 32 output pixels, 340 haloed pixels
 constexpr int BMT = (BNP + 15) / 16, BDS = 37;   // 22 M-tiles; dcol row stride (floats): odd -> conflict-free gather, 5g+2t -> near conflict-free scatter
 
-__global__ void __launch_bounds__(256, 3) vgg_conv1_bwd_kernel(const uint16_t* __restrict__ gy, const float* __restrict__ W, const float* __restrict__ img,
+__global__ void __launch_bounds__(256, 2) vgg_conv1_bwd_kernel(const uint16_t* __restrict__ gy, const float* __restrict__ W, const float* __restrict__ img,
                                                             const float* __restrict__ target, float mcoef, float* dimg, int R, int ntiles) {
   extern __shared__ __align__(16) float sd[];             // [BMT * 16][BDS]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -176,40 +184,70 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_bwd_kernel(const uint16_t* _
         bw[jj * 2 + h][nt][0] = pack_bf16(W[ch * 32 + n], W[(ch + 1) * 32 + n]);
         bw[jj * 2 + h][nt][1] = pack_bf16(W[(ch + 2) * 32 + n], W[(ch + 3) * 32 + n]);
       }
+  // The gradient vectors of the tile's 340 haloed pixels (3 M-tiles of 16 pixels per warp, 4 x 16 bytes per lane each) and the image / target
+  // values of this thread's output pixel are fetched into registers for the NEXT tile right after the MMAs of the current one have consumed
+  // them: one exposed DRAM latency per tile instead of four (three dependent M-tile rounds + the MSE-gradient loads), and that one is
+  // covered by the col2im phase and the other resident CTA.
+  constexpr int MPW = (BMT + 7) / 8;          // M-tiles per warp
+  uint4 pva[MPW][2], pvb[MPW][2];
+  float pim[3] = {0.f, 0.f, 0.f}, ptg[3] = {0.f, 0.f, 0.f};
+  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+  auto fetch = [&](long long tile) {
+    const int b = (int)(tile / (tiles_x * tiles_y)), tr = (int)(tile % (tiles_x * tiles_y));
+    const int Y0 = (tr / tiles_x) * BTH, X0 = (tr % tiles_x) * BTW;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < MPW; i++) {
+      const int mt = warp + 8 * i;
+      const int i0 = mt * 16 + g, i1 = i0 + 8;
+      const int y0 = Y0 - 1 + i0 / BHW, x0 = X0 - 1 + i0 % BHW, y1 = Y0 - 1 + i1 / BHW, x1 = X0 - 1 + i1 % BHW;
+      const bool ok0 = mt < BMT && i0 < BNP && y0 >= 0 && y0 < R && x0 >= 0 && x0 < R, ok1 = mt < BMT && i1 < BNP && y1 >= 0 && y1 < R && x1 >= 0 && x1 < R;
+      const uint4* r0 = reinterpret_cast<const uint4*>(gy + (((long long)b * R + (ok0 ? y0 : 0)) * R + (ok0 ? x0 : 0)) * 64);
+      const uint4* r1 = reinterpret_cast<const uint4*>(gy + (((long long)b * R + (ok1 ? y1 : 0)) * R + (ok1 ? x1 : 0)) * 64);
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) { pva[i][jj] = ok0 ? __ldg(r0 + jj * 4 + t) : z; pvb[i][jj] = ok1 ? __ldg(r1 + jj * 4 + t) : z; }
+    }
+    const int Y = Y0 + ty, X = X0 + tx;
+    if (target && Y < R && X < R) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const long long o = ((long long)b * 3 + c) * HW + (long long)Y * R + X;
+        pim[c] = __ldg(img + o); ptg[c] = __ldg(target + o);
+      }
+    }
+  };
+  if ((long long)blockIdx.x < (long long)ntiles) fetch(blockIdx.x);
 #pragma unroll 1
   for (long long tile = blockIdx.x; tile < (long long)ntiles; tile += gridDim.x) {
   const int b = (int)(tile / (tiles_x * tiles_y)), tr = (int)(tile % (tiles_x * tiles_y));
   const int Y0 = (tr / tiles_x) * BTH, X0 = (tr % tiles_x) * BTW;
-#pragma unroll 1
-  for (int mt = warp; mt < BMT; mt += 8) {
-    const int i0 = mt * 16 + g, i1 = i0 + 8;
-    const int y0 = Y0 - 1 + i0 / BHW, x0 = X0 - 1 + i0 % BHW, y1 = Y0 - 1 + i1 / BHW, x1 = X0 - 1 + i1 % BHW;
-    const bool ok0 = i0 < BNP && y0 >= 0 && y0 < R && x0 >= 0 && x0 < R, ok1 = i1 < BNP && y1 >= 0 && y1 < R && x1 >= 0 && x1 < R;
-    const uint4* r0 = reinterpret_cast<const uint4*>(gy + (((long long)b * R + (ok0 ? y0 : 0)) * R + (ok0 ? x0 : 0)) * 64);
-    const uint4* r1 = reinterpret_cast<const uint4*>(gy + (((long long)b * R + (ok1 ? y1 : 0)) * R + (ok1 ? x1 : 0)) * 64);
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    uint4 va[2], vb[2];
 #pragma unroll
-    for (int jj = 0; jj < 2; jj++) { va[jj] = ok0 ? __ldg(r0 + jj * 4 + t) : z; vb[jj] = ok1 ? __ldg(r1 + jj * 4 + t) : z; }
-    float acc[4][4];
+  for (int i = 0; i < MPW; i++) {
+    const int mt = warp + 8 * i;
+    if (mt < BMT) {
+      const int i0 = mt * 16 + g, i1 = i0 + 8;
+      float acc[4][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+      for (int nt = 0; nt < 4; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
 #pragma unroll
-    for (int jj = 0; jj < 2; jj++)
+      for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          mma16816<false>(acc[nt], pva[i][jj].x, pvb[i][jj].x, pva[i][jj].y, pvb[i][jj].y, bw[jj * 2][nt][0], bw[jj * 2][nt][1]);
+          mma16816<false>(acc[nt], pva[i][jj].z, pvb[i][jj].z, pva[i][jj].w, pvb[i][jj].w, bw[jj * 2 + 1][nt][0], bw[jj * 2 + 1][nt][1]);
+        }
 #pragma unroll
       for (int nt = 0; nt < 4; nt++) {
-        mma16816<false>(acc[nt], va[jj].x, vb[jj].x, va[jj].y, vb[jj].y, bw[jj * 2][nt][0], bw[jj * 2][nt][1]);
-        mma16816<false>(acc[nt], va[jj].z, vb[jj].z, va[jj].w, vb[jj].w, bw[jj * 2 + 1][nt][0], bw[jj * 2 + 1][nt][1]);
+        sd[i0 * BDS + nt * 8 + 2 * t] = acc[nt][0]; sd[i0 * BDS + nt * 8 + 2 * t + 1] = acc[nt][1];
+        sd[i1 * BDS + nt * 8 + 2 * t] = acc[nt][2]; sd[i1 * BDS + nt * 8 + 2 * t + 1] = acc[nt][3];
       }
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-      sd[i0 * BDS + nt * 8 + 2 * t] = acc[nt][0]; sd[i0 * BDS + nt * 8 + 2 * t + 1] = acc[nt][1];
-      sd[i1 * BDS + nt * 8 + 2 * t] = acc[nt][2]; sd[i1 * BDS + nt * 8 + 2 * t + 1] = acc[nt][3];
     }
   }
+  const float cim[3] = {pim[0], pim[1], pim[2]}, ctg[3] = {ptg[0], ptg[1], ptg[2]};
+  if (tile + gridDim.x < (long long)ntiles) fetch(tile + gridDim.x);
   __syncthreads();
   // ---- col2im gather: d(xs)[c](Y, X) = sum_taps dcol[(Y - (ky-1), X - (kx-1))][tap*3 + c]
-  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31, Y = Y0 + ty, X = X0 + tx;
+  const int Y = Y0 + ty, X = X0 + tx;
   if (Y < R && X < R) {
     float gs[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -222,7 +260,7 @@ __global__ void __launch_bounds__(256, 3) vgg_conv1_bwd_kernel(const uint16_t* _
     for (int c = 0; c < 3; c++) {
       const long long o = ((long long)b * 3 + c) * HW + (long long)Y * R + X;
       float v = gs[c] / v_scale[c];
-      if (target) v = fmaf(mcoef, __ldg(img + o) - __ldg(target + o), v);
+      if (target) v = fmaf(mcoef, cim[c] - ctg[c], v);
       dimg[o] = v;
     }
   }
@@ -243,7 +281,7 @@ extern "C" int mgf_vgg_conv1_fwd(const float* img, const float* target, float* m
   if (B <= 0 || R <= 0) MGF_FAIL(MGF_E_SHAPE, "vgg_conv1_fwd: empty input");
   const long long nt = (long long)((R + FTW - 1) / FTW) * ((R + FTH - 1) / FTH) * B;
   if (nt > 0x7fffffffLL) MGF_FAIL(MGF_E_SHAPE, "vgg_conv1_fwd: too many tiles");
-  const long long cap = (long long)num_sms() * 3;          // persistent: weights / offsets are set up once per CTA
+  const long long cap = (long long)num_sms() * 2;          // persistent: weights / offsets are set up once per CTA
   const unsigned grid = (unsigned)(nt < cap ? nt : cap);
   if (fwd_f16()) vgg_conv1_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(img, target, mse, W, bias, (uint16_t*)out, R, (int)nt);
   else vgg_conv1_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(img, target, mse, W, bias, (uint16_t*)out, R, (int)nt);
@@ -261,7 +299,7 @@ extern "C" int mgf_vgg_conv1_bwd(const void* gy, const float* W, const float* im
   const int smem = BMT * 16 * BDS * (int)sizeof(float);
   static bool cfg = false;
   if (!cfg) { cudaFuncSetAttribute(vgg_conv1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cfg = true; }
-  const long long cap = (long long)num_sms() * 3;
+  const long long cap = (long long)num_sms() * 2;
   const unsigned grid = (unsigned)(nt < cap ? nt : cap);
   vgg_conv1_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const uint16_t*)gy, W, img, target, mcoef, dimg, R, (int)nt);
   MGF_CHECK_LAUNCH("vgg_conv1_bwd");

@@ -15,7 +15,7 @@ for r in rows[s:e]:
     n = r['Kernel Name'].replace('<unnamed>::', '').replace('(anonymous namespace)::', '')
     n = re.sub(r'\(.*', '', n)
     n = re.sub(r'^void ', '', n)
-    if 'conv_tc_kernel' in n or 'conv_halo' in n: n = re.sub(r'^.*tc::', '', n)
+    if 'conv_tc_kernel' in n or 'conv_tc2_kernel' in n or 'conv_halo' in n: n = re.sub(r'^.*tc::', '', n)
     else: n = re.sub(r'<.*', '', n); n = n.split('::')[-1] if 'mgf::' in n else 'torch: ' + n[-40:]
     agg[n][0] += 1; agg[n][1] += ms(r)
 tot = sum(v[1] for v in agg.values())
