@@ -65,7 +65,7 @@ struct alignas(64) Params {
   int ph_taps;                   // per-phase tap lists: phase ph owns taps [ph_tap0[ph], ph_tap0[ph+1]); weights are shared by the phases
   int ph_tap0[5]; int ph_tiles;  // ph_tiles = tiles of one phase (tile order is phase-major so the persistent CTAs stay balanced)
   int x_tma; uint32_t x_bytes;   // X tile arrives by TMA (one 64/32-channel group per tile) instead of per-thread strided loads
-  int dbg;                       // experiment switches (scripts/bench_halo.py; 0 in production): 1 = epilogue only drains TMEM, 2 = no MMAs, 4 = no activation loads
+  int dbg;                       // experiment switches (scripts/bench_halo.py; 0 in production): 1 = epilogue only drains TMEM, 2 = no MMAs, 4 = no activation loads, 8 = no output store, 16 = no staging either
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -365,6 +365,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         const int h = c % GW32;
         constexpr bool SPLIT = (GW32 == 1 && BN > 32);
         uint8_t* stg_c = SPLIT ? stg + (c & 1) * (STG_BYTES / 2) : stg;
+        if (p.dbg & 16) continue;
         if (h == 0 && (!p.x_tma || SPLIT)) {               // the previous store must have finished reading the staging tile
           if (r == 0) { if (SPLIT) tma_store_wait_read<1>(); else tma_store_wait_read<NSTG - 1>(); }   // (x_tma: the caller already did this before loading X into it)
           group_sync(group);
@@ -388,7 +389,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         if (h == GW32 - 1) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           group_sync(group);
-          if (r == 0) tma_store_4d(&p.omap[phase_idx], stg_c, co - h * 32, t.x0, t.y0, t.b0);
+          if (r == 0 && !(p.dbg & 8)) tma_store_4d(&p.omap[phase_idx], stg_c, co - h * 32, t.x0, t.y0, t.b0);
         }
       }
       ovf_commit(p.ovf, valid ? ovf_mx : 0.f);      // rows outside the tile hold whatever the accumulator had
@@ -735,7 +736,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tc2_ker
 //     re-loaded only when the CTA moves to another sample / N-block.
 // L2->SM traffic per 128-pixel tile drops from 9*(16+BN/8) KB to 36 KB per channel chunk.
 constexpr int HALO_PITCH = 10;      // haloed tile row pitch in pixels: 8 output pixels + 1 halo pixel each side (no padding pixels)
-template <int BN, int KC, int BK, int NSTG_>
+template <int BN, int KC, int BK, int NSTG_, int NG_>
 struct HaloCfg {
   static constexpr int A_BOX = 18 * HALO_PITCH * BK * 2;          // bytes one TMA box delivers: 18 rows x 10 px x (128 B | 64 B)
   static constexpr int A_STAGE = ((A_BOX + 1023) / 1024) * 1024;  // stages start on swizzle-atom boundaries
@@ -743,10 +744,13 @@ struct HaloCfg {
   static constexpr int B_BYTES = KC * 9 * B_TILE;
   static constexpr int SMEM_MAX = 227 * 1024;
   static constexpr int NSTG = NSTG_;
-  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - 2 * NSTG * STG_BYTES - 2 * RACC * 4 - 1024) / A_STAGE;
+  static constexpr int NG = NG_;                                   // epilogue groups = accumulator stages in TMEM
+  static constexpr int THREADS = 64 + 128 * NG;
+  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - NG * NSTG * STG_BYTES - NG * RACC * 4 - 1024) / A_STAGE;
   static constexpr int NS = NS_RAW > 8 ? 8 : NS_RAW;
-  static constexpr int SMEM = B_BYTES + NS * A_STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + 512;
-  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM = B_BYTES + NS * A_STAGE + NG * NSTG * STG_BYTES + NG * RACC * 4 + 512;
+  static constexpr uint32_t TMEM_COLS = NG * BN <= 32 ? 32 : NG * BN <= 64 ? 64 : NG * BN <= 128 ? 128 : NG * BN <= 256 ? 256 : 512;
+  static_assert(NG >= 2 && NG <= 4 && NG * BN <= 512, "accumulator stages must fit the 512 TMEM columns");
   static_assert(NS >= 2, "halo kernel needs at least two activation stages");
 };
 
@@ -772,32 +776,37 @@ __device__ __forceinline__ HaloTile decode_halo(const Params& p, int tile, int B
   return t;
 }
 
-template <int BN, int KC, int BK, int NSTG_>
-__global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant__ Params p) {
-  using C = HaloCfg<BN, KC, BK, NSTG_>;
+// NG epilogue groups of four warps drain NG accumulator stages in turn.  The epilogue of a 64-column tile is a dependent chain of ~700-1400
+// instructions per thread (scripts/bench_halo.py: with two groups the noise+bias / reduce+X tails took 0.37-0.44 ms per launch on their own, the
+// MMAs 0.28 ms), and a group is one warp per scheduler: a third group adds the latency hiding the chain lacks.
+template <int BN, int KC, int BK, int NSTG_, int NG_>
+__global__ void __launch_bounds__(64 + 128 * NG_, 1) conv_halo_kernel(const __grid_constant__ Params p) {
+  using C = HaloCfg<BN, KC, BK, NSTG_, NG_>;
+  constexpr int NG = NG_;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sA = smem + C::B_BYTES;
   uint8_t* stg_base = sA + C::NS * C::A_STAGE;
-  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * C::NSTG * STG_BYTES);
-  uint64_t* afull = reinterpret_cast<uint64_t*>(racc_base + 2 * RACC);
+  float* racc_base = reinterpret_cast<float*>(stg_base + NG * C::NSTG * STG_BYTES);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(racc_base + NG * RACC);
   uint64_t* aempty = afull + C::NS;
   uint64_t* bfull = aempty + C::NS;
   uint64_t* tfull = bfull + 1;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* xbar = tempty + 2;                 // [group][staging buffer]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
+  uint64_t* tempty = tfull + NG;
+  uint64_t* xbar = tempty + NG;                // [group][staging buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2 * NG);
+  constexpr int W_PROD = 4 * NG, W_MMA = 4 * NG + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NS; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     mbar_init(bfull, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
-    for (int s = 0; s < 4; s++) mbar_init(&xbar[s], 1);
+    for (int s = 0; s < NG; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2 * NG; s++) mbar_init(&xbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == W_PROD) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -806,7 +815,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {     // ------------------------------------------------------ TMA producer
+  if (warp == W_PROD) {     // ------------------------------------------------------ TMA producer
     int stage = 0; uint32_t phase = 0; int cur_key = -1; int last_stage = -1; uint32_t last_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const HaloTile t = decode_halo(p, tile, BN);
@@ -838,7 +847,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
         if (++stage == C::NS) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 9) {   // ------------------------------------------------- MMA issuer
+  } else if (warp == W_MMA) {   // ------------------------------------------------- MMA issuer
     int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; int cur_key = -1; uint32_t bphase = 0;
     const uint32_t sB_addr = smem_u32(sB);
     // tap -> byte offset of its shifted view inside the haloed tile (warp-uniform, hoisted out of the tile loop)
@@ -872,7 +881,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       }
       if (elect_one()) tc_commit(&tfull[as]);
       __syncwarp();
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == NG) { as = 0; aphase ^= 1; }
     }
   } else {                 // ------------------------------------------------ epilogue groups
     const int as = warp >> 2; uint32_t aphase = 0;
@@ -884,7 +893,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
     int red_key = -1;
     if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
     uint32_t xph0 = 0, xph1 = 0; bool x_first = true;
-    for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
+    for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += NG * gridDim.x) {
       const HaloTile h = decode_halo(p, tile, BN);
       TileCoord t; t.n0 = h.n0; t.x0 = h.x0; t.y0 = h.y0; t.b0 = h.b0;
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0;
@@ -897,7 +906,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
       uint8_t* stg = stg_base + (as * C::NSTG + buf) * STG_BYTES;   // alternate staging tiles per tile
       if (p.x_tma && r == 0) {                // saved-activation tiles: requested one turn ahead (see conv_tc_kernel); NSTG == 2 (host guarantee)
         if (x_first) { mbar_arrive_expect_tx(&xbar[as * 2 + buf], p.x_bytes); tma_load_4d(&p.xmap, &xbar[as * 2 + buf], stg, t.n0, t.x0, t.y0, t.b0); }
-        const int next = tile + 2 * gridDim.x;
+        const int next = tile + NG * gridDim.x;
         if (next < p.total_tiles) {
           const HaloTile hn = decode_halo(p, next, BN);
           tma_store_wait_read<0>();
@@ -933,7 +942,7 @@ __global__ void __launch_bounds__(320, 1) conv_halo_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == W_PROD) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
@@ -1027,16 +1036,16 @@ static int launch2(const Params& p, int grid, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, int KC, int BK, int NSTG_>
+template <int BN, int KC, int BK, int NSTG_, int NG_>
 static int launch_halo(const Params& p, int grid, cudaStream_t st) {
-  using C = HaloCfg<BN, KC, BK, NSTG_>;
+  using C = HaloCfg<BN, KC, BK, NSTG_, NG_>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, KC, BK, NSTG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, KC, BK, NSTG_, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc(halo): cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_halo_kernel<BN, KC, BK, NSTG_><<<grid, 320, C::SMEM, st>>>(p);
+  conv_halo_kernel<BN, KC, BK, NSTG_, NG_><<<grid, C::THREADS, C::SMEM, st>>>(p);
   MGF_CHECK_LAUNCH("conv_tc(halo)");
   return 0;
 }
@@ -1044,6 +1053,7 @@ static int launch_halo(const Params& p, int grid, cudaStream_t st) {
 static bool g_halo_enabled = true;
 static bool g_halo_phases = false;  // halo kernel also for multi-phase (up-convolution) launches; default: those run as one wide tile per pixel block
 static bool g_cg2_enabled = true;     // CTA-pair (cta_group::2) kernel for the wide tiles (A/B switch: mgf_conv_tc_set_halo bit 4 disables it)
+static int g_halo_groups = 3;      // epilogue groups of the halo kernel (A/B switch: mgf_conv_tc_set_halo bit 5 selects 2)
 static int g_dbg = 0;             // experiment switches copied into Params::dbg (mgf_conv_tc_set_halo bits 8..10)
 static int g_halo_nstg = 1;        // epilogue staging tiles per group in the halo kernel (A/B switch: mgf_conv_tc_set_halo(1 | 2 << 1))
 
@@ -1051,13 +1061,14 @@ static int g_halo_nstg = 1;        // epilogue staging tiles per group in the ha
 }  // namespace mgf
 
 extern "C" int mgf_conv_tc_set_halo(int mode) {
-  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2); bit 3: halo kernel for multi-phase launches too; bit 4: disable the CTA-pair kernel
+  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2); bit 3: halo kernel for multi-phase launches too; bit 4: disable the CTA-pair kernel; bit 5: two epilogue groups in the halo kernel (default three); bits 8..13: experiment switches
   mgf::tc::g_halo_enabled = (mode & 1) != 0;
   const int n = (mode >> 1) & 3;
   mgf::tc::g_halo_nstg = (n == 2) ? 2 : 1;
   mgf::tc::g_halo_phases = (mode & 8) != 0;
   mgf::tc::g_cg2_enabled = (mode & 16) == 0;
-  mgf::tc::g_dbg = (mode >> 8) & 7;
+  mgf::tc::g_dbg = (mode >> 8) & 63;
+  mgf::tc::g_halo_groups = (mode & 32) ? 2 : 3;
   return 0;
 }
 
@@ -1161,7 +1172,12 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
     cudaStream_t st = (cudaStream_t)stream;
     const bool nstg2 = g_halo_nstg == 2 || p.x_tma;      // X tiles are prefetched into the second staging buffer
-#define MGF_HALO_CASE(bn, bk) if (HBN == bn && HBK == bk) return nstg2 ? launch_halo<bn, 1, bk, 2>(p, grid, st) : launch_halo<bn, 1, bk, 1>(p, grid, st);
+    // a third epilogue group pays when the per-tile tail is long (measured, scripts/bench_halo.py at 1024x512x64: noise+bias+lrelu 0.40 -> 0.34 ms,
+    // reduce+X 0.43 -> 0.41, VGG bias+ReLU 0.67 -> 0.65); a bare convert-and-store tail is MMA-bound with two (0.31 vs 0.32 ms)
+    const bool tail_work = p.noise || p.bias || p.act || p.X || p.reduce_out || p.add || p.scale_n;
+#define MGF_HALO_CASE(bn, bk) if (HBN == bn && HBK == bk) { \
+      if (g_halo_groups == 3 && tail_work) return nstg2 ? launch_halo<bn, 1, bk, 2, 3>(p, grid, st) : launch_halo<bn, 1, bk, 1, 3>(p, grid, st); \
+      return nstg2 ? launch_halo<bn, 1, bk, 2, 2>(p, grid, st) : launch_halo<bn, 1, bk, 1, 2>(p, grid, st); }
     MGF_HALO_CASE(64, 64) MGF_HALO_CASE(32, 64) MGF_HALO_CASE(64, 32) MGF_HALO_CASE(32, 32)
 #undef MGF_HALO_CASE
     MGF_FAIL(MGF_E_UNSUP, "conv_tc: no halo kernel for BN=%d KC=%d", HBN, KC);

@@ -52,9 +52,10 @@ want = sys.argv[1:]
 for name, fn in cases():
     if want and not any(w in name for w in want):
         continue
-    row = []
-    for dbg in (0, 1, 2, 4, 3, 5, 6):
-        L.mgf_conv_tc_set_halo(1 | (dbg << 8))
-        row.append("dbg%d %.3f" % (dbg, time_it(fn)))
-    L.mgf_conv_tc_set_halo(1)
-    print("%-22s %s ms" % (name, "  ".join(row)), flush=True)
+    for groups in (3, 2):
+        row = []
+        for dbg in (0, 2, 5, 6):
+            L.mgf_conv_tc_set_halo(1 | (32 if groups == 2 else 0) | (dbg << 8))
+            row.append("dbg%d %.3f" % (dbg, time_it(fn)))
+        L.mgf_conv_tc_set_halo(1)
+        print("%-20s groups%d %s ms" % (name, groups, "  ".join(row)), flush=True)
