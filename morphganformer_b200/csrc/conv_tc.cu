@@ -185,17 +185,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int NG_ = 2>
 struct Cfg {
+  static constexpr int NG = NG_;                          // epilogue groups = accumulator stages in TMEM
+  static constexpr int THREADS = 64 + 128 * NG;
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTG = (BN <= 64) ? 2 : 1;        // staging tiles per epilogue group (double-buffered when a tile is one group)
-  static constexpr int STAGES_RAW = (SMEM_BUDGET - (NSTG - 1) * 2 * STG_BYTES) / STAGE;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - (NG * NSTG - 2) * STG_BYTES - (NG - 2) * 2048) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 20 ? 20 : STAGES_RAW;
-  static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
-  static constexpr int SMEM = STAGES * STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + BAR_BYTES;
-  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 * NG) * 8 + 16;
+  static constexpr int SMEM = STAGES * STAGE + NG * NSTG * STG_BYTES + NG * RACC * 4 + BAR_BYTES;
+  static constexpr uint32_t TMEM_COLS = NG * BN <= 32 ? 32 : NG * BN <= 64 ? 64 : NG * BN <= 128 ? 128 : NG * BN <= 256 ? 256 : 512;
+  static_assert(NG * BN <= 512, "accumulator stages must fit the 512 TMEM columns");
+  static_assert(SMEM <= 227 * 1024, "shared-memory carve-up exceeds the 227 KB a CTA may opt into");
   // instruction descriptor (InstrDescriptor): D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A/B, N>>3 at 17, M>>4 at 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
@@ -407,29 +411,30 @@ __device__ __forceinline__ void flush_reduce(const Params& p, float* racc, int k
   group_sync(group);
 }
 
-template <int BN, int BK, bool G32 = false>     // G32: staged output groups are 32 columns wide (32-channel phases inside a wider tile)
-__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ Params p) {
-  using C = Cfg<BN, BK>;
+template <int BN, int BK, bool G32 = false, int NG_ = 2>     // G32: staged output groups are 32 columns wide (32-channel phases inside a wider tile); NG_: epilogue groups
+__global__ void __launch_bounds__(64 + 128 * NG_, 1) conv_tc_kernel(const __grid_constant__ Params p) {
+  using C = Cfg<BN, BK, NG_>;
+  constexpr int NG = NG_, W_PROD = 4 * NG_, W_MMA = 4 * NG_ + 1;
   constexpr int GW32 = (BN >= 64 && !G32) ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];                      // swizzled tiles need 1024-byte aligned bases
   uint8_t* stg_base = smem + C::STAGES * C::STAGE;                       // 2 x 16 KB epilogue staging, 1024-byte aligned
-  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * C::NSTG * STG_BYTES); // 2 x 256 floats: per-group d(style) partial sums
-  uint64_t* full = reinterpret_cast<uint64_t*>(racc_base + 2 * RACC);
+  float* racc_base = reinterpret_cast<float*>(stg_base + NG * C::NSTG * STG_BYTES); // NG x 256 floats: per-group d(style) partial sums
+  uint64_t* full = reinterpret_cast<uint64_t*>(racc_base + NG * RACC);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* xbar = tempty + 2;                 // [group][staging buffer]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
+  uint64_t* tempty = tfull + NG;
+  uint64_t* xbar = tempty + NG;                // [group][staging buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2 * NG);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
-    for (int s = 0; s < 4; s++) mbar_init(&xbar[s], 1);
+    for (int s = 0; s < NG; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2 * NG; s++) mbar_init(&xbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == W_PROD) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const int iters = p.kchunks * p.ntaps;
 
-  if (warp == 8) {     // ------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+  if (warp == W_PROD) {     // ------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BN);
@@ -461,7 +466,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         }
       }
     }
-  } else if (warp == 9) {   // ------------------------------------------------- MMA issuer (whole warp loops, one lane issues)
+  } else if (warp == W_MMA) {   // ------------------------------------------------- MMA issuer (whole warp loops, one lane issues)
     int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[as], aphase ^ 1);
@@ -489,7 +494,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
       }
       if (elect_one()) tc_commit(&tfull[as]); // accumulator complete -> epilogue
       __syncwarp();
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == NG) { as = 0; aphase ^= 1; }
     }
   } else {                 // ------------------------------------------------ epilogue: two groups of 4 warps, group g owns accumulator stage g
     const int as = warp >> 2; uint32_t aphase = 0;
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     int red_key = -1;
     if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
     uint32_t xph0 = 0, xph1 = 0; bool x_first = true;
-    for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
+    for (int tile = blockIdx.x + as * gridDim.x; tile < p.total_tiles; tile += NG * gridDim.x) {
       const TileCoord t = decode_tile(p, tile, BN);
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
       const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         // The tile of the group's NEXT turn is requested now, a whole epilogue ahead, so its DRAM latency is off the critical path
         // (requesting it at the start of its own turn left ~2000 cycles of latency exposed per tile: the kernel was epilogue-bound).
         if (x_first) { mbar_arrive_expect_tx(&xbar[as * 2 + buf], p.x_bytes); tma_load_4d(&p.xmap, &xbar[as * 2 + buf], stg, t.n0, t.x0, t.y0, t.b0); }
-        const int next = tile + 2 * gridDim.x;
+        const int next = tile + NG * gridDim.x;
         if (next < p.total_tiles) {
           const TileCoord tn = decode_tile(p, next, BN);
           tma_store_wait_read<0>();             // the previous turn's TMA store has finished reading the other staging buffer
@@ -555,7 +560,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == W_PROD) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
@@ -1008,16 +1013,16 @@ static int encode_x_map(Params& p, const mgf_conv_tc_desc* d, int BN, int TW, in
   return 0;
 }
 
-template <int BN, int BK, bool G32 = false>
+template <int BN, int BK, bool G32 = false, int NG = 2>
 static int launch(const Params& p, int grid, cudaStream_t st) {
-  using C = Cfg<BN, BK>;
+  using C = Cfg<BN, BK, NG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, G32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, G32, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc: cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_tc_kernel<BN, BK, G32><<<grid, 320, C::SMEM, st>>>(p);
+  conv_tc_kernel<BN, BK, G32, NG><<<grid, C::THREADS, C::SMEM, st>>>(p);
   MGF_CHECK_LAUNCH("conv_tc");
   return 0;
 }
@@ -1269,6 +1274,23 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     if (BN == 128 && BK == 64) return launch2<128, 64>(q, g2, st);
     if (BN == 256 && BK == 32) return launch2<256, 32>(q, g2, st);
     if (BN == 128 && BK == 32) return launch2<128, 32>(q, g2, st);
+  }
+  // narrow tiles with a long per-tile tail: three epilogue groups (see conv_halo_kernel); wide tiles keep two (TMEM holds two 256-column stages)
+  const bool tail_work = p.noise || p.bias || p.act || p.X || p.reduce_out || p.add || p.scale_n;
+  if (g_halo_groups == 3 && tail_work && BN <= 128) {
+    if (g32) {
+      if (BN == 128 && BK == 64) return launch<128, 64, true, 3>(p, grid, st);
+      if (BN == 128 && BK == 32) return launch<128, 32, true, 3>(p, grid, st);
+      if (BN == 64 && BK == 64) return launch<64, 64, true, 3>(p, grid, st);
+      if (BN == 64 && BK == 32) return launch<64, 32, true, 3>(p, grid, st);
+    } else {
+      if (BN == 128 && BK == 64) return launch<128, 64, false, 3>(p, grid, st);
+      if (BN == 64 && BK == 64) return launch<64, 64, false, 3>(p, grid, st);
+      if (BN == 32 && BK == 64) return launch<32, 64, false, 3>(p, grid, st);
+      if (BN == 128 && BK == 32) return launch<128, 32, false, 3>(p, grid, st);
+      if (BN == 64 && BK == 32) return launch<64, 32, false, 3>(p, grid, st);
+      if (BN == 32 && BK == 32) return launch<32, 32, false, 3>(p, grid, st);
+    }
   }
   if (g32) {
     if (BN == 128 && BK == 64) return launch<128, 64, true>(p, grid, st);

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256, 2) vgg_conv1_fwd_kernel(const float* __re
       const bool interior = in && hy >= 1 && hy <= FTH && hx >= 1 && hx <= FTW;
       const long long o = c * HW + (long long)y * R + x;
       vi[k] = in ? __ldg(ib + o) : 0.f;
-      vt[k] = (interior && tb) ? __ldg(tb + o) : vi[k];          // outside the interior: a zero difference
+      vt[k] = (interior && tb) ? __ldg(tb + o) : 0.f;           // two independent predicated loads: nothing here may wait on vi[k] (the
+                                                                // consumer decides whether the pair enters the MSE sum)
     }
   };
   if ((long long)blockIdx.x < (long long)ntiles) fetch(blockIdx.x);
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(256, 2) vgg_conv1_fwd_kernel(const float* __re
     if (e < FNE) {
       const bool in = y >= 0 && y < R && x >= 0 && x < R;
       sx[c * FPL + hy * FSW + hx] = in ? (vi[k] - v_shift[c]) * (1.f / v_scale[c]) : 0.f;
-      const float d = vi[k] - vt[k];
+      const bool interior = in && hy >= 1 && hy <= FTH && hx >= 1 && hx <= FTW;
+      const float d = (interior && target) ? vi[k] - vt[k] : 0.f;
       mse_local = fmaf(d, d, mse_local);
     }
   }
