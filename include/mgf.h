@@ -169,6 +169,12 @@ int mgf_fir4(const void* in, void* out, const float* fk4, float gain, int off, i
              float alpha, float act_gain, void* stream);
 int mgf_fir4_pad(const void* dy, void* g, const float* fk4, float gain, int B, int H, int W, int C, void* stream);
 int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
+/* 1x1 convolution with shared weights (the resnet-skip Conv2dLayer, reference training/networks.py:245-250 with kernel_size 1 as called from
+ * SynthesisBlock.forward :1157-1160, and its input gradient): out[p, n] = sum_k x[p, k] w[n, k] over P pixels of NHWC 16-bit tensors;
+ * w [N, K] is the layout of a [1, 1, N, K] mgf_conv_tc weight tensor.  is_fwd != 0: forward tensors (forward dtype, fp16 stores tracked by the
+ * overflow flag); 0: bf16 gradients.  K in {32, 64, 128, 256}, N a multiple of 32 (mgf_pointwise_supported tells); else MGF_E_UNSUP. */
+int mgf_pointwise(const void* x, const void* w, void* out, int64_t P, int K, int N, int is_fwd, void* stream);
+int mgf_pointwise_supported(int K, int N);
 int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
 
 /* ---- fused duplex attention layer (attention.cu): TransformerLayer.forward (networks.py:748-822, default GANformer config)

@@ -42,6 +42,8 @@ SIGNATURES = {
                          c_float, c_float, c_void_p]),
     "mgf_fir4_pad": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_upfir2_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_pointwise": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "mgf_pointwise_supported": (c_int, [c_int, c_int]),
     "mgf_upfir2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
     "mgf_attn_fwd": (c_int, [c_void_p] * 9 + [c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
     "mgf_attn_bwd": (c_int, [c_void_p] * 10 + [c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),

@@ -29,6 +29,7 @@ SQRT_HALF = math.sqrt(0.5)
 import os as _os
 BWD_SIDE_REDUCTIONS = _os.environ.get("MGF_BWD_SIDE", "1") != "0"      # A/B switch: d(style) reductions on the side stream
 LRELU_ALPHA = 0.2
+POINTWISE_SKIP = _os.environ.get("MGF_POINTWISE_SKIP", "1") != "0"     # A/B switch: resnet-skip 1x1 convolutions on the streaming pointwise kernel
 TWO_STAGE_MAX_RES = int(_os.environ.get("MGF_TWO_STAGE_MAX_RES", "65536"))   # A/B switch: up-conv dgrad as FIR + 9-tap strided conv up to this output size
 # A/B switches: up-conv forward as transposed conv (9 taps over four parity GEMMs) + FIR pass for output sizes in [MIN, MAX]; above MAX the
 # FIR-folded four-phase form runs in ONE tile per pixel block (BN = 4 * Cout columns, activation tiles fetched once for the four phases)
@@ -491,7 +492,10 @@ class SynthesisEngine:
                     O, I = e["conv0"].O, e["conv0"].I
                     h = x_in.shape[1]
                     v = self._buf(st, f"v{r}", (B, h, h, O), fwd=True)
-                    tc.conv_tc([x_in], self._skip_f(e), [(0, 0, 0, 0)], (B, h, h), 1, O, v, tag="g.fwd")
+                    if POINTWISE_SKIP and _L().mgf_pointwise_supported(I, O):      # HBM-bound levels: streaming mma.sync kernel (pointwise.cu)
+                        _lib.check(_L().mgf_pointwise(_p(x_in), _p(self._skip_f(e)), _p(v), B * h * h, I, O, 1, _s(self.dev)), "mgf_pointwise")
+                    else:
+                        tc.conv_tc([x_in], self._skip_f(e), [(0, 0, 0, 0)], (B, h, h), 1, O, v, tag="g.fwd")
                     x = self._buf(st, f"xout{r}", (B, r, r, O), fwd=True)
                     _lib.check(_L().mgf_upfir2_add(_p(v), _p(z1), _p(x), e["fk4"], e["skip_gain"], B, h, h, O, _s(self.dev)), "mgf_upfir2_add")
                 else:
@@ -702,7 +706,10 @@ class SynthesisEngine:
             gprev = self._buf(st, f"g{r // 2}", tuple(x_in.shape))
             if resnet:
                 main.wait_event(ev_dv)                         # the FIR adjoint of the skip branch ran beside conv1's backward
-                tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd", fwd=False)
+                if POINTWISE_SKIP and _L().mgf_pointwise_supported(L0.O, L0.I):
+                    _lib.check(_L().mgf_pointwise(_p(dv), _p(e["skip_b"]), _p(gs), B * h * h, L0.O, L0.I, 0, _s(self.dev)), "mgf_pointwise")
+                else:
+                    tc.conv_tc([dv], e["skip_b"], [(0, 0, 0, 0)], (B, h, h), 1, L0.I, gs, tag="g.bwd", fwd=False)
             ds0 = self._dgrad(L0, dy0, st, B, gprev, add=gs)
             self._style_bwd(L0, ds0, R0, st, dws, B)
             g = gprev
