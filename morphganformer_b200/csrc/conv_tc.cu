@@ -1121,7 +1121,7 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
   // resident weights for many tiles
   // (measured: a win for C = 64 -- 0.95 -> 0.68 ms on 64->64 @1024^2 x8 -- but not for C = 128, where the generic kernel's
   // 128-wide N tile beats two 64-wide halo passes; scripts/bench_conv_tc.py)
-  bool halo = g_halo_enabled && !ph_taps && (d->phases == 1 || g_halo_phases) && d->n_a == 1 && d->ntaps == 9 && (Cc == 64 || Cc == 32) && d->bn == 0 && d->GW >= 16 &&
+  bool halo = g_halo_enabled && !ph_taps && (d->phases == 1 || g_halo_phases) && d->n_a == 1 && d->ntaps == 9 && (Cc == 64 || Cc == 32 || (Cc == 128 && d->Cout == 64)) && d->bn == 0 && d->GW >= 16 &&
               (long long)d->GH * d->GW >= 256LL * 256 && (per_sample || d->w_G == 1);
   if (halo) {
     int seen = 0;
@@ -1133,8 +1133,10 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     if (seen != 0x1FF) halo = false;
   }
   if (halo) {
-    const int KC = 1;
-    const int HBK = (int)Cc;                      // 64 (128B-swizzled rows) or 32 (64B-swizzled rows)
+    // 128 -> 64 channels (the input gradient of VGG conv2_1): two 64-channel chunks per tile, 147 KB of resident weights, two activation
+    // stages, one staging tile per group (so the saved activation, if any, is read per thread instead of by TMA)
+    const int KC = (Cc == 128) ? 2 : 1;
+    const int HBK = (Cc == 128) ? 64 : (int)Cc;   // 64 (128B-swizzled rows) or 32 (64B-swizzled rows)
     int HBN = (d->Cout % 64 == 0) ? 64 : 32;
     p.TW = 8; p.TH = 16; p.TB = 1; p.rows = 128;
     p.NB = d->NB; p.GH = d->GH; p.GW = d->GW;
@@ -1173,9 +1175,10 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     p.out_f16 = f16 && d->out_fwd; p.x_f16 = f16 && d->x_fwd; p.add_f16 = f16 && d->add_fwd;
     p.ovf = p.out_f16 ? overflow_flag() : nullptr;
     if (int e = encode_out_maps(p, d, HBN, 8, 16, 1)) return e;
-    if (int e = encode_x_map(p, d, HBN, 8, 16, 1, 128)) return e;
+    if (KC == 1) { if (int e = encode_x_map(p, d, HBN, 8, 16, 1, 128)) return e; }
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
     cudaStream_t st = (cudaStream_t)stream;
+    if (KC == 2) return launch_halo<64, 2, 64, 1, 2>(p, grid, st);
     const bool nstg2 = g_halo_nstg == 2 || p.x_tma;      // X tiles are prefetched into the second staging buffer
     // a third epilogue group pays when the per-tile tail is long (measured, scripts/bench_halo.py at 1024x512x64: noise+bias+lrelu 0.40 -> 0.34 ms,
     // reduce+X 0.43 -> 0.41, VGG bias+ReLU 0.67 -> 0.65); a bare convert-and-store tail is MMA-bound with two (0.31 vs 0.32 ms)

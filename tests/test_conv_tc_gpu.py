@@ -119,7 +119,7 @@ def test_phase_output_and_multi_amap():
 @pytest.mark.parametrize("cfg", [
     # B, H, W, Cin, Cout
     (1, 256, 256, 64, 64), (2, 256, 256, 64, 64), (1, 256, 256, 64, 128), (1, 272, 264, 64, 32), (1, 256, 512, 64, 256),
-    (2, 256, 256, 32, 32), (1, 264, 272, 32, 64),
+    (2, 256, 256, 32, 32), (1, 264, 272, 32, 64), (1, 256, 256, 128, 64), (2, 264, 272, 128, 64),      # last two: two 64-channel chunks, resident weights
 ])
 def test_conv3x3_halo_variant(cfg):
     from morphganformer_b200 import tc, _lib
@@ -227,3 +227,25 @@ def test_cta_pair_kernel_equals_single_cta_kernel(cfg):
         _lib.lib().mgf_conv_tc_set_halo(1)
     assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max()
     _check(outs[0], ref)
+
+
+def test_halo_two_chunk_variant_with_saved_activation_mask():
+    """128 -> 64 channels through the two-chunk halo kernel with the ReLU mask of a saved activation in the tail (the shape of the input
+    gradient of VGG conv2_1 feeding conv1_2's ReLU backward): X is read per thread here (one staging tile per group), so halo and generic
+    kernels must agree exactly up to summation order."""
+    from morphganformer_b200 import tc, _lib
+    b, h, w, ci, co = 2, 256, 256, 128, 64
+    x = _bf(util.case_tensor((b, h, w, ci), 11))
+    wt = _bf(util.case_tensor((co, ci, 3, 3), 12) * (1.0 / np.sqrt(9 * ci)))
+    X = util.case_tensor((b, h, w, co), 13).to(_lib.forward_torch_dtype()).cuda()
+    outs = []
+    for halo in (1, 0):
+        _lib.lib().mgf_conv_tc_set_halo(halo)
+        out = torch.empty(b, h, w, co, dtype=torch.bfloat16, device="cuda")
+        tc.conv_tc([x.cuda()], tc.pack_w3x3(wt).to(torch.bfloat16).cuda(), tc.TAPS_3X3, (b, h, w), 1, co, out, X=X, actgrad=True, ag_alpha=0.0, fwd=False)
+        torch.cuda.synchronize()
+        outs.append(out)
+    _lib.lib().mgf_conv_tc_set_halo(1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1) * (X.float().cpu().permute(0, 3, 1, 2) > 0)
+    _check(outs[1], ref, "generic")
+    _check(outs[0], ref, "halo KC=2")
