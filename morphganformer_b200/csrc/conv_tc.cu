@@ -242,12 +242,15 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         if (p.X && (p.reduce_out || p.actgrad) && p.x_tma) mbar_wait(xbar, xphase);
         return;
       }
+      // phase / channel offset of the current 32-column chunk, advanced incrementally (a division per chunk showed up in an issue-bound tail)
+      int phase_idx = phase_lo, co = t.n0 - phase_lo * p.Cout - 32;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
-        const int col = t.n0 + c * 32;
-        const int phase_idx = col / p.Cout, co = col - phase_idx * p.Cout;
-        const long long oy = (long long)y * p.osy + p.ofy[phase_idx], ox = (long long)x * p.osx + p.ofx[phase_idx];
-        const long long obase = (((long long)b * p.OH + oy) * p.OW + ox) * p.OC + co;      // this chunk's 32 output channels of this pixel
+        co += 32;
+        if (co >= p.Cout) { co -= p.Cout; phase_idx++; }
+        // element offset of this chunk's 32 output channels of this pixel (only the per-thread X / residual loads need it)
+        const long long obase = (p.add || (p.X && !p.x_tma))
+            ? ((((long long)b * p.OH + ((long long)y * p.osy + p.ofy[phase_idx])) * p.OW + ((long long)x * p.osx + p.ofx[phase_idx])) * p.OC + co) : 0;
         uint32_t raw[32];
         tmem_ld32(tacc + (uint32_t)(c * 32), raw);
         if (c == BN / 32 - 1) {          // the accumulator now lives in registers: hand the TMEM stage back to the MMA issuer at once
@@ -271,24 +274,38 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
           // read this thread's row (same swizzle as the store path); the outputs later overwrite exactly the slots read here.
           if (c == 0) mbar_wait(xbar, xphase);
           const uint8_t* row = stg + r * (GX32 * 64);
+          uint32_t xw[16];
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const int j = (c % GX32) * 4 + q;
             const int pos = (GX32 == 2) ? (j ^ (r & 7)) : (j ^ ((r >> 1) & 3));
             const uint4 u = *reinterpret_cast<const uint4*>(row + pos * 16);
-            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+            xw[q * 4] = u.x; xw[q * 4 + 1] = u.y; xw[q * 4 + 2] = u.z; xw[q * 4 + 3] = u.w;
+          }
+          // warp-uniform branch on the storage type instead of both conversions and a select per pair
+          if (p.x_f16) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], p.x_f16); xv[q * 8 + e * 2] = valid ? f.x : 0.f; xv[q * 8 + e * 2 + 1] = valid ? f.y : 0.f; }
+            for (int e = 0; e < 16; e++) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xw[e])); xv[2 * e] = f.x; xv[2 * e + 1] = f.y; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) { const float2 f = unpack_bf16(xw[e]); xv[2 * e] = f.x; xv[2 * e + 1] = f.y; }
+          }
+          if (!valid) {          // rows past the tile's last pixel hold stale staging data
+#pragma unroll
+            for (int j = 0; j < 32; j++) xv[j] = 0.f;
           }
         } else if (needX) {
           if (valid) {
             const uint4* xp = reinterpret_cast<const uint4*>(p.X + obase);
+            uint32_t xw[16];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint4 u = __ldg(xp + q);
-              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+            for (int q = 0; q < 4; q++) { const uint4 u = __ldg(xp + q); xw[q * 4] = u.x; xw[q * 4 + 1] = u.y; xw[q * 4 + 2] = u.z; xw[q * 4 + 3] = u.w; }
+            if (p.x_f16) {
 #pragma unroll
-              for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], p.x_f16); xv[q * 8 + e * 2] = f.x; xv[q * 8 + e * 2 + 1] = f.y; }
+              for (int e = 0; e < 16; e++) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xw[e])); xv[2 * e] = f.x; xv[2 * e + 1] = f.y; }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; e++) { const float2 f = unpack_bf16(xw[e]); xv[2 * e] = f.x; xv[2 * e + 1] = f.y; }
             }
           } else {
 #pragma unroll
@@ -351,16 +368,21 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         if (p.add && valid) {
           const uint4* ap = reinterpret_cast<const uint4*>(p.add + obase);
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const uint4 u = __ldg(ap + q);
-            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+          uint32_t aw[16];
 #pragma unroll
-            for (int e = 0; e < 4; e++) { const float2 f = unpack16(w4[e], p.add_f16); v[q * 8 + e * 2] += f.x; v[q * 8 + e * 2 + 1] += f.y; }
+          for (int q = 0; q < 4; q++) { const uint4 u = __ldg(ap + q); aw[q * 4] = u.x; aw[q * 4 + 1] = u.y; aw[q * 4 + 2] = u.z; aw[q * 4 + 3] = u.w; }
+          if (p.add_f16) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&aw[e])); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) { const float2 f = unpack_bf16(aw[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
           }
         }
         if (p.actgrad) {
+          const float gpos = p.ag_gain, gneg = p.ag_alpha * p.ag_gain;
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] *= (xv[j] > 0.f ? 1.f : p.ag_alpha) * p.ag_gain;
+          for (int j = 0; j < 32; j++) v[j] *= (xv[j] > 0.f ? gpos : gneg);
         }
         // stage this thread's 32 outputs (64 B) into the swizzled shared-memory tile; a 64-channel group (or the whole tile for
         // BN = 32) then leaves with ONE TMA store: fully coalesced, asynchronous, clipped at the image border by the hardware.
@@ -380,11 +402,17 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const TileCoord& 
         }
         {
           uint8_t* row = stg_c + r * (GW32 * 64);
+          uint32_t pw[16];
+          if (p.out_f16) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) pw[e] = pack_f16_sat(v[2 * e], v[2 * e + 1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) pw[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+          }
 #pragma unroll
           for (int q = 0; q < 4; q++) {
-            uint4 u;
-            u.x = pack16(v[q * 8 + 0], v[q * 8 + 1], p.out_f16); u.y = pack16(v[q * 8 + 2], v[q * 8 + 3], p.out_f16);
-            u.z = pack16(v[q * 8 + 4], v[q * 8 + 5], p.out_f16); u.w = pack16(v[q * 8 + 6], v[q * 8 + 7], p.out_f16);
+            const uint4 u = make_uint4(pw[q * 4], pw[q * 4 + 1], pw[q * 4 + 2], pw[q * 4 + 3]);
             const int j = h * 4 + q;
             const int pos = (GW32 == 2) ? (j ^ (r & 7)) : (j ^ ((r >> 1) & 3));     // 128B / 64B swizzle, as the tensor map expects
             *reinterpret_cast<uint4*>(row + pos * 16) = u;
