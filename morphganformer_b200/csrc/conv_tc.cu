@@ -982,6 +982,194 @@ __global__ void __launch_bounds__(64 + 128 * NG_, 1) conv_halo_kernel(const __gr
   }
 }
 
+// ================================================================================================================
+// CTA-pair halo kernel (tcgen05.mma.cta_group::2): two CTAs of a cluster work on two neighbouring 8 x 16 tiles of the same (sample, N block);
+// CTA 0 issues one M = 256 MMA per (tap, k-step) that reads each CTA's own haloed activation tile and HALF of the resident weight tile
+// (BN / 2 rows) from each CTA's shared memory.  The N = 64 halo kernel is bound by the 128 B/clk shared-memory port (stage-isolation runs,
+// scripts/bench_halo.py: the 36 MMAs of a tile take 2260 cycles against a 1150-cycle tensor floor; operand reads 6 KB per MMA); in pair mode
+// the weight reads per SM halve (5 KB per MMA) and the resident weights shrink to 37 KB, which buys back activation stages.
+// Protocol as in conv_tc2_kernel: TMA completions of both CTAs are counted on CTA 0's barriers, CTA 0's MMA warp frees stages / publishes
+// accumulators in both CTAs with multicast commits, the epilogue groups of both CTAs arrive on CTA 0's `tempty`.
+template <int BN, int BK, int NSTG_, int NG_>
+struct Halo2Cfg {
+  static constexpr int A_BOX = 18 * HALO_PITCH * BK * 2;
+  static constexpr int A_STAGE = ((A_BOX + 1023) / 1024) * 1024;
+  static constexpr int B_TILE = (BN / 2) * BK * 2;                 // this CTA's half of one tap's weight tile
+  static constexpr int B_BYTES = 9 * B_TILE;
+  static constexpr int SMEM_MAX = 227 * 1024;
+  static constexpr int NSTG = NSTG_;
+  static constexpr int NG = NG_;
+  static constexpr int THREADS = 64 + 128 * NG;
+  static constexpr int NS_RAW = (SMEM_MAX - B_BYTES - NG * NSTG * STG_BYTES - NG * RACC * 4 - 1024) / A_STAGE;
+  static constexpr int NS = NS_RAW > 6 ? 6 : NS_RAW;
+  static constexpr int SMEM = B_BYTES + NS * A_STAGE + NG * NSTG * STG_BYTES + NG * RACC * 4 + 512;
+  static constexpr uint32_t TMEM_COLS = NG * BN <= 32 ? 32 : NG * BN <= 64 ? 64 : NG * BN <= 128 ? 128 : NG * BN <= 256 ? 256 : 512;
+  static_assert(NS >= 2 && NG * BN <= 512 && BN % 16 == 0, "pair halo kernel configuration");
+};
+
+template <int BN, int BK, int NSTG_, int NG_>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * NG_, 1) conv_halo2_kernel(const __grid_constant__ Params p) {
+  using C = Halo2Cfg<BN, BK, NSTG_, NG_>;
+  constexpr int NG = NG_;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + C::B_BYTES;
+  uint8_t* stg_base = sA + C::NS * C::A_STAGE;
+  float* racc_base = reinterpret_cast<float*>(stg_base + NG * C::NSTG * STG_BYTES);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(racc_base + NG * RACC);      // used in CTA 0 only
+  uint64_t* aempty = afull + C::NS;
+  uint64_t* bfull = aempty + C::NS;                                          // used in CTA 0 only
+  uint64_t* tfull = bfull + 1;
+  uint64_t* tempty = tfull + NG;                                             // used in CTA 0 only
+  uint64_t* xbar = tempty + NG;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2 * NG);
+  constexpr int W_PROD = 4 * NG, W_MMA = 4 * NG + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int pair_tiles = p.total_tiles >> 1;          // host: tiles per (sample, N block) are even, so the two tiles of a pair share the weights
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NS; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    mbar_init(bfull, 1);
+    for (int s = 0; s < NG; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
+    for (int s = 0; s < 2 * NG; s++) mbar_init(&xbar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == W_PROD) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == W_PROD) {     // ------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0; uint32_t phase = 0; int cur_key = -1; int last_stage = -1; uint32_t last_phase = 0;
+    for (int pt = cid; pt < pair_tiles; pt += nclusters) {
+      const HaloTile t = decode_halo(p, 2 * pt + rank, BN);
+      if (t.key != cur_key) {
+        if (last_stage >= 0) mbar_wait(&aempty[last_stage], last_phase);      // every MMA issued so far has read the resident weights
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(bfull, 2u * (uint32_t)C::B_BYTES);
+          const int wbase = p.per_sample ? t.b0 * p.w_T : 0;
+          for (int tp = 0; tp < 9; tp++)
+            tma_load_3d_2cta(&p.bmap, bfull, sB + tp * C::B_TILE, 0, t.n0 + rank * (BN / 2), wbase + p.taps[tp].wz);
+        }
+        __syncwarp();
+        cur_key = t.key;
+      }
+      mbar_wait(&aempty[stage], phase ^ 1);
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(&afull[stage], 2u * (uint32_t)C::A_BOX);
+        tma_load_4d_2cta(&p.amap[0], &afull[stage], sA + stage * C::A_STAGE, 0, t.x0 - 1, t.y0 - 1, t.b0);
+      }
+      __syncwarp();
+      last_stage = stage; last_phase = phase;
+      if (++stage == C::NS) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == W_MMA) {   // ------------------------------------------------- MMA issuer (CTA 0 only)
+    if (rank == 0) {
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; int cur_key = -1; uint32_t bphase = 0;
+      const uint32_t sB_addr = smem_u32(sB);
+      uint32_t tap_off[9];
+#pragma unroll
+      for (int tp = 0; tp < 9; tp++) tap_off[tp] = (uint32_t)(((p.taps[tp].dy + 1) * HALO_PITCH + p.taps[tp].dx + 1) * (BK * 2));
+      for (int pt = cid; pt < pair_tiles; pt += nclusters) {
+        const HaloTile t = decode_halo(p, 2 * pt, BN);
+        if (t.key != cur_key) { mbar_wait(bfull, bphase); bphase ^= 1; cur_key = t.key; }
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        mbar_wait(&afull[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(sA + stage * C::A_STAGE);
+#pragma unroll
+          for (int tp = 0; tp < 9; tp++) {
+            const uint64_t adesc = make_desc_halo<BK>(sa + tap_off[tp]);
+            const uint64_t bdesc = make_desc<BK>(sB_addr + (uint32_t)(tp * C::B_TILE));
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++)
+              tc_mma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (tp > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_2cta(&aempty[stage]);
+        }
+        __syncwarp();
+        if (++stage == C::NS) { stage = 0; phase ^= 1; }
+        if (elect_one()) tc_commit_2cta(&tfull[as]);
+        __syncwarp();
+        if (++as == NG) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {                 // ------------------------------------------------ epilogue groups (both CTAs)
+    const int as = warp >> 2; uint32_t aphase = 0;
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const int tx = r & 7, ty = r >> 3;
+    const float nstr = (p.noise && p.noise_strength) ? *p.noise_strength : 1.f;
+    float* racc = racc_base + as * RACC;
+    int red_key = -1;
+    if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
+    uint32_t xph0 = 0, xph1 = 0; bool x_first = true;
+    for (int pt = cid + as * nclusters; pt < pair_tiles; pt += NG * nclusters) {
+      const HaloTile h = decode_halo(p, 2 * pt + rank, BN);
+      TileCoord t; t.n0 = h.n0; t.x0 = h.x0; t.y0 = h.y0; t.b0 = h.b0;
+      const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0;
+      const bool valid = x < p.GW && y < p.GH;
+      if (p.reduce_out && h.key != red_key) {
+        if (red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
+        red_key = h.key;
+      }
+      const int buf = (C::NSTG == 2) ? (int)aphase : 0;
+      uint8_t* stg = stg_base + (as * C::NSTG + buf) * STG_BYTES;
+      if (p.x_tma && r == 0) {                // saved-activation tiles: requested one turn ahead; NSTG == 2 (host guarantee)
+        if (x_first) { mbar_arrive_expect_tx(&xbar[as * 2 + buf], p.x_bytes); tma_load_4d(&p.xmap, &xbar[as * 2 + buf], stg, t.n0, t.x0, t.y0, t.b0); }
+        const int next = pt + NG * nclusters;
+        if (next < pair_tiles) {
+          const HaloTile hn = decode_halo(p, 2 * next + rank, BN);
+          tma_store_wait_read<0>();
+          mbar_arrive_expect_tx(&xbar[as * 2 + (buf ^ 1)], p.x_bytes);
+          tma_load_4d(&p.xmap, &xbar[as * 2 + (buf ^ 1)], stg_base + (as * C::NSTG + (buf ^ 1)) * STG_BYTES, hn.n0, hn.x0, hn.y0, hn.b0);
+        }
+      }
+      x_first = false;
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.noise && valid) {
+        if (p.superpix) {
+          const float2 n2 = __ldg(reinterpret_cast<const float2*>(p.noise + (long long)b * p.noise_bstride + (long long)y * (2 * p.OW) + 2 * x));
+          nz[0] = n2.x * nstr; nz[1] = n2.y * nstr;
+        } else {
+          const int ph0 = t.n0 / p.Cout;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int ph = ph0 + k;
+            if (k == 0 || (k * p.Cout < BN && ph < 4))
+              nz[k] = __ldg(p.noise + (long long)b * p.noise_bstride + ((long long)y * p.osy + p.ofy[ph]) * p.OW + (long long)x * p.osx + p.ofx[ph]) * nstr;
+          }
+        }
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      epilogue_tile<BN, C::NSTG, (BN >= 64 ? 2 : 1)>(p, t, x, y, b, valid, tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(as * BN), lane, nz[0], nz[1], nz[2], nz[3],
+                                 stg, as, r, racc, &xbar[as * 2 + buf], buf ? xph1 : xph0, &tempty[as], rank != 0);
+      if (buf) xph1 ^= 1; else xph0 ^= 1;
+      aphase ^= 1;
+    }
+    if (p.reduce_out && red_key >= 0) flush_reduce<BN>(p, racc, red_key, as, r);
+    if (r == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync();                              // neither CTA may leave (or free its TMEM) while the pair's MMAs / remote arrivals are in flight
+  if (warp == W_PROD) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1083,6 +1271,25 @@ static int launch_halo(const Params& p, int grid, cudaStream_t st) {
   return 0;
 }
 
+template <int BN, int BK, int NSTG_, int NG_>
+static int launch_halo2(const Params& p, int grid, cudaStream_t st) {
+  using C = Halo2Cfg<BN, BK, NSTG_, NG_>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel<BN, BK, NSTG_, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc(halo pair): cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  conv_halo2_kernel<BN, BK, NSTG_, NG_><<<grid, C::THREADS, C::SMEM, st>>>(p);      // __cluster_dims__(2,1,1): grid is even
+  MGF_CHECK_LAUNCH("conv_tc(halo pair)");
+  return 0;
+}
+
+// CTA-pair halo kernel for the 64-channel layers: OFF by default (A/B switch: mgf_conv_tc_set_halo bit 6 enables it).  Measured on B200
+// (scripts/bench_halo.py, 8 images): it is correct (tests/test_conv_tc_gpu.py runs both) but SLOWER than the one-CTA kernel -- 1024^2 32-channel
+// forward 0.372 vs 0.333 ms, dgrad + reduction 0.402 vs 0.359, VGG conv1_2 0.669 vs 0.632: halving the weight reads (6 -> 5 KB per MMA) buys less
+// than the pair costs (every tile waits for the slower CTA's activation tile, accumulator hand-over and tail through cluster-scope barriers).
+static bool g_halo_pair = false;
 static bool g_halo_enabled = true;
 static bool g_halo_phases = false;  // halo kernel also for multi-phase (up-convolution) launches; default: those run as one wide tile per pixel block
 static bool g_cg2_enabled = true;     // CTA-pair (cta_group::2) kernel for the wide tiles (A/B switch: mgf_conv_tc_set_halo bit 4 disables it)
@@ -1094,7 +1301,7 @@ static int g_halo_nstg = 1;        // epilogue staging tiles per group in the ha
 }  // namespace mgf
 
 extern "C" int mgf_conv_tc_set_halo(int mode) {
-  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2); bit 3: halo kernel for multi-phase launches too; bit 4: disable the CTA-pair kernel; bit 5: two epilogue groups in the halo kernel (default three); bits 8..13: experiment switches
+  // bit 0: halo kernel on/off; bits 1..2: staging tiles per epilogue group (0 = default 1, else 1 or 2); bit 3: halo kernel for multi-phase launches too; bit 4: disable the CTA-pair kernel; bit 5: two epilogue groups in the halo kernel (default three); bit 6: enable the CTA-pair halo kernel (default off: slower); bits 8..13: experiment switches
   mgf::tc::g_halo_enabled = (mode & 1) != 0;
   const int n = (mode >> 1) & 3;
   mgf::tc::g_halo_nstg = (n == 2) ? 2 : 1;
@@ -1102,6 +1309,7 @@ extern "C" int mgf_conv_tc_set_halo(int mode) {
   mgf::tc::g_cg2_enabled = (mode & 16) == 0;
   mgf::tc::g_dbg = (mode >> 8) & 63;
   mgf::tc::g_halo_groups = (mode & 32) ? 2 : 3;
+  mgf::tc::g_halo_pair = (mode & 64) != 0;
   return 0;
 }
 
@@ -1207,6 +1415,19 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     int grid = num_sms(); if (grid > p.total_tiles) grid = p.total_tiles;
     cudaStream_t st = (cudaStream_t)stream;
     if (KC == 2) return launch_halo<64, 2, 64, 1, 2>(p, grid, st);
+    // CTA-pair kernel: 64 -> 64 channel tiles whose pair shares the weights (an even number of tiles per sample and N block)
+    if (g_halo_pair && HBN == 64 && HBK == 64 && p.tiles_hw % 2 == 0 && p.total_tiles >= 2 * num_sms() && !p.dbg) {
+      Params q = p;
+      q.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);
+      cuuint64_t dims[3] = {(cuuint64_t)d->w_K, (cuuint64_t)d->w_NT, (cuuint64_t)(d->w_G * d->w_T)};
+      cuuint64_t strides[2] = {(cuuint64_t)d->w_K * 2, (cuuint64_t)d->w_K * d->w_NT * 2};
+      cuuint32_t box[3] = {(cuuint32_t)HBK, (cuuint32_t)(HBN / 2), 1};
+      if (int e = encode(&q.bmap, d->w, 3, dims, strides, box, HBK)) return e;
+      const int g2 = (num_sms() / 2) * 2;
+      const bool tail3 = g_halo_groups == 3 && (p.noise || p.bias || p.act || p.X || p.reduce_out || p.add || p.scale_n);
+      if (p.x_tma || g_halo_nstg == 2) return tail3 ? launch_halo2<64, 64, 2, 3>(q, g2, st) : launch_halo2<64, 64, 2, 2>(q, g2, st);
+      return tail3 ? launch_halo2<64, 64, 1, 3>(q, g2, st) : launch_halo2<64, 64, 1, 2>(q, g2, st);
+    }
     const bool nstg2 = g_halo_nstg == 2 || p.x_tma;      // X tiles are prefetched into the second staging buffer
     // a third epilogue group pays when the per-tile tail is long (measured, scripts/bench_halo.py at 1024x512x64: noise+bias+lrelu 0.40 -> 0.34 ms,
     // reduce+X 0.43 -> 0.41, VGG bias+ReLU 0.67 -> 0.65); a bare convert-and-store tail is MMA-bound with two (0.31 vs 0.32 ms)

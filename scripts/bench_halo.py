@@ -1,6 +1,6 @@
 """Stage-isolation experiments on the halo convolution kernel (64-channel 3x3 layers at 512^2 / 1024^2): the same launch timed with the
 epilogue reduced to a TMEM drain (dbg 1), without MMAs (dbg 2), without activation loads (dbg 4), to see which stage bounds the tile rate.
-    python scripts/bench_halo.py [names...]"""
+    python scripts/bench_halo.py [--stages] [names...]       (without --stages: only the CTA-pair vs one-CTA comparison)"""
 import sys, os, math
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -48,9 +48,15 @@ def cases():
     yield "vgg1_2.bwd.X", lambda: tc.conv_tc([gv], wvb, tc.TAPS_3X3, (B, H, W), 1, 64, dv, X=xv, actgrad=True, ag_alpha=0.0, fwd=False, tag="x")
 
 
-want = sys.argv[1:]
+want = [a for a in sys.argv[1:] if not a.startswith("--")]
 for name, fn in cases():
     if want and not any(w in name for w in want):
+        continue
+    L.mgf_conv_tc_set_halo(1 | 64); t_pair = time_it(fn)
+    L.mgf_conv_tc_set_halo(1); t_single = time_it(fn)
+    L.mgf_conv_tc_set_halo(1)
+    print("%-20s CTA-pair kernel %.3f ms, one-CTA kernel %.3f ms" % (name, t_pair, t_single), flush=True)
+    if "--stages" not in sys.argv:
         continue
     for groups in (3, 2):
         row = []

@@ -249,3 +249,33 @@ def test_halo_two_chunk_variant_with_saved_activation_mask():
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1) * (X.float().cpu().permute(0, 3, 1, 2) > 0)
     _check(outs[1], ref, "generic")
     _check(outs[0], ref, "halo KC=2")
+
+
+@pytest.mark.parametrize("tail", ["plain", "fwd", "bwd"])
+def test_cta_pair_halo_kernel_equals_one_cta_halo_kernel(tail):
+    """The CTA-pair form of the halo kernel (tcgen05.mma.cta_group::2, half of the resident weights per CTA; off by default because it measured
+    slower, mgf_conv_tc_set_halo bit 6) against the one-CTA halo kernel on the same launch: identical arithmetic, so bit-identical outputs
+    (the d(style) reduction differs by atomic order only)."""
+    from morphganformer_b200 import tc, _lib
+    b, h, w, c = 2, 512, 256, 64
+    x = _bf(util.case_tensor((b, h, w, c), 21)).cuda()
+    wt = _bf(util.case_tensor((b, 9, c, c), 22) * (1.0 / np.sqrt(9 * c))).cuda()
+    bias = util.case_tensor((c,), 23).cuda()
+    X = util.case_tensor((b, h, w, c), 24).to(_lib.forward_torch_dtype()).cuda()
+    s2 = (util.case_tensor((b, c), 25).abs() + 0.5).cuda()
+    outs, reds = [], []
+    for mode in (1 | 64, 1):
+        _lib.lib().mgf_conv_tc_set_halo(mode)
+        out = torch.empty(b, h, w, c, dtype=torch.bfloat16, device="cuda")
+        red = torch.zeros(b, c, device="cuda")
+        if tail == "plain":
+            tc.conv_tc([x], wt, tc.TAPS_3X3, (b, h, w), 1, c, out, fwd=False)
+        elif tail == "fwd":
+            tc.conv_tc([x], wt, tc.TAPS_3X3, (b, h, w), 1, c, out, bias=bias, act=1, gain=1.4, fwd=False)
+        else:
+            tc.conv_tc([x], wt, tc.TAPS_3X3, (b, h, w), 1, c, out, scale_n=s2, reduce_out=red, X=X, actgrad=True, ag_gain=1.4, reduce_per_sample=True, fwd=False)
+        torch.cuda.synchronize()
+        outs.append(out); reds.append(red)
+    _lib.lib().mgf_conv_tc_set_halo(1)
+    assert torch.equal(outs[0], outs[1])
+    assert torch.allclose(reds[0], reds[1], rtol=1e-4, atol=1e-3)
