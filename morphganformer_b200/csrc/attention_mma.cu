@@ -285,9 +285,9 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(AttnMP p) {
 // Shared memory: sKhi, sKlo [16][C+32] (forward dtype) | sVr [16][C+32] bf16 (VM rows, for dA) | sVp uint2 [C/8][32] fp16 (ctl) |
 // sKp uint2 [C/8][32] bf16 (Kf, N-permuted, for dS Kf) | sm1, sb, sR [C] fp32 |
 // sP [128][24] bf16 (probabilities of the round, 48-byte rows) | sD [128][C/NH + 8] bf16 (dctl of the round, one channel group)
-// NH = number of channel groups the dVM phase is split into (2 above 256 channels: keeps the staging buffer at 67 KB).
+// NH = number of channel groups the dVM phase is split into (2 from 256 channels: keeps the staging buffer at 34 / 67 KB).
 constexpr int SPS = 24;
-__host__ __device__ inline int nh_of(int C) { return C > 256 ? 2 : 1; }
+__host__ __device__ inline int nh_of(int C) { return C >= 256 ? 2 : 1; }
 __host__ __device__ inline int drow(int C) { return C / nh_of(C) + 8; }
 static int bwd_smem(int C) { return 3 * NT * krow(C) * 2 + 2 * (C / 8) * 32 * 8 + 3 * C * 4 + 128 * SPS * 2 + 128 * drow(C) * 2; }
 
@@ -297,9 +297,11 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* ptr) {
 }
 
 template <bool F16, int C32>
-__global__ void __launch_bounds__(256, 1) attn_bwd_mma_kernel(AttnMP p) {
+// up to 256 channels two CTAs share an SM (88 KB of shared memory each at C = 256, 128 registers): the kernel is latency-bound, a second CTA doubles
+// the loads in flight
+__global__ void __launch_bounds__(256, (C32 <= 8) ? 2 : 1) attn_bwd_mma_kernel(AttnMP p) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  constexpr int NH = (C32 > 8) ? 2 : 1;
+  constexpr int NH = (C32 >= 8) ? 2 : 1;
   constexpr int JH = C32 / NH;                             // 32-channel chunks per channel group
   constexpr int NTG = JH * 4;                              // n-tiles (8 channels) per channel group
   constexpr int NTW = (NTG + 7) / 8;                       // n-tiles per warp in the dVM phase (1, 1, 2, 4, 3, 4 for C32 = 1..16)
@@ -609,7 +611,7 @@ extern "C" int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, cons
   if (int e = check_c(C, "attn_bwd")) return e;
   AttnMP p{}; p.X = X; p.dz = (const __nv_bfloat16*)dz; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm;
   p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.dmask = dmask; p.tabK = tabK; p.tabV = tabV; p.HW = HW; p.C = C; p.nbs = noise_bstride;
-  p.pix_per_cta = pix_per_cta(HW, B, 1);      // one wave of 1 CTA per SM
+  p.pix_per_cta = pix_per_cta(HW, B, C <= 256 ? 2 : 1);      // one wave: two CTAs per SM up to 256 channels, one above
   dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
   const int rc = fwd_f16() ? launch_bwd<true>(p, grid, bwd_smem(C), (cudaStream_t)stream) : launch_bwd<false>(p, grid, bwd_smem(C), (cudaStream_t)stream);
   if (rc) MGF_FAIL(MGF_E_SHAPE, "attn_bwd: unsupported C=%d", C);
