@@ -16,7 +16,7 @@ def _p(t):
 
 
 @pytest.mark.parametrize("fwd", ["fp16", "bf16"])
-@pytest.mark.parametrize("B,R", [(1, 16), (2, 40), (2, 64), (1, 200)])
+@pytest.mark.parametrize("B,R", [(1, 16), (2, 40), (2, 64), (1, 200), (2, 520)])      # last: ragged AND several tiles per persistent CTA (register prefetch path)
 def test_vgg_conv1_fwd_bwd(B, R, fwd):
     L = _lib.lib()
     _lib.set_forward_dtype(fwd)
