@@ -605,17 +605,20 @@ __global__ void __launch_bounds__(64 + 128 * NG_, 1) conv_tc_kernel(const __grid
 // Protocol: every CTA's TMA producer fills its own stage and counts the bytes on CTA 0's `full` barrier (cta_group::2 loads); CTA 0's MMA warp
 // frees a stage / publishes an accumulator in BOTH CTAs with multicast commits; the epilogue groups of both CTAs drain their own TMEM
 // and arrive on CTA 0's `tempty` barrier (256 arrivals).
-template <int BN, int BK>
+template <int BN, int BK, int NG_ = 2>
 struct Cfg2 {
+  static constexpr int NG = NG_;                         // epilogue groups = accumulator stages (three for BN = 128 launches with a fused tail)
+  static constexpr int THREADS = 64 + 128 * NG;
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the weight tile
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTG = 1;
-  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - (NG - 2) * (STG_BYTES + 2048)) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
-  static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
-  static constexpr int SMEM = STAGES * STAGE + 2 * NSTG * STG_BYTES + 2 * RACC * 4 + BAR_BYTES;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 * NG) * 8 + 16;
+  static constexpr int SMEM = STAGES * STAGE + NG * NSTG * STG_BYTES + NG * RACC * 4 + BAR_BYTES;
+  static constexpr uint32_t TMEM_COLS = NG * BN <= 256 ? 256 : 512;
+  static_assert(NG * BN <= 512 && SMEM <= 227 * 1024, "pair kernel configuration");
 };
 
 __device__ __forceinline__ TileCoord decode_pair(const Params& p, int pt, int rank, int BN) {
@@ -630,29 +633,30 @@ __device__ __forceinline__ TileCoord decode_pair(const Params& p, int pt, int ra
   return t;
 }
 
-template <int BN, int BK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tc2_kernel(const __grid_constant__ Params p) {
-  using C = Cfg2<BN, BK>;
+template <int BN, int BK, int NG_ = 2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * NG_, 1) conv_tc2_kernel(const __grid_constant__ Params p) {
+  using C = Cfg2<BN, BK, NG_>;
+  constexpr int NG = NG_, W_PROD = 4 * NG_, W_MMA = 4 * NG_ + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stg_base = smem + C::STAGES * C::STAGE;
-  float* racc_base = reinterpret_cast<float*>(stg_base + 2 * C::NSTG * STG_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(racc_base + 2 * RACC);     // used in CTA 0 only
+  float* racc_base = reinterpret_cast<float*>(stg_base + NG * C::NSTG * STG_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(racc_base + NG * RACC);    // used in CTA 0 only
   uint64_t* empty = full + C::STAGES;
   uint64_t* tfull = empty + C::STAGES;
-  uint64_t* tempty = tfull + 2;                                            // used in CTA 0 only
-  uint64_t* xbar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
+  uint64_t* tempty = tfull + NG;                                           // used in CTA 0 only
+  uint64_t* xbar = tempty + NG;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2 * NG);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
+    for (int s = 0; s < NG; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == W_PROD) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -663,7 +667,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tc2_ker
   const int iters = p.kchunks * p.ntaps;
   const int pair_tiles = p.total_tiles;        // host: number of PAIR tiles
 
-  if (warp == 8) {     // ------------------------------------------------------ TMA producer (both CTAs)
+  if (warp == W_PROD) {     // ------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0; uint32_t phase = 0;
     for (int pt = cid; pt < pair_tiles; pt += nclusters) {
       const TileCoord t = decode_pair(p, pt, rank, BN);
@@ -684,7 +688,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tc2_ker
         }
       }
     }
-  } else if (warp == 9) {   // ------------------------------------------------- MMA issuer (CTA 0 only)
+  } else if (warp == W_MMA) {   // ------------------------------------------------- MMA issuer (CTA 0 only)
     if (rank == 0) {
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
       for (int pt = cid; pt < pair_tiles; pt += nclusters) {
@@ -706,7 +710,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tc2_ker
         }
         if (elect_one()) tc_commit_2cta(&tfull[as]);
         __syncwarp();
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (++as == NG) { as = 0; aphase ^= 1; }
       }
     }
   } else {                 // ------------------------------------------------ epilogue (both CTAs): group g drains accumulator stage g
@@ -718,7 +722,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tc2_ker
     float* racc = racc_base + as * RACC;
     int red_key = -1;
     if (p.reduce_out) { for (int j = r; j < RACC; j += 128) racc[j] = 0.f; group_sync(as); }
-    for (int pt = cid + as * nclusters; pt < pair_tiles; pt += 2 * nclusters) {
+    for (int pt = cid + as * nclusters; pt < pair_tiles; pt += NG * nclusters) {
       const TileCoord t = decode_pair(p, pt, rank, BN);
       const int x = t.x0 + tx, y = t.y0 + ty, b = t.b0 + tb;
       const bool valid = (r < p.rows) && x < p.GW && y < p.GH && b < p.NB;
@@ -751,7 +755,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) conv_tc2_ker
   }
   tc_fence_before();
   cluster_sync();                              // neither CTA may leave (or free its TMEM) while the pair's MMAs / remote arrivals are in flight
-  if (warp == 8) {
+  if (warp == W_PROD) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
@@ -1243,16 +1247,16 @@ static int launch(const Params& p, int grid, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int NG = 2>
 static int launch2(const Params& p, int grid, cudaStream_t st) {
-  using C = Cfg2<BN, BK>;
+  using C = Cfg2<BN, BK, NG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, BK, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) MGF_FAIL((int)e, "conv_tc(2cta): cannot set %d bytes of dynamic shared memory: %s", C::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  conv_tc2_kernel<BN, BK><<<grid, 320, C::SMEM, st>>>(p);      // __cluster_dims__(2,1,1): grid is even
+  conv_tc2_kernel<BN, BK, NG><<<grid, C::THREADS, C::SMEM, st>>>(p);      // __cluster_dims__(2,1,1): grid is even
   MGF_CHECK_LAUNCH("conv_tc(2cta)");
   return 0;
 }
@@ -1522,6 +1526,9 @@ extern "C" int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream) {
     if (int e = encode(&q.bmap, d->w, 3, dims, strides, box, BK)) return e;
     q.tx_bytes = (uint32_t)((128 * BK + (BN / 2) * BK) * 2);
     int g2 = (num_sms() / 2) * 2; if (g2 > 2 * pairs) g2 = (int)(2 * pairs);
+    const bool tail3 = g_halo_groups == 3 && (p.noise || p.bias || p.act || p.X || p.reduce_out || p.add || p.scale_n);
+    if (BN == 128 && BK == 64 && tail3) return launch2<128, 64, 3>(q, g2, st);
+    if (BN == 128 && BK == 32 && tail3) return launch2<128, 32, 3>(q, g2, st);
     if (BN == 256 && BK == 64) return launch2<256, 64>(q, g2, st);
     if (BN == 128 && BK == 64) return launch2<128, 64>(q, g2, st);
     if (BN == 256 && BK == 32) return launch2<256, 32>(q, g2, st);
