@@ -128,8 +128,12 @@ typedef struct {
   int32_t phase_ntaps[4];
 } mgf_conv_tc_desc;
 int mgf_conv_tc(const mgf_conv_tc_desc* d, void* stream);
-/* debugging / A-B measurement: 0 disables the halo (shared-memory tap reuse) variant that mgf_conv_tc picks for C = 64/128 3x3 layers */
-int mgf_conv_tc_set_halo(int enabled);
+/* debugging / A-B measurement switches of mgf_conv_tc (process-wide; production value: 1).  Bit 0: halo (shared-memory tap reuse) kernel for the
+ * 64- / 32-channel and 128 -> 64 channel 3x3 layers; bits 1..2: staging tiles per epilogue group in the halo kernel (0 = automatic); bit 3: halo kernel
+ * for multi-phase launches too; bit 4: disable the CTA-pair (cta_group::2) kernel of the wide tiles; bit 5: two epilogue groups everywhere instead of
+ * three where the tile tail has work; bit 6: enable the CTA-pair halo kernel (correct but measured slower, off by default); bits 8..12: stage-isolation
+ * experiments of scripts/bench_halo.py (results are wrong while set). */
+int mgf_conv_tc_set_halo(int mode);
 
 /* ---- bf16 synthesis-engine helpers (engine_kernels.cu); activations NHWC bf16, coefficients fp32 ------------------
  * style_fwd : s[b,i] = ((wg[b,:] . A[i,:]) * again + abias[i]) * sgain  (FullyConnectedLayer affine, networks.py:138-150, :1022,
