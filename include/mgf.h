@@ -199,6 +199,9 @@ int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, const float* Sc
  * of tabK / of tabV per sample.  The tables depend on the forward dtype in effect when they were built. */
 int64_t mgf_attn_table_bytes(int which, int C);
 int mgf_attn_tables(const float* Kf, const float* VM, void* tabK, void* tabV, int B, int C, void* stream);
+/* A/B measurement switch (process-wide; default 1): 0 keeps the one-warp-per-pixel-tile backward kernel for every layer instead of the
+ * split-channel kernel (several warps per tile) that mgf_attn_bwd picks for the low-resolution 512-channel layers. */
+int mgf_attn_set_split(int enabled);
 
 /* ---- mapping network z -> ws and its backward wrt z (mapping.cu): training/networks.py MappingNetwork.forward :894-942 with the
  * GANformer-default configuration (16 local + 1 global latents x 32, 4 resnet blocks, latent self-attention, positional maps).

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mgf_attn_bwd": (c_int, [c_void_p] * 10 + [c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
     "mgf_attn_table_bytes": (c_int64, [c_int, c_int]),
     "mgf_attn_tables": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mgf_attn_set_split": (c_int, [c_int]),
     "mgf_lpips_prep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mgf_mapping_param_floats": (c_int, []),
     "mgf_mapping_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

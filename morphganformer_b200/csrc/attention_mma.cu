@@ -542,6 +542,313 @@ __global__ void __launch_bounds__(256, (C32 <= 8) ? 2 : 1) attn_bwd_mma_kernel(A
   if (p.R) for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&p.R[(long long)b * C + i], sR[i]);
 }
 
+// ------------------------------------------------------------------------------------------- backward, low-resolution layers
+// At 4^2 .. 32^2 a launch has only 8 .. 512 pixel tiles: one warp per 16-pixel x 512-channel tile is a 12 K-instruction dependent chain
+// (27-38 us per launch whatever the grid size, profiles/r02b_membound_ncu.md).  Here WPT warps share a tile, each owning C / WPT channels:
+// the score / norm partial sums and the dA / sdot partial sums are exchanged through shared memory (every warp adds the parts in the same order, so
+// all of them continue with bit-identical probabilities), everything else is per channel.  A CTA of 8 warps holds 8 / WPT tiles per round.
+template <int C32, int WPT>
+struct SplitCfg {
+  static constexpr int TPC = 8 / WPT;                  // tiles per CTA round
+  static constexpr int JW = C32 / WPT;                 // 32-channel chunks per warp
+  static constexpr int ROWS = TPC * 16;
+  static_assert(C32 % WPT == 0 && 8 % WPT == 0, "split-channel attention: WPT must divide the chunk count and the warp count");
+};
+template <int C32, int WPT>
+static int bwd_split_smem(int C) {
+  using S = SplitCfg<C32, WPT>;
+  return 3 * NT * krow(C) * 2 + 2 * (C / 8) * 32 * 8 + 3 * C * 4 + S::ROWS * SPS * 2 + S::ROWS * (C + 8) * 2 + 2 * 8 * 32 * 10 * 4;
+}
+
+__device__ __forceinline__ void tile_sync(int tile, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(tile + 1), "r"(nthreads) : "memory"); }
+
+template <bool F16, int C32, int WPT>
+__global__ void __launch_bounds__(256, 1) attn_bwd_split_kernel(AttnMP p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using S = SplitCfg<C32, WPT>;
+  constexpr int TPC = S::TPC, JW = S::JW, ROWS = S::ROWS;
+  constexpr int NTG = C32 * 4, NTW = NTG / 8;              // n-tiles (8 channels) in all, per warp in the dVM phase
+  constexpr int UJ = JW < 2 ? JW : 2;
+  const int C = p.C, KS = krow(C), DS = C + 8;
+  uint16_t* sKhi = reinterpret_cast<uint16_t*>(smraw);
+  uint16_t* sKlo = sKhi + NT * KS;
+  uint16_t* sVr = sKlo + NT * KS;
+  uint2* sVp = reinterpret_cast<uint2*>(sVr + NT * KS);
+  uint2* sKp = sVp + (C / 8) * 32;
+  float* sm1 = reinterpret_cast<float*>(sKp + (C / 8) * 32);
+  float* sb = sm1 + C;
+  float* sR = sb + C;
+  uint16_t* sP = reinterpret_cast<uint16_t*>(sR + C);
+  uint16_t* sD = sP + ROWS * SPS;
+  float* sRedA = reinterpret_cast<float*>(sD + ROWS * DS);  // [8 warps][32 lanes][10]: score / norm partial sums
+  float* sRedB = sRedA + 8 * 32 * 10;                       // same shape: dA / sdot partial sums
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int tl = warp / WPT, part = warp % WPT, j0 = part * JW;
+  const float* VMb = p.VM + (long long)b * NT * C;
+  __shared__ __align__(8) uint64_t tbar;
+  const bool bulk = p.tabK || p.tabV;
+  if (bulk && threadIdx.x == 0) {
+    tbar_init(&tbar);
+    tbar_expect(&tbar, (uint32_t)((p.tabK ? tabk_bytes(C) : 0) + (p.tabV ? tabv_bytes(C) : 0)));
+    if (p.tabK) {
+      bulk_copy(sKhi, p.tabK, (uint32_t)(2 * rows_bytes(C)), &tbar);
+      bulk_copy(sKp, reinterpret_cast<const unsigned char*>(p.tabK) + 2 * rows_bytes(C), (uint32_t)perm_bytes(C), &tbar);
+    }
+    if (p.tabV) bulk_copy(sVr, reinterpret_cast<const unsigned char*>(p.tabV) + (size_t)b * tabv_bytes(C), (uint32_t)tabv_bytes(C), &tbar);
+  }
+  if (!p.tabK) { fill_rowtable<F16>(sKhi, sKlo, p.Kf, C); fill_permtable<false>(sKp, p.Kf, C); }
+  if (!p.tabV) { fill_rowtable<false>(sVr, nullptr, VMb, C); fill_permtable<true>(sVp, VMb, C); }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sb[i] = p.bias ? p.bias[i] : 0.f; sm1[i] = 1.f + p.bm[i]; sR[i] = 0.f; }
+  __syncthreads();
+  if (bulk) tbar_wait(&tbar);
+  const float ns = (p.noise && p.nstr) ? *p.nstr : 0.f;
+  const long long p0 = (long long)blockIdx.x * p.pix_per_cta;
+  long long pend = p0 + p.pix_per_cta; if (pend > p.HW) pend = p.HW;
+  const float* mbr = p.mb + b * NT;
+  float dvm[NTW][4];
+#pragma unroll
+  for (int i = 0; i < NTW; i++) { dvm[i][0] = dvm[i][1] = dvm[i][2] = dvm[i][3] = 0.f; }
+
+  for (long long base = p0; base < pend; base += ROWS) {
+    const long long f0 = base + tl * 16;
+    const bool active = f0 < pend;                        // uniform over the WPT warps of a tile
+    uint16_t* myP = sP + tl * 16 * SPS;
+    uint16_t* myD = sD + (long long)tl * 16 * DS;
+    const long long r0 = f0 + g, r1 = f0 + g + 8;
+    const bool v0 = r0 < pend, v1 = r1 < pend;
+    const long long q0 = v0 ? r0 : pend - 1, q1 = v1 ? r1 : pend - 1;
+    const uint4* x0 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.X) + ((long long)b * p.HW + q0) * C);
+    const uint4* x1 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.X) + ((long long)b * p.HW + q1) * C);
+    const uint4* g0 = reinterpret_cast<const uint4*>(p.dz + ((long long)b * p.HW + q0) * C);
+    const uint4* g1 = reinterpret_cast<const uint4*>(p.dz + ((long long)b * p.HW + q1) * C);
+    float P[8], M[8], rn0 = 0.f, rn1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { M[i] = 1.f; P[i] = 0.f; }
+    uint32_t pa0 = 0, pa1 = 0, pa2 = 0, pa3 = 0;
+    float nz0 = 0.f, nz1 = 0.f;
+    const float gm0 = v0 ? p.gain : 0.f, gm1 = v1 ? p.gain : 0.f;
+    if (active) {
+      // ---- partial scores and squared norms over this warp's channels
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, ss0 = 0.f, ss1 = 0.f;
+#pragma unroll (UJ)
+      for (int jj = 0; jj < JW; jj++) {
+        const int j = j0 + jj;
+        const uint4 a = __ldg(x0 + j * 4 + t), bq = __ldg(x1 + j * 4 + t);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float2 fa = upk<F16>(aw[e]), fb = upk<F16>(bw[e]);
+          ss0 = fmaf(fa.x, fa.x, ss0); ss0 = fmaf(fa.y, fa.y, ss0);
+          ss1 = fmaf(fb.x, fb.x, ss1); ss1 = fmaf(fb.y, fb.y, ss1);
+        }
+        const int off = (j * 4 + t) * 8;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(sKhi + g * KS + off), h1 = *reinterpret_cast<const uint4*>(sKhi + (g + 8) * KS + off);
+        const uint4 l0 = *reinterpret_cast<const uint4*>(sKlo + g * KS + off), l1 = *reinterpret_cast<const uint4*>(sKlo + (g + 8) * KS + off);
+        mma16816<F16>(s0, a.x, bq.x, a.y, bq.y, h0.x, h0.y); mma16816<F16>(s0, a.z, bq.z, a.w, bq.w, h0.z, h0.w);
+        mma16816<F16>(s1, a.x, bq.x, a.y, bq.y, h1.x, h1.y); mma16816<F16>(s1, a.z, bq.z, a.w, bq.w, h1.z, h1.w);
+        mma16816<F16>(s0, a.x, bq.x, a.y, bq.y, l0.x, l0.y); mma16816<F16>(s0, a.z, bq.z, a.w, bq.w, l0.z, l0.w);
+        mma16816<F16>(s1, a.x, bq.x, a.y, bq.y, l1.x, l1.y); mma16816<F16>(s1, a.z, bq.z, a.w, bq.w, l1.z, l1.w);
+      }
+      ss0 = quad_sum(ss0); ss1 = quad_sum(ss1);
+      float* mine = sRedA + (warp * 32 + lane) * 10;
+      mine[0] = s0[0]; mine[1] = s0[1]; mine[2] = s0[2]; mine[3] = s0[3]; mine[4] = s1[0]; mine[5] = s1[1]; mine[6] = s1[2]; mine[7] = s1[3];
+      mine[8] = ss0; mine[9] = ss1;
+      tile_sync(tl, WPT * 32);
+      float tot[10];
+#pragma unroll
+      for (int i = 0; i < 10; i++) tot[i] = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPT; w++) {
+        const float* o = sRedA + ((tl * WPT + w) * 32 + lane) * 10;
+#pragma unroll
+        for (int i = 0; i < 10; i++) tot[i] += o[i];
+      }
+      rn0 = rsqrtf(tot[8] / (float)C + 1e-8f); rn1 = rsqrtf(tot[9] / (float)C + 1e-8f);
+      const float* sc0 = p.Sc + q0 * NT; const float* sc1 = p.Sc + q1 * NT;
+      const float2 ca0 = *reinterpret_cast<const float2*>(sc0 + 2 * t), ca1 = *reinterpret_cast<const float2*>(sc0 + 8 + 2 * t);
+      const float2 cb0 = *reinterpret_cast<const float2*>(sc1 + 2 * t), cb1 = *reinterpret_cast<const float2*>(sc1 + 8 + 2 * t);
+      const float2 m0 = *reinterpret_cast<const float2*>(mbr + 2 * t), m1 = *reinterpret_cast<const float2*>(mbr + 8 + 2 * t);
+      P[0] = tot[0] + ca0.x + m0.x; P[1] = tot[1] + ca0.y + m0.y; P[4] = tot[4] + ca1.x + m1.x; P[5] = tot[5] + ca1.y + m1.y;
+      P[2] = tot[2] + cb0.x + m0.x; P[3] = tot[3] + cb0.y + m0.y; P[6] = tot[6] + cb1.x + m1.x; P[7] = tot[7] + cb1.y + m1.y;
+      const float mx0 = quad_max(fmaxf(fmaxf(P[0], P[1]), fmaxf(P[4], P[5])));
+      const float mx1 = quad_max(fmaxf(fmaxf(P[2], P[3]), fmaxf(P[6], P[7])));
+      P[0] = __expf(P[0] - mx0); P[1] = __expf(P[1] - mx0); P[4] = __expf(P[4] - mx0); P[5] = __expf(P[5] - mx0);
+      P[2] = __expf(P[2] - mx1); P[3] = __expf(P[3] - mx1); P[6] = __expf(P[6] - mx1); P[7] = __expf(P[7] - mx1);
+      const float i0 = 1.f / quad_sum(P[0] + P[1] + P[4] + P[5]), i1 = 1.f / quad_sum(P[2] + P[3] + P[6] + P[7]);
+      P[0] *= i0; P[1] *= i0; P[4] *= i0; P[5] *= i0; P[2] *= i1; P[3] *= i1; P[6] *= i1; P[7] *= i1;
+      if (p.dmask) load_dmask(p.dmask + ((long long)b * p.HW + q0) * NT, p.dmask + ((long long)b * p.HW + q1) * NT, t, M);
+      float A[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) A[i] = P[i] * M[i];
+      pa0 = pk<true>(A[0], A[1]); pa1 = pk<true>(A[2], A[3]); pa2 = pk<true>(A[4], A[5]); pa3 = pk<true>(A[6], A[7]);
+      if (p.noise) { nz0 = p.noise[b * p.nbs + q0] * ns; nz1 = p.noise[b * p.nbs + q1] * ns; }
+      if (part == 0) {
+        *reinterpret_cast<uint32_t*>(myP + g * SPS + 2 * t) = pack_bf16(A[0], A[1]); *reinterpret_cast<uint32_t*>(myP + g * SPS + 8 + 2 * t) = pack_bf16(A[4], A[5]);
+        *reinterpret_cast<uint32_t*>(myP + (g + 8) * SPS + 2 * t) = pack_bf16(A[2], A[3]); *reinterpret_cast<uint32_t*>(myP + (g + 8) * SPS + 8 + 2 * t) = pack_bf16(A[6], A[7]);
+      }
+    }
+    float dA0[4] = {0.f, 0.f, 0.f, 0.f}, dA1[4] = {0.f, 0.f, 0.f, 0.f}, sd0 = 0.f, sd1 = 0.f;
+    if (active) {
+      // ---- pass B over this warp's channels: ctl, du, dctl -> partial dA and sdot; dctl staged for the dVM phase
+#pragma unroll (UJ)
+      for (int jj = 0; jj < JW; jj++) {
+        const int j = j0 + jj;
+        const uint4 a = __ldg(x0 + j * 4 + t), bq = __ldg(x1 + j * 4 + t);
+        const uint4 ga = __ldg(g0 + j * 4 + t), gb = __ldg(g1 + j * 4 + t);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w};
+        const uint32_t gaw[4] = {ga.x, ga.y, ga.z, ga.w}, gbw[4] = {gb.x, gb.y, gb.z, gb.w};
+        const int ch = (j * 4 + t) * 8;
+        const float4 m1a = *reinterpret_cast<const float4*>(sm1 + ch), m1b = *reinterpret_cast<const float4*>(sm1 + ch + 4);
+        const float4 ba = *reinterpret_cast<const float4*>(sb + ch), bb = *reinterpret_cast<const float4*>(sb + ch + 4);
+        const float m1v[8] = {m1a.x, m1a.y, m1a.z, m1a.w, m1b.x, m1b.y, m1b.z, m1b.w};
+        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        uint32_t dc0[4], dc1[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          float acc[4] = {m1v[2 * m], m1v[2 * m + 1], m1v[2 * m], m1v[2 * m + 1]};
+          const uint2 vb = sVp[(j * 4 + m) * 32 + lane];
+          mma16816<true>(acc, pa0, pa1, pa2, pa3, vb.x, vb.y);
+          const float2 xa = upk<F16>(aw[m]), xb = upk<F16>(bw[m]);
+          const float2 da = unpack_bf16(gaw[m]), db = unpack_bf16(gbw[m]);
+          const float xn0 = xa.x * rn0, xn1 = xa.y * rn0, xn2 = xb.x * rn1, xn3 = xb.y * rn1;
+          const float du0 = da.x * gm0 * ((xn0 * acc[0] + nz0 + bv[2 * m]) > 0.f ? 1.f : p.alpha);
+          const float du1 = da.y * gm0 * ((xn1 * acc[1] + nz0 + bv[2 * m + 1]) > 0.f ? 1.f : p.alpha);
+          const float du2 = db.x * gm1 * ((xn2 * acc[2] + nz1 + bv[2 * m]) > 0.f ? 1.f : p.alpha);
+          const float du3 = db.y * gm1 * ((xn3 * acc[3] + nz1 + bv[2 * m + 1]) > 0.f ? 1.f : p.alpha);
+          dc0[m] = pack_bf16(du0 * xn0, du1 * xn1); dc1[m] = pack_bf16(du2 * xn2, du3 * xn3);
+          sd0 = fmaf(du0 * acc[0], xa.x, sd0); sd0 = fmaf(du1 * acc[1], xa.y, sd0);
+          sd1 = fmaf(du2 * acc[2], xb.x, sd1); sd1 = fmaf(du3 * acc[3], xb.y, sd1);
+        }
+        const int off = (j * 4 + t) * 8;
+        const uint4 w0 = *reinterpret_cast<const uint4*>(sVr + g * KS + off), w1 = *reinterpret_cast<const uint4*>(sVr + (g + 8) * KS + off);
+        mma16816<false>(dA0, dc0[0], dc1[0], dc0[1], dc1[1], w0.x, w0.y); mma16816<false>(dA0, dc0[2], dc1[2], dc0[3], dc1[3], w0.z, w0.w);
+        mma16816<false>(dA1, dc0[0], dc1[0], dc0[1], dc1[1], w1.x, w1.y); mma16816<false>(dA1, dc0[2], dc1[2], dc0[3], dc1[3], w1.z, w1.w);
+        *reinterpret_cast<uint4*>(myD + g * DS + off) = make_uint4(dc0[0], dc0[1], dc0[2], dc0[3]);
+        *reinterpret_cast<uint4*>(myD + (g + 8) * DS + off) = make_uint4(dc1[0], dc1[1], dc1[2], dc1[3]);
+      }
+      sd0 = quad_sum(sd0); sd1 = quad_sum(sd1);
+      float* mine = sRedB + (warp * 32 + lane) * 10;
+      mine[0] = dA0[0]; mine[1] = dA0[1]; mine[2] = dA0[2]; mine[3] = dA0[3]; mine[4] = dA1[0]; mine[5] = dA1[1]; mine[6] = dA1[2]; mine[7] = dA1[3];
+      mine[8] = sd0; mine[9] = sd1;
+    }
+    __syncthreads();                                     // dctl / probabilities of all tiles staged, partial sums visible
+    // ---- CTA-wide phase: dVM[16, C] += P^T[16, ROWS px] dctl[ROWS px, C]; warp w owns n-tiles {w, w+8, ...}
+    {
+      const int lr = lane & 7, lq = lane >> 3;
+      const int i2 = lq >> 1;
+#pragma unroll
+      for (int ks = 0; ks < TPC; ks++) {
+        if (base + ks * 16 < pend) {                      // CTA-uniform
+          uint32_t af[4];
+          ldsm_x4_t(af, sP + (ks * 16 + (lq >> 1) * 8 + lr) * SPS + (lq & 1) * 8);
+#pragma unroll
+          for (int i = 0; i < NTW; i += 2) {
+            const int nt_l = warp + (i + i2) * 8;
+            uint32_t bf[4];
+            ldsm_x4_t(bf, sD + (long long)(ks * 16 + (lq & 1) * 8 + lr) * DS + nt_l * 8);
+            mma16816<false>(dvm[i], af[0], af[1], af[2], af[3], bf[0], bf[1]);
+            mma16816<false>(dvm[i + 1], af[0], af[1], af[2], af[3], bf[2], bf[3]);
+          }
+        }
+      }
+    }
+    if (active) {
+      float tot[10];
+#pragma unroll
+      for (int i = 0; i < 10; i++) tot[i] = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPT; w++) {
+        const float* o = sRedB + ((tl * WPT + w) * 32 + lane) * 10;
+#pragma unroll
+        for (int i = 0; i < 10; i++) tot[i] += o[i];
+      }
+      // dP = dA * M; dS = P * (dP - sum_t P dP)
+      const float d00 = tot[0] * M[0], d01 = tot[1] * M[1], d02 = tot[2] * M[2], d03 = tot[3] * M[3];
+      const float d10 = tot[4] * M[4], d11 = tot[5] * M[5], d12 = tot[6] * M[6], d13 = tot[7] * M[7];
+      const float ad0 = quad_sum(P[0] * d00 + P[1] * d01 + P[4] * d10 + P[5] * d11);
+      const float ad1 = quad_sum(P[2] * d02 + P[3] * d03 + P[6] * d12 + P[7] * d13);
+      const uint32_t sa0 = pack_bf16(P[0] * (d00 - ad0), P[1] * (d01 - ad0)), sa1 = pack_bf16(P[2] * (d02 - ad1), P[3] * (d03 - ad1));
+      const uint32_t sa2 = pack_bf16(P[4] * (d10 - ad0), P[5] * (d11 - ad0)), sa3 = pack_bf16(P[6] * (d12 - ad1), P[7] * (d13 - ad1));
+      const float k30 = rn0 * rn0 * rn0 * tot[8] / (float)C, k31 = rn1 * rn1 * rn1 * tot[9] / (float)C;
+      // ---- pass C over this warp's channels: dX = dS Kf + rn * dxn - x * k3 ; R[c] += dX * x
+      uint4* o0 = reinterpret_cast<uint4*>(p.dX + ((long long)b * p.HW + q0) * C);
+      uint4* o1 = reinterpret_cast<uint4*>(p.dX + ((long long)b * p.HW + q1) * C);
+#pragma unroll (UJ)
+      for (int jj = 0; jj < JW; jj++) {
+        const int j = j0 + jj;
+        const uint4 a = __ldg(x0 + j * 4 + t), bq = __ldg(x1 + j * 4 + t);
+        const uint4 ga = __ldg(g0 + j * 4 + t), gb = __ldg(g1 + j * 4 + t);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w};
+        const uint32_t gaw[4] = {ga.x, ga.y, ga.z, ga.w}, gbw[4] = {gb.x, gb.y, gb.z, gb.w};
+        const int ch = (j * 4 + t) * 8;
+        const float4 m1a = *reinterpret_cast<const float4*>(sm1 + ch), m1b = *reinterpret_cast<const float4*>(sm1 + ch + 4);
+        const float4 ba = *reinterpret_cast<const float4*>(sb + ch), bb = *reinterpret_cast<const float4*>(sb + ch + 4);
+        const float m1v[8] = {m1a.x, m1a.y, m1a.z, m1a.w, m1b.x, m1b.y, m1b.z, m1b.w};
+        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        uint32_t ow0[4], ow1[4];
+        float rr[8];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          float acc[4] = {m1v[2 * m], m1v[2 * m + 1], m1v[2 * m], m1v[2 * m + 1]};
+          const uint2 vb = sVp[(j * 4 + m) * 32 + lane];
+          mma16816<true>(acc, pa0, pa1, pa2, pa3, vb.x, vb.y);
+          float dx[4] = {0.f, 0.f, 0.f, 0.f};
+          const uint2 kb = sKp[(j * 4 + m) * 32 + lane];
+          mma16816<false>(dx, sa0, sa1, sa2, sa3, kb.x, kb.y);
+          const float2 xa = upk<F16>(aw[m]), xb = upk<F16>(bw[m]);
+          const float2 da = unpack_bf16(gaw[m]), db = unpack_bf16(gbw[m]);
+          const float du0 = da.x * gm0 * ((xa.x * rn0 * acc[0] + nz0 + bv[2 * m]) > 0.f ? 1.f : p.alpha);
+          const float du1 = da.y * gm0 * ((xa.y * rn0 * acc[1] + nz0 + bv[2 * m + 1]) > 0.f ? 1.f : p.alpha);
+          const float du2 = db.x * gm1 * ((xb.x * rn1 * acc[2] + nz1 + bv[2 * m]) > 0.f ? 1.f : p.alpha);
+          const float du3 = db.y * gm1 * ((xb.y * rn1 * acc[3] + nz1 + bv[2 * m + 1]) > 0.f ? 1.f : p.alpha);
+          const float d0 = dx[0] + rn0 * du0 * acc[0] - xa.x * k30, d1 = dx[1] + rn0 * du1 * acc[1] - xa.y * k30;
+          const float d2 = dx[2] + rn1 * du2 * acc[2] - xb.x * k31, d3 = dx[3] + rn1 * du3 * acc[3] - xb.y * k31;
+          ow0[m] = pack_bf16(d0, d1); ow1[m] = pack_bf16(d2, d3);
+          rr[2 * m] = (v0 ? d0 * xa.x : 0.f) + (v1 ? d2 * xb.x : 0.f);
+          rr[2 * m + 1] = (v0 ? d1 * xa.y : 0.f) + (v1 ? d3 * xb.y : 0.f);
+        }
+        if (v0) o0[j * 4 + t] = make_uint4(ow0[0], ow0[1], ow0[2], ow0[3]);
+        if (v1) o1[j * 4 + t] = make_uint4(ow1[0], ow1[1], ow1[2], ow1[3]);
+        float h4[4], h2[2];
+        {
+          const bool up = (g & 4) != 0;
+#pragma unroll
+          for (int e = 0; e < 4; e++) { const float send = up ? rr[e] : rr[e + 4], keep = up ? rr[e + 4] : rr[e]; h4[e] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+        }
+        {
+          const bool up = (g & 2) != 0;
+#pragma unroll
+          for (int e = 0; e < 2; e++) { const float send = up ? h4[e] : h4[e + 2], keep = up ? h4[e + 2] : h4[e]; h2[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+        }
+        {
+          const bool up = (g & 1) != 0;
+          const float send = up ? h2[0] : h2[1], keep = up ? h2[1] : h2[0];
+          atomicAdd(&sR[ch + g], keep + __shfl_xor_sync(0xffffffffu, send, 4));
+        }
+      }
+    }
+    __syncthreads();                                     // staging buffers and partial sums are rewritten by the next round
+  }
+#pragma unroll
+  for (int i = 0; i < NTW; i++) {
+    const int nt = warp + i * 8;
+    float* d = p.dVM + (long long)b * NT * C + nt * 8 + 2 * t;
+    atomicAdd(d + g * C, dvm[i][0]); atomicAdd(d + g * C + 1, dvm[i][1]);
+    atomicAdd(d + (g + 8) * C, dvm[i][2]); atomicAdd(d + (g + 8) * C + 1, dvm[i][3]);
+  }
+  __syncthreads();
+  if (p.R) for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&p.R[(long long)b * C + i], sR[i]);
+}
+
+template <bool F16, int WPT>
+int launch_bwd_split(const AttnMP& p, dim3 grid, cudaStream_t st) {
+  const int smem = bwd_split_smem<16, WPT>(p.C);
+  static bool done = false;
+  if (!done) { cudaFuncSetAttribute(attn_bwd_split_kernel<F16, 16, WPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); done = true; }
+  attn_bwd_split_kernel<F16, 16, WPT><<<grid, 256, smem, st>>>(p);
+  return 0;
+}
+
 template <bool F16>
 int launch_fwd(const AttnMP& p, dim3 grid, int smem, cudaStream_t st) {
   switch (p.C / 32) {
@@ -572,6 +879,8 @@ int pix_per_cta(long long HW, int B, int ctas_per_sm) {
   if (ppc < 128) ppc = HW < 128 ? (HW + 15) / 16 * 16 : 128;
   return (int)ppc;
 }
+
+bool g_attn_split = true;     // split-channel backward kernel for the low-resolution layers (A/B switch: mgf_attn_set_split)
 
 int check_c(int C, const char* who) {
   const int n = C / 32;
@@ -611,6 +920,21 @@ extern "C" int mgf_attn_bwd(const void* X, const void* dz, const float* Kf, cons
   if (int e = check_c(C, "attn_bwd")) return e;
   AttnMP p{}; p.X = X; p.dz = (const __nv_bfloat16*)dz; p.Kf = Kf; p.Sc = Sc; p.mb = maskbias; p.VM = VM; p.bm = bm;
   p.noise = noise; p.nstr = nstr; p.bias = bias; p.gain = gain; p.alpha = alpha; p.dX = (__nv_bfloat16*)dX; p.dVM = dVM; p.R = R; p.dmask = dmask; p.tabK = tabK; p.tabV = tabV; p.HW = HW; p.C = C; p.nbs = noise_bstride;
+  // low-resolution 512-channel layers: several warps per pixel tile (attn_bwd_split_kernel) while the tiles of the launch do not fill the SMs
+  if (C == 512 && g_attn_split) {
+    const long long tiles = (HW + 15) / 16 * B;
+    const int wpt = tiles <= num_sms() ? 8 : (tiles / 2 <= num_sms() ? 4 : (tiles / 4 <= num_sms() ? 2 : 0));
+    if (wpt) {
+      p.pix_per_cta = (8 / wpt) * 16;
+      dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
+      const bool f16 = fwd_f16();
+      if (wpt == 8) { if (f16) launch_bwd_split<true, 8>(p, grid, (cudaStream_t)stream); else launch_bwd_split<false, 8>(p, grid, (cudaStream_t)stream); }
+      else if (wpt == 4) { if (f16) launch_bwd_split<true, 4>(p, grid, (cudaStream_t)stream); else launch_bwd_split<false, 4>(p, grid, (cudaStream_t)stream); }
+      else { if (f16) launch_bwd_split<true, 2>(p, grid, (cudaStream_t)stream); else launch_bwd_split<false, 2>(p, grid, (cudaStream_t)stream); }
+      MGF_CHECK_LAUNCH("attn_bwd(split)");
+      return 0;
+    }
+  }
   p.pix_per_cta = pix_per_cta(HW, B, C <= 256 ? 2 : 1);      // one wave: two CTAs per SM up to 256 channels, one above
   dim3 grid((unsigned)((HW + p.pix_per_cta - 1) / p.pix_per_cta), B);
   const int rc = fwd_f16() ? launch_bwd<true>(p, grid, bwd_smem(C), (cudaStream_t)stream) : launch_bwd<false>(p, grid, bwd_smem(C), (cudaStream_t)stream);
@@ -635,3 +959,6 @@ extern "C" int mgf_attn_tables(const float* Kf, const float* VM, void* tabK, voi
   MGF_CHECK_LAUNCH("attn_tables");
   return 0;
 }
+
+/* A/B switch: 0 keeps the one-warp-per-tile backward kernel for every layer */
+extern "C" int mgf_attn_set_split(int enabled) { mgf::g_attn_split = enabled != 0; return 0; }

@@ -16,7 +16,9 @@ for (B, HW, C) in [(8, 16384, 256), (8, 4096, 512), (8, 1024, 512), (8, 256, 512
     _lib.check(L.mgf_attn_tables(p(Kf), p(VM), p(tabK), p(tabV), B, C, s))
     def fwd(): _lib.check(L.mgf_attn_fwd(p(X), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(out), None, None, p(tabK), p(tabV), B, HW, C, 0, s))
     def bwd(): _lib.check(L.mgf_attn_bwd(p(X), p(dz), p(Kf), p(Sc), p(mb), p(VM), p(bm), p(noise), p(ns), p(bias), 1.4, 0.2, p(dX), p(dVM), p(R), None, p(tabK), p(tabV), B, HW, C, 0, s))
-    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+    def bwd1():
+        L.mgf_attn_set_split(0); bwd(); L.mgf_attn_set_split(1)
+    for name, fn in (("fwd", fwd), ("bwd", bwd), ("bwd(one warp per tile)", bwd1)):
         ts = []
         for i in range(7):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -26,7 +26,10 @@ def _p(t):
 
 @pytest.mark.parametrize("fwd", ["fp16", "bf16"])
 @pytest.mark.parametrize("dropout,tables", [(False, False), (True, False), (False, True), (True, True)])
-@pytest.mark.parametrize("B,HW,C", [(2, 16, 32), (2, 100, 64), (3, 1032, 128), (2, 4096, 256), (1, 500, 384), (2, 1000, 512), (8, 16, 512)])
+# the 512-channel cases below 148 * 4 pixel tiles take the split-channel backward kernel: 8 warps per tile (2 x 1000 ragged, 8 x 16),
+# 4 (8 x 512), 2 (8 x 1024, 8 x 1000 ragged); 2 x 4096 x 512 stays on the one-warp-per-tile kernel
+@pytest.mark.parametrize("B,HW,C", [(2, 16, 32), (2, 100, 64), (3, 1032, 128), (2, 4096, 256), (1, 500, 384), (2, 1000, 512), (8, 16, 512),
+                                    (8, 512, 512), (8, 1024, 512), (8, 1000, 512), (2, 4096, 512)])
 def test_attn_fwd_bwd_vs_torch(B, HW, C, fwd, dropout, tables):
     L = _lib.lib()
     _lib.set_forward_dtype(fwd)
@@ -122,3 +125,29 @@ def test_attn_kernel_vs_oracle_transformer_layer(res, C, B):
     scale = ref.detach().abs().max().item()
     assert (out.float().cpu() - ref.detach()).abs().max().item() < 4 * 2.0 ** -10 * scale
     assert ((dX.float().cpu() - gX).norm() / gX.norm()).item() < 1.5e-2
+
+
+@pytest.mark.parametrize("B,HW", [(8, 16), (8, 256), (8, 512), (8, 1024)])
+def test_attn_bwd_split_kernel_equals_one_warp_per_tile_kernel(B, HW):
+    """The split-channel backward kernel (several warps per pixel tile, partial sums exchanged through shared memory) against the
+    one-warp-per-tile kernel on the same inputs: same arithmetic up to the order of the partial sums."""
+    L = _lib.lib()
+    C = 512
+    g = torch.Generator(device="cuda").manual_seed(HW)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    X16 = (r(B, HW, C) * 1.5).to(_lib.forward_torch_dtype())
+    Kf, Sc, mb = r(16, C) * (2.0 / C ** 0.5), r(HW, 16), r(B, 16) * 0.3
+    VM, bm, noise, ns, bias = r(B, 16, C) * 0.3, r(C) * 0.1, r(HW), torch.tensor([0.2], device="cuda"), r(C) * 0.1
+    dz16 = r(B, HW, C).to(torch.bfloat16)
+    s = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for split in (1, 0):
+        L.mgf_attn_set_split(split)
+        dX = torch.empty(B, HW, C, device="cuda", dtype=torch.bfloat16); dVM = torch.zeros(B, 16, C, device="cuda"); R = torch.zeros(B, C, device="cuda")
+        _lib.check(L.mgf_attn_bwd(_p(X16), _p(dz16), _p(Kf), _p(Sc), _p(mb), _p(VM), _p(bm), _p(noise), _p(ns), _p(bias), 1.4142135, 0.2, _p(dX), _p(dVM), _p(R),
+                                  None, None, None, B, HW, C, 0, s), "bwd")
+        torch.cuda.synchronize()
+        outs.append((dX.float(), dVM, R))
+    L.mgf_attn_set_split(1)
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    assert rel(outs[0][0], outs[1][0]) < 4e-3 and rel(outs[0][1], outs[1][1]) < 2e-3 and rel(outs[0][2], outs[1][2]) < 2e-3
