@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) lpips_head_kernel(const __nv_bfloat16* __
 // pixels of every 2x2 window AND y = max over the window, in one pass over f (the separate head + pool kernels read f twice).
 // Same lane-group-per-window layout as the backward kernel below.
 template <int VPL, bool f16>
-__global__ void __launch_bounds__(256, VPL == 1 ? 3 : 1) lpips_tap_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1, const float* __restrict__ lin,
+__global__ void __launch_bounds__(256, VPL == 1 ? 3 : 2) lpips_tap_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ n1, const float* __restrict__ lin,
                                                                  __nv_bfloat16* __restrict__ y, float* val, float2* __restrict__ stats, int H, int W, int C) {
   // stats (optional) [B,H,W] = (|f|, g . f) per pixel with g = 2 lin (f inv - n1): the two channel reductions the backward kernel needs; they cost
   // this pass one FFMA per element and 8 bytes per pixel, and take the whole first pass (3 FMAs per element + shuffles) out of the backward kernel
@@ -571,7 +571,11 @@ extern "C" int mgf_lpips_tap_pool_fwd(const void* x, const void* n1, const float
   if (!(C == 64 || C == 128 || C == 256 || C == 512) || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "lpips_tap_pool_fwd: C in {64,128,256,512}, even H/W");
   const int vpl = C == 512 ? 2 : 1, lpp = (C / 8) / vpl, wpw = 32 / lpp;
   const long long nwin = (long long)(H / 2) * (W / 2);
-  long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
+  // about two waves of resident CTAs over all images (3 or 2 CTAs per SM): every warp then walks several windows, so the per-warp set-up (the
+  // lin weights) and the per-CTA reduction are amortised on the small taps too (relu3_3 / relu4_3 ran 1-2 windows per warp)
+  long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw);
+  long long cap = ((long long)num_sms() * (vpl == 1 ? 6 : 4) + B - 1) / B; if (cap < 1) cap = 1;
+  if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define MGF_TPF(V, F) lpips_tap_pool_fwd_kernel<V, F><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, (__nv_bfloat16*)y, val, (float2*)stats, H, W, C)
