@@ -591,7 +591,10 @@ extern "C" int mgf_lpips_tap_pool_bwd(const void* x, const void* n1, const float
   if (!(C == 64 || C == 128 || C == 256 || C == 512) || H % 2 || W % 2) MGF_FAIL(MGF_E_SHAPE, "lpips_tap_pool_bwd: C in {64,128,256,512}, even H/W");
   const int vpl = C == 512 ? 2 : 1, lpp = (C / 8) / vpl, wpw = 32 / lpp;
   const long long nwin = (long long)(H / 2) * (W / 2);
-  long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw); const long long cap = (long long)num_sms() * 8; if (blocks > cap) blocks = cap;
+  long long blocks = (nwin + 8 * wpw - 1) / (8 * wpw);
+  long long cap = (long long)num_sms() * 8;
+  if (vpl == 2) { cap = ((long long)num_sms() * 4 + B - 1) / B; if (cap < 1) cap = 1; }      // 512-channel tap: two resident CTAs per SM, about two waves
+  if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define MGF_TPB(V, F) do { if (stats) lpips_tap_pool_bwd_kernel<V, F, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)n1, lin, coef, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, (const float2*)stats, H, W, C); \

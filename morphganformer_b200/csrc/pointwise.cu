@@ -34,9 +34,19 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const uint16_t* __restri
   constexpr int K = 32 * K32;
   const int KS = wrow(K);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  for (int i = threadIdx.x; i < N * (K / 8); i += blockDim.x) {
-    const int n = i / (K / 8), v = i - n * (K / 8);
-    *reinterpret_cast<uint4*>(sW + n * KS + v * 8) = __ldg(reinterpret_cast<const uint4*>(W + (long long)n * K) + v);
+  // weight staging, eight 16-byte loads in flight per thread (a one-load-per-trip loop cost 16 dependent L2 round trips at K = 256, N = 128)
+  {
+    const int nvec = N * (K / 8);
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += 8 * blockDim.x) {
+      uint4 w[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int i = i0 + u * blockDim.x; if (i < nvec) w[u] = __ldg(reinterpret_cast<const uint4*>(W) + i); }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + u * blockDim.x;
+        if (i < nvec) { const int n = i / (K / 8), v = i - n * (K / 8); *reinterpret_cast<uint4*>(sW + n * KS + v * 8) = w[u]; }
+      }
+    }
   }
   __syncthreads();
   float mx = 0.f;
