@@ -490,6 +490,15 @@ def run_native(args):
         # DRAM bytes are not measurable from inside the process (no CUPTI metrics without a profiler): null here; the per-launch
         # dram__bytes_read/write of the same command are in the committed ncu tables (profiles/r02_*.md)
         traffic, traffic_src = None, "ncu tables under profiles/ (not measurable in-process)"
+        # ... except when the committed ncu capture of this very launch list (scripts/ncu_capture_r02e.sh -> summarize_traffic.py) still
+        # describes the build: same number of conv launches per step.  Then `traffic` = DRAM bytes read + written by the conv launches
+        # of ONE step (sum over the launches `achieved` is computed over), taken under ncu, not in this run.
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02e_conv_dram_traffic.json")))
+            if int(tj["conv_launches_per_step"]) == len(recs) // 2 and B == 8 and R == 1024 and use_lpips:
+                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes of one step)", "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk_src + " bf16_tflops_sustained",
                 "executed_tflops": exe / (tms / 1000.0) / 1e12, "launches_per_step": len(recs) // 2, "kernel_ms_per_step": tms / 2,

@@ -10,7 +10,10 @@ def run(name, fn, nbytes):
     ts = []
     for i in range(7):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        e0.record(); rc = fn(); e1.record(); torch.cuda.synchronize()
+        if rc:
+            print("%-34s FAILED rc=%d %s" % (name, rc, L.mgf_last_error()), flush=True)
+            return
         if i >= 2: ts.append(e0.elapsed_time(e1))
     print("%-34s %.3f ms  %6.0f GB/s" % (name, min(ts), nbytes / min(ts) / 1e6), flush=True)
 B = 8
@@ -46,3 +49,24 @@ wc = torch.randn(64, 32, device="cuda") * 0.1; b64 = torch.zeros(64, device="cud
 run("vgg_conv1_fwd 1024 (+mse)", lambda: L.mgf_vgg_conv1_fwd(p(img), p(tgt), p(mse), p(wc), p(b64), p(h0), B, R_, s), img.numel() * 8 + h0.numel() * 2)
 run("vgg_conv1_fwd 1024 (no mse)", lambda: L.mgf_vgg_conv1_fwd(p(img), None, None, p(wc), p(b64), p(h0), B, R_, s), img.numel() * 4 + h0.numel() * 2)
 run("vgg_conv1_bwd 1024 (+mse grad)", lambda: L.mgf_vgg_conv1_bwd(p(h0), p(wc), p(img), p(tgt), 0.1, p(dimg), B, R_, s), img.numel() * 12 + h0.numel() * 2)
+
+# LPIPS tap + 2x2 max-pool forward, then the backward fed with the forward's per-pixel reductions (as lpips_engine.py runs them):
+# forward bytes = x + n1 read, pooled y written (2.25 x tensor bytes) + 8 B / pixel of stats; backward = x, n1, dx + dy/4 + stats (3.25 x)
+for (H, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
+    f = bf(B, H, H, C).abs().to(torch.float16).view(torch.bfloat16); n1 = (bf(B, H, H, C).abs() * 0.1).to(torch.float16).view(torch.bfloat16)
+    lin = torch.rand(C, device="cuda"); val = torch.zeros(B, device="cuda"); coef = torch.full((B,), 0.5, device="cuda")
+    y = torch.empty(B, H // 2, H // 2, C, dtype=torch.bfloat16, device="cuda"); stats = torch.empty(B, H, H, 2, device="cuda")
+    dy = bf(B, H // 2, H // 2, C); dx = torch.empty(B, H, H, C, dtype=torch.bfloat16, device="cuda"); n = f.numel() * 2
+    run("lpips_tap_pool_fwd %dx%d C%d" % (H, H, C), lambda: L.mgf_lpips_tap_pool_fwd(p(f), p(n1), p(lin), p(y), p(val), p(stats), B, H, H, C, s), 2.25 * n + stats.numel() * 4)
+    run("lpips_tap_pool_bwd+stats %dx%d C%d" % (H, H, C), lambda: L.mgf_lpips_tap_pool_bwd(p(f), p(n1), p(lin), p(coef), p(dy), p(dx), p(stats), B, H, H, C, s), 3.25 * n + stats.numel() * 4)
+# first stage of the up-convolution input gradient: dy [B,H,W,C] -> g [B,H+2,W+2,C] (bf16), bytes = both tensors once
+fk = (ctypes.c_float * 4)(0.125, 0.375, 0.375, 0.125)
+for (H, C) in [(1024, 32), (512, 64), (256, 128), (128, 256)]:
+    dy = bf(B, H, H, C); gq = torch.empty(B, H + 2, H + 2, C, dtype=torch.bfloat16, device="cuda")
+    run("fir4_pad %dx%d C%d" % (H, H, C), lambda: L.mgf_fir4_pad(p(dy), p(gq), fk, 4.0, B, H, H, C, s), dy.numel() * 2 + gq.numel() * 2)
+# resnet-skip 1x1 convolution (pointwise.cu) and its input gradient: bytes = input + output
+for (H, K, N) in [(512, 64, 32), (256, 128, 64), (128, 256, 128)]:
+    x = bf(B, H, H, K); w = bf(N, K) * 0.1; o = torch.empty(B, H, H, N, dtype=torch.bfloat16, device="cuda")
+    run("pointwise fwd %dx%d %d->%d" % (H, H, K, N), lambda: L.mgf_pointwise(p(x), p(w), p(o), B * H * H, K, N, 0, s), x.numel() * 2 + o.numel() * 2)
+    wt = bf(K, N) * 0.1
+    run("pointwise dgrad %dx%d %d->%d" % (H, H, N, K), lambda: L.mgf_pointwise(p(o), p(wt), p(x), B * H * H, N, K, 0, s), x.numel() * 2 + o.numel() * 2)
