@@ -14,6 +14,7 @@ python bench.py --steps 100 --warmup 5 --no-aux --no-cpu-baseline > $OUT/bench_s
 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-aux --no-graph > $OUT/ncu_bench_plain_$TAG.json 2>/dev/null || exit 1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --print-units base --clock-control none --csv \
     --log-file $OUT/traffic_$TAG.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-aux --no-graph > $OUT/ncu_traffic_$TAG.log 2>&1
+python bench.py --workload pairs > $OUT/pairs_n1_$TAG.json 2>/dev/null
 python scripts/bench_membound.py > $OUT/membound_$TAG.txt 2>&1
 timeout 120 python scripts/bench_attn.py > $OUT/attn_$TAG.txt 2>&1
 ls -l $OUT/*$TAG*
