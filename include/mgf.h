@@ -180,6 +180,11 @@ int mgf_upfir2_add(const void* v, const void* add, void* out, const float* fk4, 
 int mgf_pointwise(const void* x, const void* w, void* out, int64_t P, int K, int N, int is_fwd, void* stream);
 int mgf_pointwise_supported(int K, int N);
 int mgf_upfir2_bwd(const void* dout, void* dv, const float* fk4, float gain, int B, int h, int w, int C, void* stream);
+/* A/B switch of the three FIR walkers above: bit 0 mgf_fir4 / mgf_fir4_pad, bit 1 mgf_upfir2_add, bit 2 mgf_upfir2_bwd run with 4 channels per thread
+ * instead of 8 (half the registers per thread, twice the resident warps; identical results).  Default 2 (upfir2_add only: the one that gains).
+ * Process-wide, not thread-safe: set once at start-up. */
+int mgf_fir_set_mode(int bits);
+int mgf_fir_get_mode(void);
 
 /* ---- fused duplex attention layer (attention.cu): TransformerLayer.forward (networks.py:748-822, default GANformer config)
  * + noise + bias_act tail (:1036-1040) in one pass over X [B,HW,C] bf16; Kf [16,C], Sc [HW,16], maskbias [B,16], VM [B,16,C],

@@ -45,6 +45,8 @@ SIGNATURES = {
     "mgf_pointwise": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "mgf_pointwise_supported": (c_int, [c_int, c_int]),
     "mgf_upfir2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "mgf_fir_set_mode": (c_int, [c_int]),
+    "mgf_fir_get_mode": (c_int, []),
     "mgf_attn_fwd": (c_int, [c_void_p] * 9 + [c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
     "mgf_attn_bwd": (c_int, [c_void_p] * 10 + [c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
     "mgf_attn_table_bytes": (c_int64, [c_int, c_int]),

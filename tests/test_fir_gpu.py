@@ -15,6 +15,18 @@ pytestmark = pytest.mark.gpu
 FK = (ctypes.c_float * 4)(0.125, 0.375, 0.375, 0.125)
 
 
+@pytest.fixture(autouse=True, params=[0, 7], ids=["vec8", "vec4"])
+def fir_mode(request):
+    """Every test of this file runs with both forms of the FIR walkers: 8 channels per thread and 4 channels per thread
+    (`mgf_fir_set_mode` bits 0-2: fir4 / upfir2_add / upfir2_bwd); the library default is restored afterwards."""
+    from morphganformer_b200 import _lib
+    L = _lib.lib()
+    old = L.mgf_fir_get_mode()
+    L.mgf_fir_set_mode(request.param)
+    yield request.param
+    L.mgf_fir_set_mode(old)
+
+
 def _setup(fwd):
     from morphganformer_b200 import _lib
     _lib.set_forward_dtype(fwd)
