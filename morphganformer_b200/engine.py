@@ -749,8 +749,8 @@ class _SynthesisFn(torch.autograd.Function):
 
 
 def smoke():
-    """tiny tc-engine forward+backward on cuda:0 (called from __graft_entry__.smoke): fp16-forward mode, seeded, image within 1e-2 of the
-    exact-fp32 ops engine's image range."""
+    """tiny tc-engine forward+backward on cuda:0 (called from __graft_entry__.smoke): fp16-forward mode, seeded, image within 1e-2 max-abs
+    (absolute, the north_star bar; measured 8.35e-3 with ws drawn directly, image range 4.1) of the exact-fp32 ops engine."""
     import os, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "tests"))
@@ -769,5 +769,5 @@ def smoke():
     G.synthesis.engine = "ops"
     ref, _ = G.synthesis(ws.detach(), pos=G.pos, mask=mask, noise_mode="const", return_att_maps=False)
     err, rng = (img.detach() - ref).abs().max().item(), max(1.0, ref.abs().max().item())
-    assert err < 2e-2, "tc engine deviates from the ops engine: %g of range %g" % (err, rng)
+    assert err < 1e-2, "tc engine deviates from the ops engine: %g max-abs (range %g)" % (err, rng)
     print("smoke ok: tc engine 64x64 fwd+bwd, max|img_tc - img_fp32| = %.3g (range %.3g), |dws| = %.3g" % (err, rng, ws.grad.abs().max().item()))
