@@ -399,7 +399,8 @@ def run_native(args):
     target_host = torch.tanh(torch.randn(B, 3, R, R, generator=gen)).pin_memory()
     noise_host = torch.randn(W + 2 * K + 8, B, 17, 32, generator=gen).pin_memory()
     step_noise = torch.zeros(total_steps, B, 17, 32)
-    step_noise[:noise_host.shape[0]] = noise_host
+    n_rows = min(noise_host.shape[0], total_steps)       # e2e re-uploads its own rows; the device-resident run reads the first W + K
+    step_noise[:n_rows] = noise_host[:n_rows]
     P = Projector(G, lsd, B, total_steps, latent_mean=mean, latent_std=std, use_lpips=use_lpips, step_noise=step_noise)
     P.set_targets(target_host.to(dev))
     if not args.no_graph:
