@@ -66,6 +66,9 @@ class Projector:
         if step_noise is None:
             g = torch.Generator(device=self.dev).manual_seed(noise_seed)
             step_noise = torch.randn(steps, batch, k, zd, generator=g, device=self.dev)
+        if step_noise.dim() != 4 or step_noise.shape[0] < steps or tuple(step_noise.shape[1:]) != (batch, k, zd):
+            raise ValueError("step_noise must be [>= steps, batch, k, z_dim] = [>= %d, %d, %d, %d] (the Adam kernel indexes it by the device step counter), got %s"
+                             % (steps, batch, k, zd, tuple(step_noise.shape)))
         self.step_noise = step_noise.to(self.dev, torch.float32).contiguous()
         self.lp = LpipsEngine(lpips_state_dict, self.dev) if (use_lpips and engine == "tc") else None
         self.lp32 = None
